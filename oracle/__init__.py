@@ -1,0 +1,430 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/libmcmc_oracle.so``, the CPU restatement of the reference's sampler hot path
+(see ``oracle/mcmc_oracle.c`` for the reference file:line each function follows).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this package,
+and only as the checker / reported baseline.  The product package ``mini_mcmc_b200`` never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmcmc_oracle.so")
+
+# target kinds (shared numbering with include/minimcmc.h)
+T_GAUSSIAN2D, T_ISO_GAUSSIAN, T_POISSON, T_ROSENBROCK_ND = 1, 2, 3, 4
+T_ROSENBROCK_2D, T_DIFF_GAUSSIAN2D, T_DENSE_GAUSSIAN, T_STD_NORMAL = 5, 6, 7, 8
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (building the checker is not using it)."""
+    srcs = [os.path.join(_HERE, f) for f in ("mcmc_oracle.c", "nuts_impl.inc", "orc_rng.h", "orc_targets.h")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_gaussian2d_logp_kat.restype = C.c_double
+        _lib.orc_iso_unnorm_logp_kat.restype = C.c_double
+        _lib.orc_iso_proposal_logp_kat.restype = C.c_double
+        _lib.orc_poisson_logp_kat.restype = C.c_double
+        _lib.orc_ln_factorial_kat.restype = C.c_double
+        _lib.orc_nonneg_logq_kat.restype = C.c_double
+        _lib.orc_target_logp_grad.restype = C.c_float
+        _lib.orc_nuts_find_reasonable_epsilon.restype = C.c_double
+        _lib.orc_init_tables()
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+# ------------------------------------------------------------------ RNG
+class SmallRng:
+    """rand 0.9 SmallRng (xoshiro256++) with the rand / rand_distr sampling routines the reference uses."""
+
+    def __init__(self, seed: int):
+        self.state = np.zeros(4, dtype=np.uint64)
+        lib().orc_smallrng_seed_state(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _p(self.state, C.c_uint64))
+
+    def _fill(self, kind, n):
+        out = np.empty(n, dtype=np.float64)
+        lib().orc_smallrng_fill(_p(self.state, C.c_uint64), kind, _p(out, C.c_double), None, C.c_int64(n))
+        return out
+
+    def next_u64(self, n=1):
+        out = np.empty(n, dtype=np.uint64)
+        lib().orc_smallrng_fill(_p(self.state, C.c_uint64), 0, None, _p(out, C.c_uint64), C.c_int64(n))
+        return out
+
+    def f64(self, n):
+        return self._fill(1, n)
+
+    def f32(self, n):
+        return self._fill(2, n).astype(np.float32)
+
+    def normal(self, n):
+        return self._fill(3, n)
+
+    def exp1(self, n):
+        return self._fill(4, n)
+
+    def bool_half(self, n):
+        return self._fill(5, n).astype(np.uint8)
+
+    def open01(self, n):
+        return self._fill(6, n)
+
+
+def philox4x32_10(key, ctr):
+    k = np.asarray(key, dtype=np.uint32)
+    c = np.asarray(ctr, dtype=np.uint32)
+    out = np.empty(4, dtype=np.uint32)
+    lib().orc_philox(_p(k, C.c_uint32), _p(c, C.c_uint32), _p(out, C.c_uint32))
+    return out
+
+
+def init_positions(n, d, seed):
+    """core.rs _init: [n, d] StandardNormal f64 from SmallRng(seed)."""
+    out = np.empty((n, d), dtype=np.float64)
+    lib().orc_init_positions(_p(out, C.c_double), C.c_int64(n), C.c_int64(d), C.c_uint64(seed))
+    return out
+
+
+def init_det(n, d):
+    return init_positions(n, d, 42)
+
+
+# ------------------------------------------------------------------ targets
+class Target:
+    def __init__(self, kind, dim, params=(), vec=None, mat=None):
+        self.kind, self.dim = kind, dim
+        self.params = _f64(np.asarray(params, dtype=np.float64).reshape(-1)) if len(params) else np.zeros(1)
+        self.n_params = len(params)
+        self.vec = _f32(vec) if vec is not None else None
+        self.mat = _f32(mat) if mat is not None else None
+
+    def args(self):
+        return (self.kind, self.dim, _p(self.params, C.c_double), self.n_params, _p(self.vec, C.c_float),
+                _p(self.mat, C.c_float))
+
+
+def rosenbrock_nd(dim):
+    return Target(T_ROSENBROCK_ND, dim)
+
+
+def rosenbrock_2d(a, b):
+    return Target(T_ROSENBROCK_2D, 2, (a, b))
+
+
+def diff_gaussian2d(mean, cov):
+    cov = np.asarray(cov, dtype=np.float64)
+    return Target(T_DIFF_GAUSSIAN2D, 2, (mean[0], mean[1], cov[0, 0], cov[0, 1], cov[1, 0], cov[1, 1]))
+
+
+def std_normal(dim):
+    return Target(T_STD_NORMAL, dim)
+
+
+def dense_gaussian(mean, prec, norm_const=0.0):
+    mean = _f32(mean)
+    return Target(T_DENSE_GAUSSIAN, mean.shape[0], (norm_const,), vec=mean, mat=_f32(prec))
+
+
+def logp_grad(target: Target, x):
+    x = _f32(x)
+    g = np.empty(target.dim, dtype=np.float32)
+    lp = lib().orc_target_logp_grad(*target.args(), _p(x, C.c_float), _p(g, C.c_float))
+    return float(lp), g
+
+
+def gaussian2d_logp(mean, cov, x, normalized=False):
+    cov = np.asarray(cov, dtype=np.float64)
+    p6 = _f64([mean[0], mean[1], cov[0, 0], cov[0, 1], cov[1, 0], cov[1, 1]])
+    xx = _f64(x)
+    return float(lib().orc_gaussian2d_logp_kat(_p(p6, C.c_double), _p(xx, C.c_double), int(normalized)))
+
+
+def iso_unnorm_logp(std, x):
+    xx = _f64(x)
+    return float(lib().orc_iso_unnorm_logp_kat(C.c_double(std), _p(xx, C.c_double), len(xx)))
+
+
+def iso_proposal_logp(std, frm, to):
+    a, b = _f64(frm), _f64(to)
+    return float(lib().orc_iso_proposal_logp_kat(C.c_double(std), _p(a, C.c_double), _p(b, C.c_double), len(a)))
+
+
+def poisson_logp(lam, k):
+    return float(lib().orc_poisson_logp_kat(C.c_double(lam), C.c_uint64(k)))
+
+
+def ln_factorial(k):
+    return float(lib().orc_ln_factorial_kat(C.c_uint64(k)))
+
+
+def nonneg_logq(x, y):
+    return float(lib().orc_nonneg_logq_kat(C.c_uint64(x), C.c_uint64(y)))
+
+
+# ------------------------------------------------------------------ MH
+def mh_cont_run_replay(kind, tparams, prop_std, state, n_collect, n_discard, noise, u, want_trace=False):
+    """state [chains, D] f64 (copied); noise [chains, steps, D]; u [chains, steps].
+    Returns (out [chains, n_collect, D], final_state, trace or None)."""
+    state = _f64(state).copy()
+    chains, D = state.shape
+    steps = n_collect + n_discard
+    noise, u = _f64(noise), _f64(u)
+    assert noise.shape == (chains, steps, D) and u.shape == (chains, steps)
+    tp = _f64(tparams)
+    out = np.empty((chains, n_collect, D), dtype=np.float64)
+    trace = np.empty((chains, steps, 4), dtype=np.float64) if want_trace else None
+    rc = lib().orc_mh_cont_run_replay(kind, _p(tp, C.c_double), C.c_double(prop_std), _p(state, C.c_double),
+                                      C.c_int64(chains), D, C.c_int64(n_collect), C.c_int64(n_discard),
+                                      _p(noise, C.c_double), _p(u, C.c_double), _p(out, C.c_double),
+                                      _p(trace, C.c_double))
+    assert rc == 0
+    return out, state, trace
+
+
+def mh_cont_reference_tape(chain_seed, prop_seed, chains, steps, D):
+    noise = np.empty((chains, steps, D), dtype=np.float64)
+    u = np.empty((chains, steps), dtype=np.float64)
+    lib().orc_mh_cont_reference_tape(C.c_uint64(chain_seed), C.c_uint64(prop_seed), C.c_int64(chains),
+                                     C.c_int64(steps), D, _p(noise, C.c_double), _p(u, C.c_double))
+    return noise, u
+
+
+def mh_poisson_run_replay(lam, state, n_collect, n_discard, flip, u):
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    chains = state.shape[0]
+    flip = np.ascontiguousarray(flip, dtype=np.uint8)
+    u = _f64(u)
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_poisson_run_replay(C.c_double(lam), _p(state, C.c_uint64), C.c_int64(chains), C.c_int64(n_collect),
+                                    C.c_int64(n_discard), _p(flip, C.c_uint8), _p(u, C.c_double),
+                                    _p(out, C.c_uint64))
+    return out, state
+
+
+def mh_poisson_run_philox(lam, state, n_collect, n_discard, seed, chain_offset=0, step_base=0):
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    chains = state.shape[0]
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_poisson_run_philox(C.c_double(lam), _p(state, C.c_uint64), C.c_int64(chains),
+                                    C.c_int64(chain_offset), C.c_int64(step_base), C.c_int64(n_collect),
+                                    C.c_int64(n_discard), C.c_uint64(seed), _p(out, C.c_uint64))
+    return out, state
+
+
+def mh_poisson_run_reference(lam, state, n_collect, n_discard, seed, flip_seed=12345, out=None):
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    chains = state.shape[0]
+    if out is None:
+        out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_poisson_run_reference(C.c_double(lam), _p(state, C.c_uint64), C.c_int64(chains),
+                                       C.c_int64(n_collect), C.c_int64(n_discard), C.c_uint64(seed),
+                                       C.c_uint64(flip_seed), _p(out, C.c_uint64))
+    return out, state
+
+
+# ------------------------------------------------------------------ HMC
+def hmc_run_replay(target: Target, positions, step_size, n_leapfrog, n_collect, n_discard, momenta, u,
+                   want_trace=False):
+    """positions [chains, D] f32 (copied); momenta [steps, chains, D]; u [steps, chains].
+    Returns (out [chains, n_collect, D], final positions, trace [steps, chains, 4] or None)."""
+    pos = _f32(positions).copy()
+    chains, D = pos.shape
+    steps = n_collect + n_discard
+    momenta, u = _f32(momenta), _f32(u)
+    assert momenta.shape == (steps, chains, D) and u.shape == (steps, chains)
+    out = np.empty((chains, n_collect, D), dtype=np.float32)
+    trace = np.empty((steps, chains, 4), dtype=np.float32) if want_trace else None
+    rc = lib().orc_hmc_run_replay(*target.args(), _p(pos, C.c_float), C.c_int64(chains), C.c_double(step_size),
+                                  int(n_leapfrog), C.c_int64(n_collect), C.c_int64(n_discard),
+                                  _p(momenta, C.c_float), _p(u, C.c_float), _p(out, C.c_float),
+                                  _p(trace, C.c_float))
+    assert rc == 0
+    return out, pos, trace
+
+
+def hmc_run_reference(target: Target, positions, step_size, n_leapfrog, n_collect, n_discard, seed, want_out=True):
+    pos = _f32(positions).copy()
+    chains, D = pos.shape
+    out = np.empty((chains, n_collect, D), dtype=np.float32) if want_out else None
+    rc = lib().orc_hmc_run_reference(*target.args(), _p(pos, C.c_float), C.c_int64(chains), C.c_double(step_size),
+                                     int(n_leapfrog), C.c_int64(n_collect), C.c_int64(n_discard), C.c_uint64(seed),
+                                     _p(out, C.c_float))
+    assert rc == 0
+    return out, pos
+
+
+# ------------------------------------------------------------------ NUTS
+def nuts_find_reasonable_epsilon(target: Target, x, p, scalar_f32=False):
+    x, p = _f32(x), _f32(p)
+    return float(lib().orc_nuts_find_reasonable_epsilon(*target.args(), _p(x, C.c_float), _p(p, C.c_float),
+                                                        int(scalar_f32)))
+
+
+def nuts_build_tree(target: Target, x, p, g, logu, v, j, epsilon, joint_0, rng_seed):
+    x, p, g = _f32(x), _f32(p), _f32(g)
+    D = target.dim
+    vec = np.empty((8, D), dtype=np.float32)
+    scal = np.empty(5, dtype=np.float64)
+    lib().orc_nuts_build_tree(*target.args(), _p(x, C.c_float), _p(p, C.c_float), _p(g, C.c_float),
+                              C.c_double(logu), int(v), int(j), C.c_double(epsilon), C.c_double(joint_0),
+                              C.c_uint64(rng_seed), _p(vec, C.c_float), _p(scal, C.c_double))
+    names = ["position_minus", "mom_minus", "grad_minus", "position_plus", "mom_plus", "grad_plus",
+             "position_prime", "grad_prime"]
+    res = {n: vec[i] for i, n in enumerate(names)}
+    res.update(logp_prime=scal[0], n_prime=int(scal[1]), s_prime=bool(scal[2]), alpha_prime=scal[3],
+               n_alpha_prime=int(scal[4]))
+    return res
+
+
+def nuts_run(target: Target, positions, target_accept, n_collect, n_discard, *, seed=0, progress=False,
+             scalar_f32=False, max_depth=0, tapes=None, record=False, cap_unifs=None, state=None):
+    """Multi-chain NUTS.  tapes = (normals, exps, unifs) per chain -> replay mode; otherwise reference
+    streams from SmallRng(seed + i + 1), recorded if ``record``.
+    Returns dict(out, positions, counts, state, depths, n_grad, tapes)."""
+    pos = _f32(positions).copy()
+    chains, D = pos.shape
+    steps = n_collect + n_discard
+    out = np.zeros((chains, n_collect, D), dtype=np.float32)
+    counts = np.zeros((chains, 3), dtype=np.int64)
+    depths = np.zeros((chains, max(steps, 1)), dtype=np.int32)
+    n_grad = np.zeros(chains, dtype=np.int64)
+    st = np.tile(np.array([-1.0, 1.0, 0.0, np.log(10.0), 0.0]), (chains, 1)) if state is None else _f64(state).copy()
+    if tapes is not None:
+        normals, exps, unifs = (_f64(t) for t in tapes)
+        mode = 1
+    elif record:
+        cap_u = cap_unifs or (steps + 1) * 2100
+        normals = np.zeros((chains, (steps + 1) * D), dtype=np.float64)
+        exps = np.zeros((chains, steps + 1), dtype=np.float64)
+        unifs = np.zeros((chains, cap_u), dtype=np.float64)
+        mode = 0
+    else:
+        normals = exps = unifs = None
+        mode = 0
+    capn = normals.shape[1] if normals is not None else 0
+    cape = exps.shape[1] if exps is not None else 0
+    capu = unifs.shape[1] if unifs is not None else 0
+    rc = lib().orc_nuts_run(*target.args(), _p(pos, C.c_float), C.c_int64(chains), C.c_double(target_accept),
+                            int(scalar_f32), mode, C.c_uint64(seed), C.c_int64(n_collect), C.c_int64(n_discard),
+                            int(progress), int(max_depth), _p(out, C.c_float), _p(normals, C.c_double),
+                            C.c_int64(capn), _p(exps, C.c_double), C.c_int64(cape), _p(unifs, C.c_double),
+                            C.c_int64(capu), _p(counts, C.c_int64), _p(st, C.c_double), _p(depths, C.c_int32),
+                            _p(n_grad, C.c_int64))
+    assert rc == 0
+    if record:
+        assert (counts[:, 2] <= capu).all(), "uniform tape overflow while recording"
+    return dict(out=out, positions=pos, counts=counts, state=st, depths=depths, n_grad=n_grad,
+                tapes=(normals, exps, unifs))
+
+
+# ------------------------------------------------------------------ stats
+def autocov_bf(data):
+    data = _f32(data)
+    n, d = data.shape
+    out = np.empty((n, d), dtype=np.float32)
+    lib().orc_autocov_bf(_p(data, C.c_float), C.c_int64(n), C.c_int64(d), _p(out, C.c_float))
+    return out
+
+
+def autocov_fft(data):
+    data = _f32(data)
+    n, d = data.shape
+    out = np.empty((n, d), dtype=np.float32)
+    lib().orc_autocov_fft(_p(data, C.c_float), C.c_int64(n), C.c_int64(d), _p(out, C.c_float))
+    return out
+
+
+def split_rhat_mean_ess(sample):
+    sample = _f32(sample)
+    c, n, p = sample.shape
+    rhat = np.empty(p, dtype=np.float32)
+    ess = np.empty(p, dtype=np.float32)
+    rc = lib().orc_split_rhat_mean_ess(_p(sample, C.c_float), C.c_int64(c), C.c_int64(n), C.c_int64(p),
+                                       _p(rhat, C.c_float), _p(ess, C.c_float))
+    assert rc == 0
+    return rhat, ess
+
+
+def basic_stats(data):
+    data = _f32(data)
+    out = np.empty(5, dtype=np.float32)
+    lib().orc_basic_stats(_p(data, C.c_float), C.c_int64(data.shape[0]), _p(out, C.c_float))
+    return dict(min=out[0], median=out[1], max=out[2], mean=out[3], std=out[4])
+
+
+def run_stats(sample):
+    rhat, ess = split_rhat_mean_ess(sample)
+    return dict(ess=basic_stats(ess), rhat=basic_stats(rhat))
+
+
+# ------------------------------------------------------------------ progress trackers (src/stats.rs:189-307)
+class MultiChainTracker:
+    """MultiChainTracker, src/stats.rs:189-307 (f32 running mean / mean-of-squares, rhat = sqrt(var/W))."""
+
+    ALPHA = np.float32(0.01)
+
+    def __init__(self, n_chains, n_params):
+        self.n = 0
+        self.p_accept = np.float32(0.0)
+        self.last_state = np.zeros((n_chains, n_params), dtype=np.float32)
+        self.mean = np.zeros((n_chains, n_params), dtype=np.float32)
+        self.mean_sq = np.zeros((n_chains, n_params), dtype=np.float32)
+
+    def step(self, x):
+        self.n += 1
+        n = np.float32(self.n)
+        x = np.asarray(x, dtype=np.float32).reshape(self.mean.shape)
+        self.mean = (self.mean * (n - np.float32(1.0)) + x) / n
+        self.mean_sq = x * x if self.n == 1 else (self.mean_sq * (n - np.float32(1.0)) + x * x) / n
+        p = self.p_accept
+        one = np.float32(1.0)
+        for a, b in zip(x, self.last_state):
+            accepted = np.float32(1.0 if np.any(a != b) else 0.0)
+            p = (one - self.ALPHA) * p + self.ALPHA * accepted
+        self.p_accept = p
+        self.last_state = x.copy()
+
+    def rhat(self):
+        n = np.float32(self.n)
+        n_chains = np.float32(self.mean.shape[0])
+        mean_chain = self.mean.mean(axis=0, dtype=np.float32)
+        fac = n / (n_chains - np.float32(1.0))
+        between = ((self.mean - mean_chain[None, :]) ** 2).sum(axis=0, dtype=np.float32) * fac
+        sm2 = (self.mean_sq - self.mean * self.mean) * n / (n - np.float32(1.0))
+        within = sm2.mean(axis=0, dtype=np.float32)
+        var = within * ((n - np.float32(1.0)) / n) + between * (np.float32(1.0) / n)
+        return np.sqrt(var / within)

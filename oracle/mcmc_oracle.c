@@ -1,0 +1,671 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the mini-mcmc (v0.8.3) sampler hot path: MH / HMC / NUTS transitions and the
+ * split-Rhat / ESS diagnostics.  The reference is Rust and cannot be compiled here (no rustc/cargo,
+ * no vendored crates, no network), so this restatement is the parity oracle AND the reported CPU
+ * baseline (bench.py cpu_baseline / --impl reference, "kind": "port").  It is pinned against every
+ * golden vector the reference's own tests hold for this path (tests/test_oracle_golden.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load this library.
+ * The product (mini_mcmc_b200 / libminimcmc.so) never links, imports or calls it.
+ *
+ * Reference lines followed (relative to /root/reference):
+ *   MH step            src/metropolis_hastings.rs:303-315     run_chain   src/core.rs:55-73
+ *   init / init_det    src/core.rs:394-435
+ *   HMC step/leapfrog  src/hmc.rs:304-431                     HMC::run    src/hmc.rs:137-158
+ *   NUTS               src/nuts.rs:410-996  (nuts_impl.inc)
+ *   stats              src/stats.rs:310-336, 396-654
+ *   targets/proposals  src/distributions.rs, examples/poisson_mh.rs (orc_targets.h)
+ *
+ * Build: gcc -O3 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "orc_rng.h"
+#include "orc_targets.h"
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ RNG exports */
+
+ORC_API void orc_init_tables(void) { orc_zig_init(); }
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+ORC_API void orc_smallrng_seed_state(uint64_t seed, uint64_t *state4) {
+    orc_smallrng r;
+    orc_smallrng_seed(&r, seed);
+    memcpy(state4, r.s, 32);
+}
+/* kind: 0 u64, 1 f64 uniform, 2 f32 uniform (as double), 3 normal f64, 4 exp1 f64, 5 bool(0.5), 6 open01 */
+ORC_API void orc_smallrng_fill(uint64_t *state4, int kind, double *out, uint64_t *out_u64, int64_t n) {
+    orc_zig_init();
+    orc_smallrng r;
+    memcpy(r.s, state4, 32);
+    for (int64_t i = 0; i < n; ++i) {
+        switch (kind) {
+        case 0: out_u64[i] = orc_next_u64(&r); break;
+        case 1: out[i] = orc_next_f64(&r); break;
+        case 2: out[i] = (double)orc_next_f32(&r); break;
+        case 3: out[i] = orc_next_normal(&r); break;
+        case 4: out[i] = orc_next_exp1(&r); break;
+        case 5: out[i] = (double)orc_next_bool_half(&r); break;
+        case 6: out[i] = orc_next_open01(&r); break;
+        }
+    }
+    memcpy(state4, r.s, 32);
+}
+
+ORC_API void orc_philox(const uint32_t *key2, const uint32_t *ctr4, uint32_t *out4) {
+    orc_philox4x32_10(key2, ctr4, out4);
+}
+
+/* _init, src/core.rs:421-435: n*d StandardNormal f64 draws from one SmallRng, row-major. */
+ORC_API void orc_init_positions(double *out, int64_t n, int64_t d, uint64_t seed) {
+    orc_zig_init();
+    orc_smallrng r;
+    orc_smallrng_seed(&r, seed);
+    for (int64_t i = 0; i < n * d; ++i) out[i] = orc_next_normal(&r);
+}
+
+/* ------------------------------------------------------------------ target exports (KATs) */
+
+ORC_API double orc_gaussian2d_logp_kat(const double *p6, const double *x2, int normalized) {
+    return normalized ? orc_gaussian2d_logp(p6, x2) : orc_gaussian2d_unnorm_logp(p6, x2);
+}
+ORC_API double orc_iso_unnorm_logp_kat(double std, const double *x, int D) { return orc_iso_unnorm_logp(std, x, D); }
+ORC_API double orc_iso_proposal_logp_kat(double std, const double *from, const double *to, int D) {
+    return orc_iso_proposal_logp(std, from, to, D);
+}
+ORC_API double orc_poisson_logp_kat(double lambda, uint64_t k) { return orc_poisson_logp(lambda, k); }
+ORC_API double orc_ln_factorial_kat(uint64_t k) { return orc_ln_factorial(k); }
+ORC_API double orc_nonneg_logq_kat(uint64_t x, uint64_t y) { return orc_nonneg_logq(x, y); }
+
+static void orc_make_target(orc_target *t, int kind, int dim, const double *params, int n_params, const float *vec,
+                            const float *mat) {
+    memset(t, 0, sizeof(*t));
+    t->kind = kind;
+    t->dim = dim;
+    for (int i = 0; i < n_params && i < 8; ++i) t->p[i] = params[i];
+    t->vec = vec;
+    t->mat = mat;
+    orc_target_prepare(t);
+}
+
+ORC_API float orc_target_logp_grad(int kind, int dim, const double *params, int n_params, const float *vec,
+                                   const float *mat, const float *x, float *g) {
+    orc_target t;
+    orc_make_target(&t, kind, dim, params, n_params, vec, mat);
+    return orc_logp_grad_f32(&t, x, g);
+}
+
+/* ------------------------------------------------------------------ Metropolis-Hastings */
+
+/* One MH transition, src/metropolis_hastings.rs:303-315, continuous f64 state.
+ * target kind GAUSSIAN2D (p6) or ISO_GAUSSIAN (p[0] = std); proposal IsotropicGaussian(prop_std).
+ * noise[D] are the StandardNormal draws z_d; proposed_d = (0 + std*z_d) + x_d, the order of
+ * Normal::sample (mean + std*z) followed by `x + *eps` (src/distributions.rs:364-372). */
+static inline int orc_mh_cont_step(int kind, const double *tp, double prop_std, double *x, int D, const double *noise,
+                                   double u, double *lp_out) {
+    double prop[64];
+    for (int i = 0; i < D; ++i) prop[i] = (0.0 + prop_std * noise[i]) + x[i];
+    double cur_lp, prop_lp;
+    if (kind == ORC_T_GAUSSIAN2D) {
+        cur_lp = orc_gaussian2d_unnorm_logp(tp, x);
+        prop_lp = orc_gaussian2d_unnorm_logp(tp, prop);
+    } else {
+        cur_lp = orc_iso_unnorm_logp(tp[0], x, D);
+        prop_lp = orc_iso_unnorm_logp(tp[0], prop, D);
+    }
+    double qf = orc_iso_proposal_logp(prop_std, x, prop, D);
+    double qb = orc_iso_proposal_logp(prop_std, prop, x, D);
+    double r = (prop_lp + qb) - (cur_lp + qf);
+    int acc = r > log(u);
+    if (acc)
+        for (int i = 0; i < D; ++i) x[i] = prop[i];
+    if (lp_out) { lp_out[0] = cur_lp; lp_out[1] = prop_lp; lp_out[2] = r; }
+    return acc;
+}
+
+/* run_chain (src/core.rs:55-73) over all chains with replayed noise[chains,steps,D] and u[chains,steps].
+ * trace (optional) [chains,steps,4] = cur_lp, prop_lp, log_ratio, accepted.  state is updated in place. */
+ORC_API int orc_mh_cont_run_replay(int kind, const double *tp, double prop_std, double *state, int64_t chains, int D,
+                                   int64_t n_collect, int64_t n_discard, const double *noise, const double *u,
+                                   double *out, double *trace) {
+    if (D > 64) return -1;
+    const int64_t steps = n_collect + n_discard;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        double *x = state + c * D;
+        for (int64_t i = 0; i < steps; ++i) {
+            double lp[3];
+            int acc = orc_mh_cont_step(kind, tp, prop_std, x, D, noise + (c * steps + i) * D, u[c * steps + i], lp);
+            if (trace) {
+                double *tr = trace + (c * steps + i) * 4;
+                tr[0] = lp[0]; tr[1] = lp[1]; tr[2] = lp[2]; tr[3] = (double)acc;
+            }
+            if (i >= n_discard) memcpy(out + (c * n_collect + (i - n_discard)) * D, x, sizeof(double) * D);
+        }
+    }
+    return 0;
+}
+
+/* The reference's own streams for MetropolisHastings<f64> + IsotropicGaussian:
+ *  - accept uniforms: chain i uses SmallRng::seed_from_u64(1 + seed + i)  (src/metropolis_hastings.rs:187-193)
+ *  - proposal noise : every chain holds a CLONE of the proposal, i.e. the same SmallRng(prop_seed) stream
+ *    (:149-159); each sample() call draws D+1 normals and discards the last (zip polls the infinite
+ *    sampler first, src/distributions.rs:364-372).
+ * Fills noise[chains,steps,D] and u[chains,steps] so the tape can be replayed on both sides. */
+ORC_API void orc_mh_cont_reference_tape(uint64_t chain_seed, uint64_t prop_seed, int64_t chains, int64_t steps, int D,
+                                        double *noise, double *u) {
+    orc_zig_init();
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_smallrng cr, pr;
+        orc_smallrng_seed(&cr, 1 + chain_seed + (uint64_t)c);
+        orc_smallrng_seed(&pr, prop_seed);
+        for (int64_t i = 0; i < steps; ++i) {
+            for (int d = 0; d < D; ++d) noise[(c * steps + i) * D + d] = orc_next_normal(&pr);
+            (void)orc_next_normal(&pr); /* the D+1-th draw, discarded */
+            u[c * steps + i] = orc_next_f64(&cr);
+        }
+    }
+}
+
+/* Poisson MH transition (examples/poisson_mh.rs + src/metropolis_hastings.rs:303-315), u64 state. */
+static inline uint64_t orc_mh_poisson_step(double lambda, uint64_t x, int flip, double u) {
+    uint64_t y = (x == 0) ? 1 : (flip ? x + 1 : x - 1);
+    double cur_lp = orc_poisson_logp(lambda, x);
+    double prop_lp = orc_poisson_logp(lambda, y);
+    double qf = orc_nonneg_logq(x, y);
+    double qb = orc_nonneg_logq(y, x);
+    double r = (prop_lp + qb) - (cur_lp + qf);
+    return (r > log(u)) ? y : x;
+}
+
+ORC_API int orc_mh_poisson_run_replay(double lambda, uint64_t *state, int64_t chains, int64_t n_collect,
+                                      int64_t n_discard, const uint8_t *flip, const double *u, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        uint64_t x = state[c];
+        for (int64_t i = 0; i < steps; ++i) {
+            x = orc_mh_poisson_step(lambda, x, flip[c * steps + i], u[c * steps + i]);
+            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
+        }
+        state[c] = x;
+    }
+    return 0;
+}
+
+/* Twin of the CUDA path's native Philox keying (include/minimcmc.h "RNG contract"):
+ * key = seed, ctr = (chain_lo, chain_hi, step>>1, 0); step parity selects words (0,1) / (2,3);
+ * bits = w_lo | w_hi<<32; flip = bits & 1; u = (bits >> 11) * 2^-53. */
+ORC_API int orc_mh_poisson_run_philox(double lambda, uint64_t *state, int64_t chains, int64_t chain_offset,
+                                      int64_t step_base, int64_t n_collect, int64_t n_discard, uint64_t seed,
+                                      uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        uint64_t x = state[c];
+        const uint64_t gc = (uint64_t)(c + chain_offset);
+        for (int64_t i = 0; i < steps; ++i) {
+            const uint64_t gs = (uint64_t)(step_base + i);
+            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 1), 0u};
+            uint32_t w[4];
+            orc_philox4x32_10(key, ctr, w);
+            const int h = (int)(gs & 1) * 2;
+            uint64_t bits = (uint64_t)w[h] | ((uint64_t)w[h + 1] << 32);
+            int flip = (int)(bits & 1);
+            double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+            x = orc_mh_poisson_step(lambda, x, flip, u);
+            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
+        }
+        state[c] = x;
+    }
+    return 0;
+}
+
+/* The reference CPU path for Poisson MH as it runs today (rayon over chains, one SmallRng per chain for
+ * the accept uniform seeded 1+seed+i; the example's flips come from ThreadRng which is not reproducible,
+ * so a per-chain SmallRng(flip_seed + i) stands in for it).  Used as the CPU baseline. */
+ORC_API int orc_mh_poisson_run_reference(double lambda, uint64_t *state, int64_t chains, int64_t n_collect,
+                                         int64_t n_discard, uint64_t seed, uint64_t flip_seed, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_smallrng cr, fr;
+        orc_smallrng_seed(&cr, 1 + seed + (uint64_t)c);
+        orc_smallrng_seed(&fr, flip_seed + (uint64_t)c);
+        uint64_t x = state[c];
+        for (int64_t i = 0; i < steps; ++i) {
+            int flip = 0;
+            if (x != 0) flip = orc_next_bool_half(&fr); /* no draw when x == 0, examples/poisson_mh.rs:37-40 */
+            double u = orc_next_f64(&cr);
+            x = orc_mh_poisson_step(lambda, x, flip, u);
+            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
+        }
+        state[c] = x;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ HMC (batched, f32) */
+
+/* HMC::step + leapfrog, src/hmc.rs:304-431, for one chain (the chain axis is a pure batch axis).
+ * eps is T (=f32 for HMC<f32,..>); eps_half = step_size * 0.5 computed in T before the multiply
+ * (:323-324, :420).  trace[4] = logp_current, logp_proposed, accept_logp, accepted. */
+static int orc_hmc_step_chain(const orc_target *t, float *x, const float *mom0, float u, float eps, int L,
+                              float *scratch, float *trace) {
+    const int D = t->dim;
+    float *pos = scratch, *mom = scratch + D, *g = scratch + 2 * D, *lgs = scratch + 3 * D;
+    const float eps_half = eps * 0.5f;
+    float logp_cur = orc_logp_grad_f32(t, x, g);
+    float ke = 0.0f;
+    for (int i = 0; i < D; ++i) {
+        lgs[i] = g[i] * eps_half;
+        mom[i] = mom0[i];
+        pos[i] = x[i];
+        ke = ke + mom0[i] * mom0[i];
+    }
+    float h_cur = -logp_cur + ke * 0.5f;
+    for (int l = 0; l < L; ++l) {
+        for (int i = 0; i < D; ++i) {
+            mom[i] = mom[i] + lgs[i];
+            pos[i] = pos[i] + mom[i] * eps;
+        }
+        (void)orc_logp_grad_f32(t, pos, g);
+        for (int i = 0; i < D; ++i) {
+            lgs[i] = g[i] * eps_half;
+            mom[i] = mom[i] + lgs[i];
+        }
+    }
+    float logp_prop = orc_logp_grad_f32(t, pos, g); /* logp_final, src/hmc.rs:429 */
+    float ke2 = 0.0f;
+    for (int i = 0; i < D; ++i) ke2 = ke2 + mom[i] * mom[i];
+    float h_prop = -logp_prop + ke2 * 0.5f;
+    float accept_logp = h_cur - h_prop;
+    int acc = accept_logp >= logf(u); /* non-strict, NaN -> reject (src/hmc.rs:366-367) */
+    if (acc)
+        for (int i = 0; i < D; ++i) x[i] = pos[i];
+    if (trace) { trace[0] = logp_cur; trace[1] = logp_prop; trace[2] = accept_logp; trace[3] = (float)acc; }
+    return acc;
+}
+
+/* HMC::run, src/hmc.rs:137-158, with replayed momenta[steps,chains,D] and u[steps,chains] (the
+ * reference's own come from burn's backend RNG, which set_seed does not control: replay only).
+ * out is [chains, n_collect, D] (the permuted view the reference returns).  positions updated in place. */
+ORC_API int orc_hmc_run_replay(int kind, int D, const double *params, int n_params, const float *vec,
+                               const float *mat, float *positions, int64_t chains, double step_size, int L,
+                               int64_t n_collect, int64_t n_discard, const float *momenta, const float *u, float *out,
+                               float *trace) {
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+    const int64_t steps = n_collect + n_discard;
+    const float eps = (float)step_size;
+#pragma omp parallel
+    {
+        float *scratch = (float *)malloc(sizeof(float) * D * 4);
+#pragma omp for schedule(static)
+        for (int64_t c = 0; c < chains; ++c) {
+            float *x = positions + c * D;
+            for (int64_t s = 0; s < steps; ++s) {
+                orc_hmc_step_chain(&t, x, momenta + (s * chains + c) * D, u[s * chains + c], eps, L, scratch,
+                                   trace ? trace + (s * chains + c) * 4 : NULL);
+                if (s >= n_discard && out) memcpy(out + (c * n_collect + (s - n_discard)) * D, x, sizeof(float) * D);
+            }
+        }
+        free(scratch);
+    }
+    return 0;
+}
+
+/* CPU baseline for HMC: same transition, momenta/uniforms from a per-chain SmallRng + ziggurat
+ * (a generous stand-in for burn's backend RNG). */
+ORC_API int orc_hmc_run_reference(int kind, int D, const double *params, int n_params, const float *vec,
+                                  const float *mat, float *positions, int64_t chains, double step_size, int L,
+                                  int64_t n_collect, int64_t n_discard, uint64_t seed, float *out) {
+    orc_zig_init();
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+    const int64_t steps = n_collect + n_discard;
+    const float eps = (float)step_size;
+#pragma omp parallel
+    {
+        float *scratch = (float *)malloc(sizeof(float) * D * 5);
+        float *mom0 = scratch + 4 * D;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t c = 0; c < chains; ++c) {
+            orc_smallrng r;
+            orc_smallrng_seed(&r, seed + (uint64_t)c + 1);
+            float *x = positions + c * D;
+            for (int64_t s = 0; s < steps; ++s) {
+                for (int i = 0; i < D; ++i) mom0[i] = (float)orc_next_normal(&r);
+                float u = orc_next_f32(&r);
+                orc_hmc_step_chain(&t, x, mom0, u, eps, L, scratch, NULL);
+                if (s >= n_discard && out) memcpy(out + (c * n_collect + (s - n_discard)) * D, x, sizeof(float) * D);
+            }
+        }
+        free(scratch);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ NUTS */
+
+enum { ORC_SRC_RNG = 0, ORC_SRC_TAPE = 1 };
+typedef struct {
+    int mode;
+    orc_smallrng rng;
+    double *normals, *exps, *unifs; /* tape (read) or recording buffers (write, may be NULL) */
+    int64_t n_normals, n_exps, n_unifs;
+    int64_t cap_normals, cap_exps, cap_unifs;
+} orc_src;
+
+#define ST double
+#define SFX(n) n##_f64
+#define ST_EXP exp
+#define ST_LOG log
+#define ST_SQRT sqrt
+#define ST_POW pow
+#define ST_EPS 2.220446049250313e-16
+#define ST_IS_F32 0
+#include "nuts_impl.inc"
+#undef ST
+#undef SFX
+#undef ST_EXP
+#undef ST_LOG
+#undef ST_SQRT
+#undef ST_POW
+#undef ST_EPS
+#undef ST_IS_F32
+
+#define ST float
+#define SFX(n) n##_f32
+#define ST_EXP expf
+#define ST_LOG logf
+#define ST_SQRT sqrtf
+#define ST_POW powf
+#define ST_EPS 1.1920929e-07f
+#define ST_IS_F32 1
+#include "nuts_impl.inc"
+#undef ST
+#undef SFX
+
+/* find_reasonable_epsilon KAT entry (src/nuts.rs:1049-1055). */
+ORC_API double orc_nuts_find_reasonable_epsilon(int kind, int D, const double *params, int n_params, const float *vec,
+                                                const float *mat, const float *x, const float *p, int scalar_f32) {
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+    return scalar_f32 ? (double)find_reasonable_epsilon_f32(&t, x, p, NULL)
+                      : find_reasonable_epsilon_f64(&t, x, p, NULL);
+}
+
+/* build_tree KAT entry (src/nuts.rs:1057-1121).  vec_out[8*D] = x-, p-, g-, x+, p+, g+, x', g';
+ * scal_out[5] = logp', n', s', alpha', n_alpha'.  Uniforms from SmallRng(rng_seed). */
+ORC_API void orc_nuts_build_tree(int kind, int D, const double *params, int n_params, const float *vec,
+                                 const float *mat, const float *x, const float *p, const float *g, double logu, int v,
+                                 int j, double epsilon, double joint_0, uint64_t rng_seed, float *vec_out,
+                                 double *scal_out) {
+    orc_zig_init();
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+    orc_src src;
+    memset(&src, 0, sizeof(src));
+    src.mode = ORC_SRC_RNG;
+    orc_smallrng_seed(&src.rng, rng_seed);
+    tree_f64 r;
+    tree_alloc_f64(&r, D);
+    build_tree_f64(&t, x, p, g, logu, v, j, epsilon, joint_0, &src, &r, NULL);
+    memcpy(vec_out, r.xm, sizeof(float) * D * 8);
+    scal_out[0] = r.logp_prime; scal_out[1] = (double)r.n_prime; scal_out[2] = (double)r.s_prime;
+    scal_out[3] = r.alpha; scal_out[4] = (double)r.n_alpha;
+    tree_free_f64(&r);
+}
+
+/* Full multi-chain NUTS run.
+ *  mode 0: reference streams — chain i draws from SmallRng::seed_from_u64(seed + i + 1)
+ *          (NUTS::set_seed, src/nuts.rs:347-353); if tape buffers are given the draws are RECORDED so the
+ *          same values can be replayed into the CUDA path.
+ *  mode 1: replay — draws are read from the tapes.
+ * Tapes are per chain: normals[chains, cap_normals], exps[chains, cap_exps], unifs[chains, cap_unifs];
+ * counts_out[chains,3] returns how many of each were consumed.
+ * progress: 0 = NUTS::run semantics (n_collect+n_discard-1 steps, slot 0 = start), 1 = run_progress.
+ * state_io[chains,5] (optional, in/out) = epsilon, epsilon_bar, h_bar, mu, m  (epsilon = -1: unset).
+ * depths[chains, steps] optional; n_grad_out[chains] optional. */
+ORC_API int orc_nuts_run(int kind, int D, const double *params, int n_params, const float *vec, const float *mat,
+                         float *positions, int64_t chains, double target_accept, int scalar_f32, int mode,
+                         uint64_t seed, int64_t n_collect, int64_t n_discard, int progress, int max_depth, float *out,
+                         double *normals, int64_t cap_normals, double *exps, int64_t cap_exps, double *unifs,
+                         int64_t cap_unifs, int64_t *counts_out, double *state_io, int32_t *depths,
+                         int64_t *n_grad_out) {
+    orc_zig_init();
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+    const int64_t steps_total = n_collect + n_discard;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_src src;
+        memset(&src, 0, sizeof(src));
+        src.mode = mode;
+        if (mode == ORC_SRC_RNG) orc_smallrng_seed(&src.rng, seed + (uint64_t)c + 1);
+        if (normals) { src.normals = normals + c * cap_normals; src.cap_normals = cap_normals; }
+        if (exps) { src.exps = exps + c * cap_exps; src.cap_exps = cap_exps; }
+        if (unifs) { src.unifs = unifs + c * cap_unifs; src.cap_unifs = cap_unifs; }
+        int64_t n_grad = 0;
+        float *pos = positions + c * D;
+        float *o = out + c * n_collect * D;
+        int32_t *dp = depths ? depths + c * steps_total : NULL;
+        if (scalar_f32) {
+            chain_state_f32 cs;
+            chain_new_f32(&cs, target_accept);
+            if (state_io) {
+                double *s = state_io + c * 5;
+                cs.epsilon = (float)s[0]; cs.epsilon_bar = (float)s[1]; cs.h_bar = (float)s[2]; cs.mu = (float)s[3];
+                cs.m = (int64_t)s[4];
+            }
+            chain_run_f32(&t, &cs, pos, &src, n_collect, n_discard, progress, max_depth, o, &n_grad, dp);
+            if (state_io) {
+                double *s = state_io + c * 5;
+                s[0] = cs.epsilon; s[1] = cs.epsilon_bar; s[2] = cs.h_bar; s[3] = cs.mu; s[4] = (double)cs.m;
+            }
+        } else {
+            chain_state_f64 cs;
+            chain_new_f64(&cs, target_accept);
+            if (state_io) {
+                double *s = state_io + c * 5;
+                cs.epsilon = s[0]; cs.epsilon_bar = s[1]; cs.h_bar = s[2]; cs.mu = s[3]; cs.m = (int64_t)s[4];
+            }
+            chain_run_f64(&t, &cs, pos, &src, n_collect, n_discard, progress, max_depth, o, &n_grad, dp);
+            if (state_io) {
+                double *s = state_io + c * 5;
+                s[0] = cs.epsilon; s[1] = cs.epsilon_bar; s[2] = cs.h_bar; s[3] = cs.mu; s[4] = (double)cs.m;
+            }
+        }
+        if (counts_out) {
+            counts_out[c * 3 + 0] = src.n_normals; counts_out[c * 3 + 1] = src.n_exps; counts_out[c * 3 + 2] = src.n_unifs;
+        }
+        if (n_grad_out) n_grad_out[c] = n_grad;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ stats (src/stats.rs) */
+
+/* autocov_bf, src/stats.rs:632-654.  data [n,d] row-major -> out [n,d]. */
+ORC_API void orc_autocov_bf(const float *data, int64_t n, int64_t d, float *out) {
+    float *col = (float *)malloc(sizeof(float) * n);
+    for (int64_t c = 0; c < d; ++c) {
+        float sum = 0.0f;
+        for (int64_t t = 0; t < n; ++t) sum += data[t * d + c];
+        float mean = sum / (float)n;
+        for (int64_t t = 0; t < n; ++t) col[t] = data[t * d + c] - mean;
+        for (int64_t lag = 0; lag < n; ++lag) {
+            float s = 0.0f;
+            for (int64_t t = 0; t < n - lag; ++t) s += col[t] * col[t + lag];
+            out[lag * d + c] = s / (float)n;
+        }
+    }
+    free(col);
+}
+
+/* radix-2 complex FFT in f32 (rustfft 6.4.1, Cargo.lock:4877, is not in the tree; any exact-arithmetic
+ * equivalent DFT differs from it only by f32 rounding, ~1e-7 relative). */
+static void orc_fft_f32(float *re, float *im, int64_t n, int inverse) {
+    for (int64_t i = 1, j = 0; i < n; ++i) {
+        int64_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) {
+            float tr = re[i]; re[i] = re[j]; re[j] = tr;
+            float ti = im[i]; im[i] = im[j]; im[j] = ti;
+        }
+    }
+    for (int64_t len = 2; len <= n; len <<= 1) {
+        double ang = 2.0 * M_PI / (double)len * (inverse ? 1.0 : -1.0);
+        for (int64_t i = 0; i < n; i += len) {
+            for (int64_t k = 0; k < len / 2; ++k) {
+                float wr = (float)cos(ang * (double)k), wi = (float)sin(ang * (double)k);
+                int64_t a = i + k, b = i + k + len / 2;
+                float xr = re[b] * wr - im[b] * wi;
+                float xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] = re[a] + xr; im[a] = im[a] + xi;
+            }
+        }
+    }
+}
+
+/* autocov_fft, src/stats.rs:576-620. */
+ORC_API void orc_autocov_fft(const float *data, int64_t n, int64_t d, float *out) {
+    int64_t n_padded = 1;
+    while (n_padded < 2 * n - 1) n_padded <<= 1;
+    float *re = (float *)malloc(sizeof(float) * n_padded * 2);
+    float *im = re + n_padded;
+    for (int64_t c = 0; c < d; ++c) {
+        float sum = 0.0f;
+        for (int64_t t = 0; t < n; ++t) sum += data[t * d + c];
+        float mean = sum / (float)n;
+        for (int64_t t = 0; t < n_padded; ++t) { re[t] = t < n ? data[t * d + c] - mean : 0.0f; im[t] = 0.0f; }
+        orc_fft_f32(re, im, n_padded, 0);
+        for (int64_t t = 0; t < n_padded; ++t) { re[t] = re[t] * re[t] + im[t] * im[t]; im[t] = 0.0f; }
+        orc_fft_f32(re, im, n_padded, 1);
+        for (int64_t t = 0; t < n; ++t) out[t * d + c] = re[t] / (float)n_padded / (float)n;
+    }
+    free(re);
+}
+
+/* split_rhat_mean_ess, src/stats.rs:396-554.  sample [c,n,p] f32 -> rhat[p], ess[p]. */
+ORC_API int orc_split_rhat_mean_ess(const float *sample, int64_t c, int64_t n, int64_t p, float *rhat_out,
+                                    float *ess_out) {
+    const int64_t half = n / 2;
+    const int64_t C = 2 * c, N = half;
+    if (N < 1) return -1;
+    /* splitcat :396-402: first `half` draws of every chain, then the LAST `half` draws of every chain */
+    float *split = (float *)malloc(sizeof(float) * C * N * p);
+    for (int64_t j = 0; j < c; ++j) {
+        memcpy(split + (j * N) * p, sample + (j * n) * p, sizeof(float) * N * p);
+        memcpy(split + ((c + j) * N) * p, sample + (j * n + (n - half)) * p, sizeof(float) * N * p);
+    }
+    float *within = (float *)malloc(sizeof(float) * p * 2);
+    float *var = within + p;
+    /* withinvar :429-477 */
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < p; ++q) {
+        float *cm = (float *)malloc(sizeof(float) * C);
+        float msum = 0.0f;
+        for (int64_t j = 0; j < C; ++j) {
+            float s = 0.0f;
+            for (int64_t t = 0; t < N; ++t) s += split[(j * N + t) * p + q];
+            cm[j] = s / (float)N;
+            msum += cm[j];
+        }
+        float overall = msum / (float)C;
+        float dsum = 0.0f;
+        for (int64_t j = 0; j < C; ++j) { float dd = cm[j] - overall; dsum += dd * dd; }
+        float b = dsum * ((float)N / (float)(C - 1));
+        float wsum = 0.0f;
+        for (int64_t j = 0; j < C; ++j) {
+            float s = 0.0f;
+            for (int64_t t = 0; t < N; ++t) { float v = split[(j * N + t) * p + q]; s += (v - cm[j]) * (v - cm[j]); }
+            wsum += s / (float)N;
+        }
+        float w = wsum / (float)C;
+        within[q] = w;
+        var[q] = (((float)N - 1.0f) / (float)N) * w + b / (float)N;
+        free(cm);
+    }
+    for (int64_t q = 0; q < p; ++q) rhat_out[q] = sqrtf(within[q] / var[q]); /* :425-427 (sic: W/var) */
+    /* ess :496-546 */
+    float *avg = (float *)calloc((size_t)(N * p), sizeof(float));
+    {
+        float *ac = (float *)malloc(sizeof(float) * N * p);
+        for (int64_t j = 0; j < C; ++j) {
+            if (N <= 100) orc_autocov_bf(split + j * N * p, N, p, ac);
+            else orc_autocov_fft(split + j * N * p, N, p, ac);
+            for (int64_t i = 0; i < N * p; ++i) avg[i] += ac[i];
+        }
+        for (int64_t i = 0; i < N * p; ++i) avg[i] = avg[i] / (float)C;
+        free(ac);
+    }
+    for (int64_t q = 0; q < p; ++q) {
+        /* rho_t = -(( -avg + within) / var) + 1 */
+#define ORC_RHO(tt) (-((-avg[(tt) * p + q] + within[q]) / var[q]) + 1.0f)
+        float mn = N >= 2 ? ORC_RHO(0) + ORC_RHO(1) : 0.0f;
+        float o = 0.0f;
+        for (int64_t t = 0; t + 1 < N; t += 2) {
+            float pt = ORC_RHO(t) + ORC_RHO(t + 1);
+            if (pt <= 0.0f) break;
+            if (pt > mn) pt = mn;
+            mn = pt;
+            o += pt;
+        }
+#undef ORC_RHO
+        float tau = -1.0f + 2.0f * o;
+        ess_out[q] = (1.0f / tau) * (float)C * (float)N;
+    }
+    free(avg);
+    free(within);
+    free(split);
+    return 0;
+}
+
+static int orc_cmp_desc(const void *a, const void *b) {
+    float x = *(const float *)a, y = *(const float *)b;
+    return (y > x) - (y < x);
+}
+/* basic_stats, src/stats.rs:310-336: sort descending; min = last, max = first, median = data[len/2],
+ * mean, std(ddof = 1).  out5 = min, median, max, mean, std. */
+ORC_API void orc_basic_stats(const float *data, int64_t n, float *out5) {
+    float *d = (float *)malloc(sizeof(float) * n);
+    memcpy(d, data, sizeof(float) * n);
+    qsort(d, (size_t)n, sizeof(float), orc_cmp_desc);
+    float sum = 0.0f;
+    for (int64_t i = 0; i < n; ++i) sum += d[i];
+    float mean = sum / (float)n;
+    /* ndarray std(ddof): Welford in the element type */
+    float m = 0.0f, s2 = 0.0f;
+    for (int64_t i = 0; i < n; ++i) {
+        float cnt = (float)(i + 1);
+        float delta = d[i] - m;
+        m += delta / cnt;
+        s2 += delta * (d[i] - m);
+    }
+    out5[0] = d[n - 1]; out5[1] = d[n / 2]; out5[2] = d[0]; out5[3] = mean;
+    out5[4] = sqrtf(s2 / ((float)n - 1.0f));
+    free(d);
+}
