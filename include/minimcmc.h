@@ -1,0 +1,228 @@
+/*
+ * minimcmc.h — C ABI of the B200-native batched MCMC engine (libminimcmc.so).
+ *
+ * This is the drop-in boundary for the sampler hot path of mini-mcmc v0.8.3.  The reference has no FFI
+ * of its own (it is one Rust crate); the entry points below are exactly what a Rust `extern "C"` shim
+ * for that path binds (INTEGRATION.md shows the binding).  Each group cites the reference interface it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every call returns int: 0 = ok, < 0 = mmc_status; mmc_last_error() gives a thread-local message.
+ *   - the library owns opaque handles and their device state; the caller owns every in/out buffer.
+ *     Entry points without suffix take HOST pointers (copies happen inside the call, on the handle's
+ *     stream, and the call returns after the result is in the caller's buffer); *_dev entry points take
+ *     DEVICE pointers plus a cudaStream_t (passed as void*) and are asynchronous.
+ *   - a handle is NOT thread-safe (mirrors `&mut self`); distinct handles are independent.
+ *   - sampler state persists inside the handle, so calling run() again continues the chains
+ *     (same as the reference structs, SURVEY.md §5 "checkpoint / resume").
+ *   - outputs are C-contiguous [chains, n_collect, dim], the layout ChainRunner::run / HMC::run /
+ *     NUTS::run return (src/core.rs:176-186, src/hmc.rs:157, src/nuts.rs:169).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     MMC_ERR_NO_DEVICE.
+ *
+ * RNG contract (native mode, i.e. no replay tape): Philox4x32-10, key = 64-bit seed,
+ *   counter = (global_chain_lo, global_chain_hi, step_word, sub).  `global_chain` = local chain index +
+ *   the handle's chain offset, `step` counts transitions since the handle was seeded, so results do not
+ *   depend on how chains are sharded over GPUs.
+ *     Poisson MH : step_word = step >> 1, sub = 0; step parity selects words (0,1) or (2,3);
+ *                  bits = w_lo | w_hi << 32; flip = bits & 1; u = (bits >> 11) * 2^-53.
+ *     MH (f64)   : step_word = step; sub 0 words (0,1) -> accept uniform (53 bit); sub 1 + j ->
+ *                  Box-Muller pair of proposal normals (2j, 2j+1), words (0,1) -> u1, (2,3) -> u2.
+ *     HMC (f32)  : step_word = step; sub j -> momenta 4j..4j+3 (Box-Muller on words (0,1), (2,3));
+ *                  sub 0x80000000 word 0 -> accept uniform (w >> 8) * 2^-24.
+ *     NUTS       : step_word = step (0 = init_chain); sub j -> normals 4j..4j+3; sub 0x80000000 word 0 ->
+ *                  Exp(1) = -ln(((w >> 8) + 0.5) * 2^-24); uniform #q of the step -> sub 0x80000001 + (q >> 1),
+ *                  words 2(q&1), 2(q&1)+1 (f64 uniforms use 53 bits, T = f32 uniforms the top 24 of the high word).
+ *   Replay mode substitutes caller-provided tapes for all of the above (parity testing).
+ */
+#ifndef MINIMCMC_H
+#define MINIMCMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMC_VERSION 100
+
+typedef enum {
+    MMC_OK = 0,
+    MMC_ERR_INVALID = -1,      /* bad argument */
+    MMC_ERR_NO_DEVICE = -2,    /* no CUDA device / driver */
+    MMC_ERR_CUDA = -3,         /* CUDA runtime error (message in mmc_last_error) */
+    MMC_ERR_UNSUPPORTED = -4,  /* combination not compiled in */
+    MMC_ERR_OVERFLOW = -5,     /* integer state left the range the device tables cover */
+    MMC_ERR_NOMEM = -6
+} mmc_status;
+
+typedef enum { MMC_F32 = 0, MMC_F64 = 1, MMC_U64 = 2 } mmc_dtype;
+
+/* Built-in targets (src/distributions.rs, examples/poisson_mh.rs).  Custom device targets get ids
+ * >= MMC_T_CUSTOM_BASE from mmc_register_target (see minimcmc_target.cuh). */
+typedef enum {
+    MMC_T_GAUSSIAN2D = 1,      /* Gaussian2D           src/distributions.rs:159-206  params = mean0,mean1,c00,c01,c10,c11 */
+    MMC_T_ISO_GAUSSIAN = 2,    /* IsotropicGaussian    src/distributions.rs:394-402  params = std                          */
+    MMC_T_POISSON = 3,         /* PoissonTarget        examples/poisson_mh.rs:10-26  params = lambda                       */
+    MMC_T_ROSENBROCK_ND = 4,   /* RosenbrockND         src/distributions.rs:527-547                                        */
+    MMC_T_ROSENBROCK_2D = 5,   /* Rosenbrock2D         src/distributions.rs:491-524  params = a,b                          */
+    MMC_T_DIFF_GAUSSIAN2D = 6, /* DiffableGaussian2D   src/distributions.rs:213-316  params = mean0,mean1,c00,c01,c10,c11 */
+    MMC_T_DENSE_GAUSSIAN = 7,  /* D-dim dense Gaussian (config C4)  params = norm_const; vec = mean[D]; mat = precision[D,D] */
+    MMC_T_STD_NORMAL = 8,      /* test target          src/nuts.rs:1024-1037                                               */
+    MMC_T_CUSTOM_BASE = 1000
+} mmc_target_kind;
+
+typedef struct {
+    int32_t kind;       /* mmc_target_kind or a registered custom id */
+    int32_t dim;
+    double params[8];
+    const float *vec;   /* HOST pointers, copied to the device at create time (may be NULL) */
+    const float *mat;
+} mmc_target_desc;
+
+/* Proposals for Metropolis-Hastings (trait Proposal, src/distributions.rs:92-101). */
+typedef enum {
+    MMC_Q_ISO_GAUSSIAN = 1, /* IsotropicGaussian::sample/logp  src/distributions.rs:360-392  param = std */
+    MMC_Q_NONNEG_RW = 2     /* NonnegativeProposal             examples/poisson_mh.rs:28-77              */
+} mmc_proposal_kind;
+
+typedef struct {
+    int32_t kind;
+    double param;
+} mmc_proposal_desc;
+
+/* ------------------------------------------------------------------ library */
+int mmc_version(void);
+const char *mmc_last_error(void);
+/* Select the CUDA device this thread's subsequent handles live on (one process per GPU). */
+int mmc_init(int device);
+/* SM count / name of the active device (diagnostics). */
+int mmc_device_info(int *sm_count, char *name, int name_len);
+
+/* ------------------------------------------------------------------ init   (src/core.rs:394-435)
+ * init_with_seed / init_det: n*d StandardNormal f64 draws from SmallRng::seed_from_u64(seed), row-major.
+ * Host routine (bit-compatible with rand 0.9 / rand_distr 0.5 so existing seeds keep their meaning). */
+int mmc_init_positions(double *out_host, int64_t n, int64_t d, uint64_t seed);
+/* Device-side N(0,1) starts for large batches, Philox keyed (seed, global_chain, step = 0xFFFFFFFF). */
+int mmc_init_positions_dev(float *out_dev, int64_t n, int64_t d, uint64_t seed, int64_t chain_offset, void *stream);
+
+/* ------------------------------------------------------------------ Metropolis-Hastings
+ * Replaces MetropolisHastings::new / .seed / ChainRunner::run for the built-in target+proposal pairs
+ * (src/metropolis_hastings.rs:149-193,303-315; src/core.rs:55-73,176-186).
+ * state dtype: MMC_F64 (continuous targets) or MMC_U64 (`usize` state of the Poisson example). */
+typedef struct mmc_mh mmc_mh;
+
+typedef struct {
+    /* all [chains, steps(, dim)] with steps = n_collect + n_discard; host pointers for mmc_mh_run,
+     * device pointers for mmc_mh_run_dev */
+    const double *noise;  /* continuous: StandardNormal draws z, proposal = (0 + std*z) + x */
+    const double *u;      /* accept uniforms in [0,1) */
+    const uint8_t *flip;  /* Poisson: 1 -> x+1, 0 -> x-1 (ignored when x == 0) */
+    double *trace;        /* optional out [chains, steps, 4]: cur_lp, prop_lp, log_ratio, accepted (continuous only) */
+} mmc_replay_mh;
+
+int mmc_mh_create(mmc_mh **h, const mmc_target_desc *target, const mmc_proposal_desc *proposal,
+                  const void *init_host, int64_t chains, int32_t dim, int32_t state_dtype);
+int mmc_mh_seed(mmc_mh *h, uint64_t seed);                  /* .seed(s): also resets the step counter */
+int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset);     /* first global chain id held by this handle */
+/* Poisson accept test: 0 = evaluate (lp'+qb)-(lp+qf) > ln(u) in f64 on the device,
+ * 1 (default) = compare the 53-bit uniform against host-built integer thresholds that encode the same
+ * predicate with the host libm's ln (bit-exact with the reference's CPU decisions). */
+int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode);
+int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay);
+int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, const mmc_replay_mh *replay_dev,
+                   void *stream);
+int mmc_mh_get_state(mmc_mh *h, void *state_host);
+int mmc_mh_set_state(mmc_mh *h, const void *state_host);
+void mmc_mh_destroy(mmc_mh *h);
+
+/* ------------------------------------------------------------------ HMC
+ * Replaces HMC::new / set_seed / step / run (src/hmc.rs:87-158,304-431).  Tensors are f32 (burn backend
+ * element type).  exact = 1 forbids FMA contraction so replayed trajectories reproduce the CPU
+ * arithmetic operation by operation; exact = 0 (default) is the throughput build. */
+typedef struct mmc_hmc mmc_hmc;
+
+typedef struct {
+    const float *momenta; /* [steps, chains, dim] */
+    const float *u;       /* [steps, chains] accept uniforms in [0,1) */
+    float *trace;         /* optional out [steps, chains, 4]: logp_current, logp_proposed, accept_logp, accepted */
+} mmc_replay_hmc;
+
+int mmc_hmc_create(mmc_hmc **h, const mmc_target_desc *target, const float *init_host, int64_t chains, int32_t dim,
+                   double step_size, int32_t n_leapfrog);
+int mmc_hmc_set_seed(mmc_hmc *h, uint64_t seed);
+int mmc_hmc_set_chain_offset(mmc_hmc *h, int64_t offset);
+int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact);
+int mmc_hmc_step(mmc_hmc *h);
+int mmc_hmc_run(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, const mmc_replay_hmc *replay);
+int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_dev,
+                    const mmc_replay_hmc *replay_dev, void *stream);
+int mmc_hmc_get_positions(mmc_hmc *h, float *positions_host);
+int mmc_hmc_positions_dev(mmc_hmc *h, float **positions_dev); /* borrowed pointer [chains, dim] */
+/* accepted transitions / total transitions since creation (device counters) */
+int mmc_hmc_get_accept_counts(mmc_hmc *h, int64_t *accepted, int64_t *total);
+/* dump the native-mode draws the sampler WOULD consume for steps [step_base, step_base+steps) so a CPU
+ * checker can replay them: momenta [steps, chains, dim], u [steps, chains] (device pointers). */
+int mmc_hmc_export_tape_dev(mmc_hmc *h, int64_t step_base, int64_t steps, float *momenta_dev, float *u_dev,
+                            void *stream);
+void mmc_hmc_destroy(mmc_hmc *h);
+
+/* ------------------------------------------------------------------ NUTS
+ * Replaces NUTS::new / set_seed / run / run_progress and NUTSChain (src/nuts.rs:123-170,347-353,410-691).
+ * scalar_dtype = type T of epsilon / joint / logu / alpha (MMC_F64 in the reference's golden tests,
+ * MMC_F32 in examples/minimal_nuts.rs).  The reference's tree has no depth cap; max_depth bounds the
+ * number of doublings (default 10 when <= 0). */
+typedef struct mmc_nuts mmc_nuts;
+
+typedef struct {
+    /* per chain tapes; all host (mmc_nuts_run) or all device (mmc_nuts_run_dev) */
+    const double *normals; int64_t cap_normals; /* [chains, cap_normals]: D for init_chain then D per step */
+    const double *exps;    int64_t cap_exps;    /* [chains, cap_exps]   : one Exp(1) per step */
+    const double *unifs;   int64_t cap_unifs;   /* [chains, cap_unifs]  : sequential uniform tape */
+} mmc_replay_nuts;
+
+int mmc_nuts_create(mmc_nuts **h, const mmc_target_desc *target, const float *init_host, int64_t chains,
+                    int32_t dim, double target_accept_p, int32_t scalar_dtype, int32_t max_depth);
+int mmc_nuts_set_seed(mmc_nuts *h, uint64_t seed);
+int mmc_nuts_set_chain_offset(mmc_nuts *h, int64_t offset);
+int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact);
+/* progress_semantics 0: NUTS::run (n_collect+n_discard-1 steps, slot 0 = starting position);
+ *                    1: NUTS::run_progress (n_collect+n_discard steps). */
+int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress_semantics, float *out_host,
+                 const mmc_replay_nuts *replay);
+int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress_semantics, float *out_dev,
+                     const mmc_replay_nuts *replay_dev, void *stream);
+/* state_host [chains, 5] = epsilon, epsilon_bar, h_bar, mu, m */
+int mmc_nuts_get_state(mmc_nuts *h, double *state_host);
+int mmc_nuts_get_positions(mmc_nuts *h, float *positions_host);
+/* counters summed over chains since creation: grad evals, transitions, tapes consumed (uniforms) and the
+ * histogram of tree depths [max_depth + 1] */
+int mmc_nuts_get_counters(mmc_nuts *h, int64_t *n_grad, int64_t *n_transitions, int64_t *depth_hist, int32_t hist_len);
+void mmc_nuts_destroy(mmc_nuts *h);
+
+/* ------------------------------------------------------------------ diagnostics
+ * Replaces split_rhat_mean_ess / RunStats::from / basic_stats (src/stats.rs:310-336,396-554).
+ * sample is [c, n, p] f32. */
+int mmc_split_rhat_ess(const float *sample_host, int64_t c, int64_t n, int64_t p, float *rhat_host, float *ess_host);
+int mmc_split_rhat_ess_dev(const float *sample_dev, int64_t c, int64_t n, int64_t p, float *rhat_host,
+                           float *ess_host, void *stream);
+/* Sharded form (one process per GPU).  `partial` is f64 [2 + n/2][p] in device memory
+ * (mmc_stats_partial_len values): row 0 = sum_j m_j, row 1 = sum_j m_j^2, row 2 + t = sum_j acov_j(t) over the
+ * LOCAL split chains.  Each call computes lags [lag0, lag0 + n_lags) (and rows 0-1 when lag0 == 0), zeroing
+ * the rows it produces first.  The caller sums the partials across ranks (ncclAllReduce /
+ * torch.distributed.all_reduce) and finalises on the host; mmc_stats_finalize returns 1 (not an error) when
+ * the Geyer truncation has not terminated within `lags_available` lags, in which case further lags are
+ * requested with another mmc_stats_partial_dev call. */
+int64_t mmc_stats_partial_len(int64_t n, int64_t p);
+int mmc_stats_partial_dev(const float *sample_dev, int64_t c_local, int64_t n, int64_t p, int64_t lag0,
+                          int64_t n_lags, double *partial_dev, void *stream);
+int mmc_stats_finalize(const double *partial_host, int64_t c_total, int64_t n, int64_t p, int64_t lags_available,
+                       float *rhat_host, float *ess_host);
+typedef struct { float min, median, max, mean, std; } mmc_basic_stats;
+typedef struct { mmc_basic_stats ess, rhat; } mmc_run_stats;
+int mmc_basic_stats_of(const float *data_host, int64_t len, mmc_basic_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIMCMC_H */

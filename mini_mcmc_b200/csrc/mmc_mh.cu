@@ -1,0 +1,348 @@
+// Metropolis-Hastings C ABI (see include/minimcmc.h) — host side of K1.
+// Compiled with -fmad=false (see mmc_mh.cuh).
+#include <cmath>
+#include <vector>
+
+#include "mmc_mh.cuh"
+
+using namespace mmc;
+
+struct mmc_mh {
+    mmc_target_desc target{};
+    mmc_proposal_desc proposal{};
+    int64_t chains = 0;
+    int32_t dim = 0;
+    int32_t dtype = MMC_F64;
+    int64_t chain_offset = 0;
+    int64_t step = 0;  // transitions since the last seed()
+    uint64_t seed = 0;
+    int32_t accept_mode = 1;
+    void *d_state = nullptr;
+    // Poisson tables
+    int32_t table_len = 0;
+    double *d_lnfact = nullptr;
+    uint64_t *d_thr_up = nullptr, *d_thr_dn = nullptr;
+    int32_t *d_error = nullptr;
+    double ln_lambda = 0, ln_half = 0;
+    // host-API staging
+    cudaStream_t stream = nullptr;
+    void *d_out = nullptr;
+    size_t d_out_bytes = 0;
+    void *d_replay[3] = {nullptr, nullptr, nullptr};
+    size_t d_replay_bytes[3] = {0, 0, 0};
+    double *d_trace = nullptr;
+    size_t d_trace_bytes = 0;
+};
+
+namespace {
+
+size_t elem_size(int32_t dtype) { return 8; }
+
+int grow(void **ptr, size_t *cap, size_t need) {
+    if (*cap >= need) return MMC_OK;
+    if (*ptr) MMC_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    MMC_CUDA(cudaMalloc(ptr, need));
+    *cap = need;
+    return MMC_OK;
+}
+
+// Smallest m in [0, 2^53] with !(r > ln(m * 2^-53)): the accept set {u : r > ln u} over the 53-bit
+// uniform grid is [0, m) because ln is monotone.  Evaluated with the host libm, the same ln the
+// reference's CPU path calls.
+uint64_t accept_threshold(double r) {
+    if (!(r > -INFINITY)) return 0;  // r = -inf or NaN: never accepted (even ln(0) = -inf fails '>')
+    const uint64_t top = 1ULL << 53;
+    auto pred = [&](uint64_t m) { return r > std::log((double)m * 0x1p-53); };
+    if (pred(top - 1)) return top;
+    uint64_t lo = 0, hi = top - 1;  // pred(lo) true, pred(hi) false
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (pred(mid)) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+int build_poisson_tables(mmc_mh *h) {
+    const double lambda = h->target.params[0];
+    MMC_REQUIRE(lambda > 0.0, "Poisson target needs lambda > 0");
+    // generous range: mean + 40 sd + slack, bounded by the u16 staging tile
+    int64_t len = (int64_t)std::ceil(lambda + 40.0 * std::sqrt(lambda) + 64.0);
+    if (len < 256) len = 256;
+    if (len > 4096) len = 4096;
+    h->table_len = (int32_t)len;
+    h->ln_lambda = std::log(lambda);
+    h->ln_half = std::log(0.5);
+    std::vector<double> lnfact(len), lp(len);
+    // ln_factorial, examples/poisson_mh.rs:79-89: 0 for k < 2, else sum_{i=1..k} ln(i) in that order.
+    double acc = 0.0;
+    for (int64_t k = 0; k < len; ++k) {
+        if (k >= 1) acc += std::log((double)k);
+        lnfact[k] = k < 2 ? 0.0 : acc;
+        lp[k] = -lambda + (double)k * h->ln_lambda - lnfact[k];
+    }
+    std::vector<uint64_t> up(len, 0), dn(len, 0);
+    for (int64_t k = 0; k + 1 < len; ++k) {
+        // x = k -> y = k + 1 : q_f = (k == 0 ? 0 : ln 1/2), q_b = ln 1/2
+        const double qf = k == 0 ? 0.0 : h->ln_half, qb = h->ln_half;
+        up[k] = accept_threshold((lp[k + 1] + qb) - (lp[k] + qf));
+        if (k >= 1) {
+            // x = k -> y = k - 1 : q_f = ln 1/2, q_b = (y == 0 ? 0 : ln 1/2)
+            const double qb2 = (k - 1 == 0) ? 0.0 : h->ln_half;
+            dn[k] = accept_threshold((lp[k - 1] + qb2) - (lp[k] + h->ln_half));
+        }
+    }
+    MMC_CUDA(cudaMalloc(&h->d_lnfact, len * sizeof(double)));
+    MMC_CUDA(cudaMalloc(&h->d_thr_up, len * sizeof(uint64_t)));
+    MMC_CUDA(cudaMalloc(&h->d_thr_dn, len * sizeof(uint64_t)));
+    MMC_CUDA(cudaMalloc(&h->d_error, sizeof(int32_t)));
+    MMC_CUDA(cudaMemcpy(h->d_lnfact, lnfact.data(), len * sizeof(double), cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaMemcpy(h->d_thr_up, up.data(), len * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaMemcpy(h->d_thr_dn, dn.data(), len * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaMemset(h->d_error, 0, sizeof(int32_t)));
+    return MMC_OK;
+}
+
+template <int D>
+int launch_cont(const MhContParams &p, bool replay, cudaStream_t stream) {
+    const int block = 128;
+    const unsigned grid = (unsigned)((p.chains + block - 1) / block);
+    if (replay)
+        mh_cont_kernel<D, true><<<grid, block, 0, stream>>>(p);
+    else
+        mh_cont_kernel<D, false><<<grid, block, 0, stream>>>(p);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+int run_cont(mmc_mh *h, int64_t n_collect, int64_t n_discard, double *out_dev, const mmc_replay_mh *rp,
+             cudaStream_t stream) {
+    MhContParams p{};
+    p.state = (double *)h->d_state;
+    p.out = out_dev;
+    p.noise = rp ? rp->noise : nullptr;
+    p.u = rp ? rp->u : nullptr;
+    p.trace = rp ? rp->trace : nullptr;
+    p.chains = h->chains;
+    p.chain_offset = h->chain_offset;
+    p.step_base = h->step;
+    p.n_collect = n_collect;
+    p.n_discard = n_discard;
+    p.key = seed_key(h->seed);
+    p.target_kind = h->target.kind;
+    for (int i = 0; i < 6; ++i) p.tp[i] = h->target.params[i];
+    const double std_ = h->proposal.param;
+    p.prop_std = std_;
+    const double var = std_ * std_;
+    p.prop_norm_term = -(double)h->dim * 0.5 * std::log(var * M_PI * std_ * std_);
+    const bool replay = rp && rp->noise && rp->u;
+    MMC_REQUIRE(!rp || replay, "MH replay needs both noise and u tapes");
+    switch (h->dim) {
+    case 1: return launch_cont<1>(p, replay, stream);
+    case 2: return launch_cont<2>(p, replay, stream);
+    case 3: return launch_cont<3>(p, replay, stream);
+    case 4: return launch_cont<4>(p, replay, stream);
+    case 8: return launch_cont<8>(p, replay, stream);
+    default:
+        set_error("continuous MH is compiled for dim in {1,2,3,4,8}, got %d", h->dim);
+        return MMC_ERR_UNSUPPORTED;
+    }
+}
+
+int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_dev, const mmc_replay_mh *rp,
+                cudaStream_t stream) {
+    MhPoissonParams p{};
+    p.state = (uint64_t *)h->d_state;
+    p.out = out_dev;
+    p.flip = rp ? rp->flip : nullptr;
+    p.u = rp ? rp->u : nullptr;
+    p.lnfact = h->d_lnfact;
+    p.thr_up = h->d_thr_up;
+    p.thr_dn = h->d_thr_dn;
+    p.table_len = h->table_len;
+    p.lambda = h->target.params[0];
+    p.ln_lambda = h->ln_lambda;
+    p.ln_half = h->ln_half;
+    p.chains = h->chains;
+    p.chain_offset = h->chain_offset;
+    p.step_base = h->step;
+    p.n_collect = n_collect;
+    p.n_discard = n_discard;
+    p.key = seed_key(h->seed);
+    p.error_flag = h->d_error;
+    const bool replay = rp && rp->flip && rp->u;
+    MMC_REQUIRE(!rp || replay, "Poisson MH replay needs both flip and u tapes");
+    const int block = kPoisWarps * 32;
+    const int64_t warps = (h->chains + 31) / 32;
+    const unsigned grid = (unsigned)((warps + kPoisWarps - 1) / kPoisWarps);
+    const size_t smem = (size_t)h->table_len * 16 + (size_t)kPoisWarps * 32 * kPoisPitch * sizeof(uint16_t);
+    auto launch = [&](auto kernel) -> int {
+        MMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, block, smem, stream>>>(p);
+        MMC_CUDA(cudaGetLastError());
+        return MMC_OK;
+    };
+    const bool thr = h->accept_mode != 0;
+    if (replay) return thr ? launch(mh_poisson_kernel<true, true>) : launch(mh_poisson_kernel<true, false>);
+    return thr ? launch(mh_poisson_kernel<false, true>) : launch(mh_poisson_kernel<false, false>);
+}
+
+int check_error_flag(mmc_mh *h, cudaStream_t stream) {
+    if (!h->d_error) return MMC_OK;
+    int32_t flag = 0;
+    MMC_CUDA(cudaMemcpyAsync(&flag, h->d_error, sizeof(flag), cudaMemcpyDeviceToHost, stream));
+    MMC_CUDA(cudaStreamSynchronize(stream));
+    if (flag) {
+        set_error("Poisson MH: a chain left the tabulated state range [0, %d)", h->table_len - 1);
+        return MMC_ERR_OVERFLOW;
+    }
+    return MMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmc_mh_create(mmc_mh **out, const mmc_target_desc *target, const mmc_proposal_desc *proposal,
+                  const void *init_host, int64_t chains, int32_t dim, int32_t state_dtype) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(out && target && proposal && init_host && chains > 0 && dim > 0, "mmc_mh_create: bad arguments");
+    const bool poisson = target->kind == MMC_T_POISSON;
+    if (poisson) {
+        MMC_REQUIRE(proposal->kind == MMC_Q_NONNEG_RW && state_dtype == MMC_U64 && dim == 1,
+                    "Poisson target needs the nonnegative random-walk proposal, u64 state and dim 1");
+    } else {
+        MMC_REQUIRE(target->kind == MMC_T_GAUSSIAN2D || target->kind == MMC_T_ISO_GAUSSIAN,
+                    "MH target kind %d is not a built-in MH target", target->kind);
+        MMC_REQUIRE(proposal->kind == MMC_Q_ISO_GAUSSIAN && state_dtype == MMC_F64,
+                    "continuous MH needs the IsotropicGaussian proposal and f64 state");
+        MMC_REQUIRE(target->kind != MMC_T_GAUSSIAN2D || dim == 2, "Gaussian2D needs dim 2");
+        MMC_REQUIRE(proposal->param > 0.0, "proposal std must be > 0");
+    }
+    mmc_mh *h = new mmc_mh();
+    h->target = *target;
+    h->proposal = *proposal;
+    h->chains = chains;
+    h->dim = dim;
+    h->dtype = state_dtype;
+    auto fail = [&](int code) { mmc_mh_destroy(h); return code; };
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    const size_t bytes = (size_t)chains * dim * elem_size(state_dtype);
+    e = cudaMalloc(&h->d_state, bytes);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(state)", __FILE__, __LINE__));
+    e = cudaMemcpy(h->d_state, init_host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy(state)", __FILE__, __LINE__));
+    if (poisson) {
+        rc = build_poisson_tables(h);
+        if (rc) return fail(rc);
+    }
+    *out = h;
+    return MMC_OK;
+}
+
+int mmc_mh_seed(mmc_mh *h, uint64_t seed) {
+    MMC_REQUIRE(h, "null handle");
+    h->seed = seed;
+    h->step = 0;
+    return MMC_OK;
+}
+
+int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset) {
+    MMC_REQUIRE(h && offset >= 0, "bad chain offset");
+    h->chain_offset = offset;
+    return MMC_OK;
+}
+
+int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode) {
+    MMC_REQUIRE(h && (mode == 0 || mode == 1), "accept mode must be 0 or 1");
+    h->accept_mode = mode;
+    return MMC_OK;
+}
+
+int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, const mmc_replay_mh *replay_dev,
+                   void *stream) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_mh_run_dev: bad arguments");
+    MMC_REQUIRE(out_dev || n_collect == 0, "mmc_mh_run_dev: out is null");
+    int rc;
+    if (h->target.kind == MMC_T_POISSON)
+        rc = run_poisson(h, n_collect, n_discard, (uint64_t *)out_dev, replay_dev, (cudaStream_t)stream);
+    else
+        rc = run_cont(h, n_collect, n_discard, (double *)out_dev, replay_dev, (cudaStream_t)stream);
+    if (rc) return rc;
+    h->step += n_collect + n_discard;
+    return MMC_OK;
+}
+
+int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
+    const int64_t steps = n_collect + n_discard;
+    const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * 8;
+    int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 8);
+    if (rc) return rc;
+    mmc_replay_mh dev_rp{};
+    const mmc_replay_mh *rp = nullptr;
+    if (replay) {
+        const bool poisson = h->target.kind == MMC_T_POISSON;
+        const size_t n_u = (size_t)h->chains * steps;
+        if (poisson) {
+            MMC_REQUIRE(replay->flip && replay->u, "Poisson MH replay needs flip and u");
+            if ((rc = grow(&h->d_replay[0], &h->d_replay_bytes[0], n_u ? n_u : 1))) return rc;
+            MMC_CUDA(cudaMemcpyAsync(h->d_replay[0], replay->flip, n_u, cudaMemcpyHostToDevice, h->stream));
+            dev_rp.flip = (const uint8_t *)h->d_replay[0];
+        } else {
+            MMC_REQUIRE(replay->noise && replay->u, "MH replay needs noise and u");
+            const size_t nb = n_u * h->dim * 8;
+            if ((rc = grow(&h->d_replay[0], &h->d_replay_bytes[0], nb ? nb : 8))) return rc;
+            MMC_CUDA(cudaMemcpyAsync(h->d_replay[0], replay->noise, nb, cudaMemcpyHostToDevice, h->stream));
+            dev_rp.noise = (const double *)h->d_replay[0];
+            if (replay->trace) {
+                if ((rc = grow((void **)&h->d_trace, &h->d_trace_bytes, n_u * 4 * 8))) return rc;
+                dev_rp.trace = h->d_trace;
+            }
+        }
+        if ((rc = grow(&h->d_replay[1], &h->d_replay_bytes[1], n_u ? n_u * 8 : 8))) return rc;
+        MMC_CUDA(cudaMemcpyAsync(h->d_replay[1], replay->u, n_u * 8, cudaMemcpyHostToDevice, h->stream));
+        dev_rp.u = (const double *)h->d_replay[1];
+        rp = &dev_rp;
+    }
+    rc = mmc_mh_run_dev(h, n_collect, n_discard, h->d_out, rp, h->stream);
+    if (rc) return rc;
+    if (out_bytes) MMC_CUDA(cudaMemcpyAsync(out_host, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (rp && rp->trace)
+        MMC_CUDA(cudaMemcpyAsync(replay->trace, h->d_trace, (size_t)h->chains * steps * 4 * 8, cudaMemcpyDeviceToHost,
+                                 h->stream));
+    MMC_CUDA(cudaStreamSynchronize(h->stream));
+    return check_error_flag(h, h->stream);
+}
+
+int mmc_mh_get_state(mmc_mh *h, void *state_host) {
+    MMC_REQUIRE(h && state_host, "mmc_mh_get_state: bad arguments");
+    MMC_CUDA(cudaMemcpy(state_host, h->d_state, (size_t)h->chains * h->dim * 8, cudaMemcpyDeviceToHost));
+    return check_error_flag(h, h->stream);
+}
+
+int mmc_mh_set_state(mmc_mh *h, const void *state_host) {
+    MMC_REQUIRE(h && state_host, "mmc_mh_set_state: bad arguments");
+    MMC_CUDA(cudaMemcpy(h->d_state, state_host, (size_t)h->chains * h->dim * 8, cudaMemcpyHostToDevice));
+    if (h->d_error) MMC_CUDA(cudaMemset(h->d_error, 0, sizeof(int32_t)));
+    return MMC_OK;
+}
+
+void mmc_mh_destroy(mmc_mh *h) {
+    if (!h) return;
+    cudaFree(h->d_state);
+    cudaFree(h->d_lnfact);
+    cudaFree(h->d_thr_up);
+    cudaFree(h->d_thr_dn);
+    cudaFree(h->d_error);
+    cudaFree(h->d_out);
+    for (auto p : h->d_replay) cudaFree(p);
+    cudaFree(h->d_trace);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""Targets and proposals mirroring `mini_mcmc::distributions` (src/distributions.rs) and the example
+targets of the reference (examples/poisson_mh.rs).  Each object is a small descriptor; the arithmetic
+lives in the analytic device functors of csrc/mmc_targets.cuh / mmc_mh.cuh."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+
+class _Target:
+    kind = 0
+    dim = 0
+
+    def _params(self):
+        return ()
+
+    def _vec(self):
+        return None
+
+    def _mat(self):
+        return None
+
+    def desc(self) -> L.TargetDesc:
+        d = L.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        for i, v in enumerate(self._params()):
+            d.params[i] = float(v)
+        self._keep = (self._vec(), self._mat())
+        if self._keep[0] is not None:
+            d.vec = self._keep[0].ctypes.data_as(C.POINTER(C.c_float))
+        if self._keep[1] is not None:
+            d.mat = self._keep[1].ctypes.data_as(C.POINTER(C.c_float))
+        return d
+
+
+@dataclass
+class Gaussian2D(_Target):
+    """Gaussian2D { mean, cov }, src/distributions.rs:159-206 (MH target, f64)."""
+    mean: np.ndarray
+    cov: np.ndarray
+    kind = L.T_GAUSSIAN2D
+    dim = 2
+
+    def _params(self):
+        m = np.asarray(self.mean, dtype=np.float64).reshape(2)
+        c = np.asarray(self.cov, dtype=np.float64).reshape(2, 2)
+        return (m[0], m[1], c[0, 0], c[0, 1], c[1, 0], c[1, 1])
+
+
+class IsotropicGaussian(_Target):
+    """IsotropicGaussian::new(std), src/distributions.rs:346-402: MH proposal (any dim) and target."""
+    kind = L.T_ISO_GAUSSIAN
+
+    def __init__(self, std: float, dim: int = 0):
+        self.std = float(std)
+        self.dim = dim
+        self._seed = None
+
+    @classmethod
+    def new(cls, std):
+        return cls(std)
+
+    def set_seed(self, seed: int):
+        # kept for API parity (src/distributions.rs:388-391); device noise is Philox keyed by the sampler seed
+        self._seed = int(seed)
+        return self
+
+    def _params(self):
+        return (self.std,)
+
+    def proposal_desc(self) -> L.ProposalDesc:
+        return L.ProposalDesc(L.Q_ISO_GAUSSIAN, self.std)
+
+
+@dataclass
+class PoissonTarget(_Target):
+    """PoissonTarget { lambda }, examples/poisson_mh.rs:10-26 (usize state)."""
+    lam: float
+    kind = L.T_POISSON
+    dim = 1
+
+    def _params(self):
+        return (self.lam,)
+
+
+class NonnegativeProposal:
+    """NonnegativeProposal, examples/poisson_mh.rs:28-77."""
+
+    def set_seed(self, seed):
+        return self
+
+    def proposal_desc(self) -> L.ProposalDesc:
+        return L.ProposalDesc(L.Q_NONNEG_RW, 0.0)
+
+
+class RosenbrockND(_Target):
+    """RosenbrockND {}, src/distributions.rs:527-547; dim is taken from the initial positions."""
+    kind = L.T_ROSENBROCK_ND
+
+    def __init__(self, dim: int = 0):
+        self.dim = dim
+
+
+@dataclass
+class Rosenbrock2D(_Target):
+    """Rosenbrock2D { a, b }, src/distributions.rs:491-524."""
+    a: float
+    b: float
+    kind = L.T_ROSENBROCK_2D
+    dim = 2
+
+    def _params(self):
+        return (self.a, self.b)
+
+
+class DiffableGaussian2D(_Target):
+    """DiffableGaussian2D::new(mean, cov), src/distributions.rs:213-316."""
+    kind = L.T_DIFF_GAUSSIAN2D
+    dim = 2
+
+    def __init__(self, mean, cov):
+        self.mean = np.asarray(mean, dtype=np.float64).reshape(2)
+        self.cov = np.asarray(cov, dtype=np.float64).reshape(2, 2)
+
+    new = classmethod(lambda cls, mean, cov: cls(mean, cov))
+
+    def _params(self):
+        c = self.cov
+        return (self.mean[0], self.mean[1], c[0, 0], c[0, 1], c[1, 0], c[1, 1])
+
+
+class StandardNormalTarget(_Target):
+    """test-only target of src/nuts.rs:1024-1037."""
+    kind = L.T_STD_NORMAL
+
+    def __init__(self, dim: int = 0):
+        self.dim = dim
+
+
+class DenseGaussian(_Target):
+    """D-dimensional Gaussian with dense covariance (BASELINE config C4): the D-dim generalisation of
+    DiffableGaussian2D::unnorm_logp_batch (src/distributions.rs:262-288).  The precision matrix is
+    computed on the host in f64 and cast to f32, like `inv_cov` in DiffableGaussian2D::new."""
+    kind = L.T_DENSE_GAUSSIAN
+
+    def __init__(self, mean, cov=None, precision=None):
+        self.mean = np.ascontiguousarray(mean, dtype=np.float32)
+        self.dim = int(self.mean.shape[0])
+        if precision is None:
+            cov = np.asarray(cov, dtype=np.float64)
+            precision = np.linalg.inv(cov)
+            sign, logdet = np.linalg.slogdet(cov)
+        else:
+            precision = np.asarray(precision, dtype=np.float64)
+            sign, logdet = np.linalg.slogdet(precision)
+            logdet = -logdet
+        precision = 0.5 * (precision + precision.T)
+        self.precision = np.ascontiguousarray(precision, dtype=np.float32)
+        self.norm_const = float(-0.5 * (self.dim * np.log(2.0 * np.pi) + logdet))
+
+    def _params(self):
+        return (self.norm_const,)
+
+    def _vec(self):
+        return self.mean
+
+    def _mat(self):
+        return self.precision

@@ -1,0 +1,93 @@
+"""`MetropolisHastings` mirroring src/metropolis_hastings.rs + the ChainRunner trait (src/core.rs:152-366),
+backed by the fused device kernels of csrc/mmc_mh.cuh through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .distributions import PoissonTarget
+
+
+class MetropolisHastings:
+    """MetropolisHastings::new(target, proposal, initial_states) — one chain per initial state
+    (src/metropolis_hastings.rs:149-159).  `.seed(s)` (…:187-193) keys the device Philox streams."""
+
+    def __init__(self, target, proposal, initial_states):
+        self.target, self.proposal = target, proposal
+        poisson = isinstance(target, PoissonTarget)
+        self._np_dtype = np.uint64 if poisson else np.float64
+        init = np.ascontiguousarray(initial_states, dtype=self._np_dtype)
+        if init.ndim != 2:
+            raise ValueError("initial_states must be [chains, dim]")
+        self.n_chains, self.dim = init.shape
+        if getattr(target, "dim", 0) == 0:
+            target.dim = self.dim
+        self._h = C.c_void_p()
+        tdesc, qdesc = target.desc(), proposal.proposal_desc()
+        L.check(L.lib.mmc_mh_create(C.byref(self._h), C.byref(tdesc), C.byref(qdesc), L.vp(init),
+                                    C.c_int64(self.n_chains), C.c_int32(self.dim),
+                                    C.c_int32(L.MMC_U64 if poisson else L.MMC_F64)))
+
+    new = classmethod(lambda cls, target, proposal, initial_states: cls(target, proposal, initial_states))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            L.lib.mmc_mh_destroy(self._h)
+            self._h = None
+
+    def seed(self, seed: int):
+        L.check(L.lib.mmc_mh_seed(self._h, C.c_uint64(seed)))
+        return self
+
+    def set_chain_offset(self, offset: int):
+        L.check(L.lib.mmc_mh_set_chain_offset(self._h, C.c_int64(offset)))
+        return self
+
+    def set_accept_mode(self, mode: int):
+        L.check(L.lib.mmc_mh_set_accept_mode(self._h, C.c_int32(mode)))
+        return self
+
+    # -- ChainRunner::run, src/core.rs:176-186
+    def run(self, n_collect: int, n_discard: int, replay=None, out=None, trace=None) -> np.ndarray:
+        """Returns the sample [chains, n_collect, dim] as a host array.  `replay` = dict(noise=, u=) or
+        dict(flip=, u=) of host arrays shaped [chains, steps(, dim)]."""
+        if out is None:
+            out = np.empty((self.n_chains, n_collect, self.dim), dtype=self._np_dtype)
+        rp = None
+        if replay is not None:
+            self._keep = {k: np.ascontiguousarray(v) for k, v in replay.items()}
+            rp = L.ReplayMH(L.vp(self._keep.get("noise")), L.vp(self._keep.get("u")), L.vp(self._keep.get("flip")),
+                            L.vp(trace))
+        L.check(L.lib.mmc_mh_run(self._h, C.c_int64(n_collect), C.c_int64(n_discard), L.vp(out),
+                                 C.byref(rp) if rp is not None else None))
+        return out
+
+    def run_device(self, n_collect: int, n_discard: int, replay=None, out=None):
+        """Same as run() but the sample stays in HBM: returns a torch tensor on the current CUDA device."""
+        import torch
+
+        tdt = torch.int64 if self._np_dtype == np.uint64 else torch.float64
+        if out is None:
+            out = torch.empty((self.n_chains, n_collect, self.dim), dtype=tdt, device="cuda")
+        rp = None
+        if replay is not None:
+            self._keep = replay
+            rp = L.ReplayMH(L.vp(replay.get("noise")), L.vp(replay.get("u")), L.vp(replay.get("flip")),
+                            L.vp(replay.get("trace")))
+        L.check(L.lib.mmc_mh_run_dev(self._h, C.c_int64(n_collect), C.c_int64(n_discard), L.vp(out),
+                                     C.byref(rp) if rp is not None else None, L.current_stream_ptr()))
+        return out
+
+    def run_progress(self, n_collect: int, n_discard: int):
+        """ChainRunner::run_progress, src/core.rs:208-360: (sample, RunStats)."""
+        from .stats import RunStats
+
+        sample = self.run(n_collect, n_discard)
+        return sample, RunStats.from_sample(sample)
+
+    def current_state(self) -> np.ndarray:
+        st = np.empty((self.n_chains, self.dim), dtype=self._np_dtype)
+        L.check(L.lib.mmc_mh_get_state(self._h, L.vp(st)))
+        return st

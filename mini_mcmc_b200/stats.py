@@ -1,0 +1,100 @@
+"""`mini_mcmc::stats` surface: split_rhat_mean_ess, RunStats, BasicStats (src/stats.rs:310-423),
+computed on the device (csrc/mmc_stats.cu); cross-GPU sums go through torch.distributed (NCCL)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class BasicStats:
+    """BasicStats, src/stats.rs:373-392."""
+    name: str
+    min: float
+    median: float
+    max: float
+    mean: float
+    std: float
+
+    def __str__(self):
+        return (f"{self.name} in [{self.min:.2f}, {self.max:.2f}], median: {self.median:.2f}, "
+                f"mean: {self.mean:.2f} ± {self.std:.2f}")
+
+
+def basic_stats(name: str, data) -> BasicStats:
+    """basic_stats, src/stats.rs:310-336 (descending sort, median = data[len/2], std ddof=1)."""
+    d = np.ascontiguousarray(data, dtype=np.float32)
+    out = L.BasicStats()
+    L.check(L.lib.mmc_basic_stats_of(L.vp(d), C.c_int64(d.shape[0]), C.byref(out)))
+    return BasicStats(name, out.min, out.median, out.max, out.mean, out.std)
+
+
+def _as_device_f32(sample):
+    import torch
+
+    if isinstance(sample, np.ndarray):
+        sample = torch.from_numpy(np.ascontiguousarray(sample))
+    return sample.to(device="cuda", dtype=torch.float32).contiguous()
+
+
+def split_rhat_mean_ess(sample, group=None):
+    """split_rhat_mean_ess(sample [c, n, p]) -> (rhat[p], ess[p]) as numpy f32 (src/stats.rs:416-423).
+
+    `sample` may be a host array or a CUDA tensor (kept in HBM).  If torch.distributed is initialised and
+    `group` is not False, `sample` is this rank's shard of the chains and the per-parameter moment sums and
+    summed autocovariances are all-reduced (NCCL over NVLink) before every rank finalises."""
+    import torch
+    import torch.distributed as dist
+
+    x = _as_device_f32(sample)
+    c, n, p = x.shape
+    sharded = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rhat = np.empty(p, dtype=np.float32)
+    ess = np.empty(p, dtype=np.float32)
+    if not sharded:
+        L.check(L.lib.mmc_split_rhat_ess_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), L.vp(rhat), L.vp(ess),
+                                             L.current_stream_ptr()))
+        return rhat, ess
+    c_total = torch.tensor([c], dtype=torch.int64, device="cuda")
+    dist.all_reduce(c_total, group=group)
+    c_total = int(c_total.item())
+    N = n // 2
+    plen = int(L.lib.mmc_stats_partial_len(C.c_int64(n), C.c_int64(p)))
+    partial = torch.zeros(plen, dtype=torch.float64, device="cuda")
+    have, block = 0, 16
+    while have < N:
+        want = min(block, N - have)
+        L.check(L.lib.mmc_stats_partial_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), C.c_int64(have),
+                                            C.c_int64(want), L.vp(partial), L.current_stream_ptr()))
+        lo = 0 if have == 0 else (2 + have) * p
+        hi = (2 + have + want) * p
+        dist.all_reduce(partial[lo:hi], group=group)  # the only collective of the whole engine
+        have += want
+        host = partial.cpu().numpy()
+        rc = L.lib.mmc_stats_finalize(L.vp(host), C.c_int64(c_total), C.c_int64(n), C.c_int64(p), C.c_int64(have),
+                                      L.vp(rhat), L.vp(ess))
+        if rc < 0:
+            L.check(rc)
+        if rc == 0:
+            break
+        block *= 2
+    return rhat, ess
+
+
+@dataclass
+class RunStats:
+    """RunStats { ess, rhat }, src/stats.rs:339-371."""
+    ess: BasicStats
+    rhat: BasicStats
+
+    @classmethod
+    def from_sample(cls, sample, group=None) -> "RunStats":
+        rhat, ess = split_rhat_mean_ess(sample, group=group)
+        return cls(basic_stats("ESS", ess), basic_stats("Split R-hat", rhat))
+
+    def __str__(self):
+        return f"{self.ess}\n{self.rhat}"

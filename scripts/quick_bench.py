@@ -1,0 +1,65 @@
+"""Development micro-benchmarks (not the driver's bench.py): device-resident timings of the main kernels."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mini_mcmc_b200 as mm  # noqa: E402
+
+
+def ev_time(fn, warm=1, reps=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), ts
+
+
+def poisson(chains=1 << 20, n_collect=9000, n_discard=1000, mode=1):
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    mh = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(42).set_accept_mode(mode)
+    out = torch.empty((chains, n_collect, 1), dtype=torch.int64, device="cuda")
+    ms, ts = ev_time(lambda: mh.run_device(n_collect, n_discard, out=out))
+    tr = chains * (n_collect + n_discard)
+    print(json.dumps(dict(k="poisson", mode=mode, chains=chains, n_collect=n_collect, ms=ms, all=ts,
+                          transitions_per_s=tr / ms * 1e3, write_GBs=chains * n_collect * 8 / ms / 1e6)))
+
+
+def hmc(chains=262144, L=50, n_collect=400, n_discard=50):
+    init = mm.init_device(chains, 3, 42).cpu().numpy()
+    h = mm.HMC(mm.RosenbrockND(), init, 0.01, L).set_seed(1)
+    out = torch.empty((chains, n_collect, 3), dtype=torch.float32, device="cuda")
+    ms, ts = ev_time(lambda: h.run_device(n_collect, n_discard, out=out), warm=1, reps=2)
+    tr = chains * (n_collect + n_discard)
+    print(json.dumps(dict(k="hmc_rosen3", chains=chains, L=L, ms=ms, all=ts, transitions_per_s=tr / ms * 1e3,
+                          grad_evals_per_s=tr * (L + 1) / ms * 1e3, tflops=tr * 2442 / ms / 1e9)))
+
+
+def stats(c=65536, n=400, p=100):
+    x = torch.randn((c, n, p), device="cuda")
+    ms, ts = ev_time(lambda: mm.split_rhat_mean_ess(x))
+    print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["poisson", "hmc", "stats"]
+    print(torch.cuda.get_device_name(0))
+    if "poisson" in which:
+        poisson(mode=1)
+        poisson(mode=0)
+        poisson(n_collect=10000, n_discard=0, mode=1)
+    if "hmc" in which:
+        hmc()
+    if "stats" in which:
+        stats()

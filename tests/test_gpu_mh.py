@@ -1,0 +1,153 @@
+"""Parity of the CUDA Metropolis-Hastings path (K1) against the oracle, through the C ABI."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mm(cuda_device):
+    import mini_mcmc_b200 as m
+
+    return m
+
+
+# ------------------------------------------------------------------ config C1: Gaussian2D, f64
+def test_c1_minimal_mh_replay_reference_streams(mm):
+    """examples/minimal_mh.rs: 4 chains x (1000 + 100), fed with the reference's own SmallRng streams
+    (proposal noise incl. the D+1 draw quirk, accept uniforms from SmallRng(1 + seed + i))."""
+    chains, n_collect, n_discard, D = 4, 1000, 100, 2
+    noise, u = oracle.mh_cont_reference_tape(42, 42, chains, n_collect + n_discard, D)
+    init = oracle.init_det(chains, D)
+    tp = [0.0, 0.0, 1.0, 0.0, 0.0, 1.0]
+    exp, exp_state, exp_trace = oracle.mh_cont_run_replay(oracle.T_GAUSSIAN2D, tp, 1.0, init, n_collect, n_discard,
+                                                          noise, u, want_trace=True)
+    mh = mm.MetropolisHastings(mm.Gaussian2D([0.0, 0.0], [[1.0, 0.0], [0.0, 1.0]]), mm.IsotropicGaussian(1.0),
+                               mm.init_det(chains, D))
+    trace = np.zeros((chains, n_collect + n_discard, 4))
+    got = mh.run(n_collect, n_discard, replay=dict(noise=noise, u=u), trace=trace)
+    assert got.shape == (chains, n_collect, D)
+    # accept decisions identical, states / log-probs within 1e-12 relative (fp64 tolerance of north_star)
+    np.testing.assert_array_equal(trace[..., 3], exp_trace[..., 3])
+    np.testing.assert_allclose(trace[..., :3], exp_trace[..., :3], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got, exp, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(mh.current_state(), exp_state, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("kind,D", [("gauss", 2), ("iso", 3), ("iso", 1)])
+def test_mh_cont_replay_random_tapes(mm, kind, D):
+    rng = np.random.default_rng(7)
+    chains, n_collect, n_discard = 257, 40, 13
+    steps = n_collect + n_discard
+    noise = rng.normal(size=(chains, steps, D))
+    u = rng.random((chains, steps))
+    u[0, 0] = 0.0  # ln(0) = -inf must accept
+    init = rng.normal(size=(chains, D))
+    if kind == "gauss":
+        tgt, tp, okind = mm.Gaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]]), [0.0, 1.0, 4.0, 2.0, 2.0, 3.0], oracle.T_GAUSSIAN2D
+    else:
+        tgt, tp, okind = mm.IsotropicGaussian(1.7, dim=D), [1.7], oracle.T_ISO_GAUSSIAN
+    exp, exp_state, _ = oracle.mh_cont_run_replay(okind, tp, 0.8, init, n_collect, n_discard, noise, u)
+    mh = mm.MetropolisHastings(tgt, mm.IsotropicGaussian(0.8), init)
+    got = mh.run(n_collect, n_discard, replay=dict(noise=noise, u=u))
+    np.testing.assert_allclose(got, exp, rtol=1e-12, atol=0)
+    # continuation: a second run keeps going from the stored state
+    noise2 = rng.normal(size=(chains, 5, D))
+    u2 = rng.random((chains, 5))
+    exp2, _, _ = oracle.mh_cont_run_replay(okind, tp, 0.8, exp_state, 5, 0, noise2, u2)
+    got2 = mh.run(5, 0, replay=dict(noise=noise2, u=u2))
+    np.testing.assert_allclose(got2, exp2, rtol=1e-12, atol=0)
+
+
+def test_mh_gaussian2d_native_distribution(mm):
+    """src/metropolis_hastings.rs:338-401 bounds (mean +-0.3, cov +-0.5) on the native Philox path."""
+    mh = mm.MetropolisHastings(mm.Gaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]]), mm.IsotropicGaussian(1.0),
+                               mm.init_det(64, 2)).seed(42)
+    s = mh.run(2000, 500).reshape(-1, 2)
+    assert np.abs(s.mean(axis=0) - [0.0, 1.0]).max() < 0.3
+    assert np.abs(np.cov(s.T) - [[4.0, 2.0], [2.0, 3.0]]).max() < 0.5
+
+
+# ------------------------------------------------------------------ config C2: Poisson, integer state
+@pytest.mark.parametrize("mode", [0, 1])
+def test_poisson_replay_bit_exact(mm, mode):
+    """Integer MH must match the oracle bit for bit under replayed flips/uniforms (both accept modes)."""
+    chains, n_collect, n_discard = 1000, 300, 37  # ragged: not multiples of the warp / tile sizes
+    steps = n_collect + n_discard
+    # the reference's accept stream: chain i <- SmallRng(1 + seed + i); flips: SmallRng(seed) per chain
+    u = np.stack([oracle.SmallRng(1 + 42 + i).f64(steps) for i in range(chains)])
+    flip = np.stack([oracle.SmallRng(1000 + i).bool_half(steps) for i in range(chains)])
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    exp, exp_state = oracle.mh_poisson_run_replay(4.0, init[:, 0], n_collect, n_discard, flip, u)
+    mh = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).set_accept_mode(mode)
+    got = mh.run(n_collect, n_discard, replay=dict(flip=flip, u=u))
+    assert got.dtype == np.uint64 and got.shape == (chains, n_collect, 1)
+    np.testing.assert_array_equal(got, exp)
+    np.testing.assert_array_equal(mh.current_state()[:, 0], exp_state)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_poisson_native_philox_bit_exact(mm, mode):
+    """Native Philox keying (seed, global chain, step) has an integer twin in the oracle: bit-exact,
+    including chain offsets (GPU-count invariance) and continuation across run() calls."""
+    chains, n_collect, n_discard = 4099, 130, 21
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    exp, exp_state = oracle.mh_poisson_run_philox(4.0, init[:, 0], n_collect, n_discard, seed=1234, chain_offset=77)
+    mh = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(1234)
+    mh.set_chain_offset(77).set_accept_mode(mode)
+    got = mh.run(n_collect, n_discard)
+    np.testing.assert_array_equal(got, exp)
+    exp2, _ = oracle.mh_poisson_run_philox(4.0, exp_state, 33, 0, seed=1234, chain_offset=77,
+                                           step_base=n_collect + n_discard)
+    got2 = mh.run(33, 0)
+    np.testing.assert_array_equal(got2, exp2)
+
+
+def test_poisson_sharding_invariance(mm):
+    """Two shards with chain offsets reproduce the single-GPU result exactly."""
+    chains = 2048
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    full = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(5).run(100, 10)
+    a = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init[:1000]).seed(5).run(100, 10)
+    b = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init[1000:]).seed(5)
+    b = b.set_chain_offset(1000).run(100, 10)
+    np.testing.assert_array_equal(np.concatenate([a, b]), full)
+
+
+def test_poisson_pmf(mm):
+    """tests/metrohast_poisson_test.rs:90-130: empirical pmf within 0.05 for k = 0..10."""
+    init = np.zeros((4096, 1), dtype=np.uint64)
+    s = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(42).run(500, 2000)
+    ks = s.reshape(-1)
+    for k in range(11):
+        pmf = math.exp(-4.0 + k * math.log(4.0) - math.lgamma(k + 1))
+        assert abs((ks == k).mean() - pmf) < 0.01
+
+
+def test_poisson_large_device_resident_properties(mm):
+    """Full-width launch (1,048,576 chains) with the draws left in HBM: size-independent properties —
+    every transition moves by at most 1, values stay in range, the pmf is right, and a spot-check of
+    rows against the oracle's Philox twin."""
+    import torch
+
+    chains, n_collect, n_discard = 1 << 20, 128, 64
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    mh = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(99)
+    out = mh.run_device(n_collect, n_discard)[:, :, 0]
+    assert out.shape == (chains, n_collect)
+    d = (out[:, 1:] - out[:, :-1]).abs()
+    assert int(d.max()) <= 1 and int(out.min()) >= 0 and int(out.max()) < 64
+    last = out[:, -1].float()
+    assert abs(float(last.mean()) - 4.0) < 0.02 and abs(float(last.var()) - 4.0) < 0.05
+    rows = [0, 1, 31, 32, 12345, chains - 1]
+    exp, _ = oracle.mh_poisson_run_philox(4.0, np.zeros(1, dtype=np.uint64), n_collect, n_discard, seed=99,
+                                          chain_offset=0)
+    np.testing.assert_array_equal(out[0].cpu().numpy().astype(np.uint64), exp[0, :, 0])
+    for r in rows[1:]:
+        e, _ = oracle.mh_poisson_run_philox(4.0, np.zeros(1, dtype=np.uint64), n_collect, n_discard, seed=99,
+                                            chain_offset=r)
+        np.testing.assert_array_equal(out[r].cpu().numpy().astype(np.uint64), e[0, :, 0])

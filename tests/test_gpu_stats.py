@@ -1,0 +1,89 @@
+"""Parity of the on-device split-Rhat / ESS (K5) against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mm(cuda_device):
+    import mini_mcmc_b200 as m
+
+    return m
+
+
+def _ar1(rng, c, n, p, phi, offset=0.0):
+    x = np.zeros((c, n, p), dtype=np.float64)
+    e = rng.normal(size=(c, n, p))
+    x[:, 0] = e[:, 0]
+    for t in range(1, n):
+        x[:, t] = phi * x[:, t - 1] + np.sqrt(1 - phi * phi) * e[:, t]
+    return (x + offset).astype(np.float32)
+
+
+@pytest.mark.parametrize("c,n,p,phi,offset", [
+    (4, 1000, 1, 0.0, 0.0),      # iid, FFT path in the reference (N = 500 > 100)
+    (6, 200, 5, 0.5, 3.0),       # brute-force path (N = 100)
+    (8, 400, 100, 0.3, -50.0),   # C5 row shape, large mean (shift robustness)
+    (3, 51, 33, 0.9, 0.0),       # odd n (middle draw dropped), p not a multiple of 32, slow mixing
+    (16, 600, 7, 0.97, 10.0),    # needs many lags
+])
+def test_split_rhat_ess_matches_oracle(mm, c, n, p, phi, offset):
+    rng = np.random.default_rng(c * 1000 + n)
+    x = _ar1(rng, c, n, p, phi, offset)
+    x[1] += 0.3  # make chains disagree a little so Rhat is not trivially 1
+    exp_rhat, exp_ess = oracle.split_rhat_mean_ess(x)
+    rhat, ess = mm.split_rhat_mean_ess(x)
+    np.testing.assert_allclose(rhat, exp_rhat, rtol=1e-4)
+    np.testing.assert_allclose(ess, exp_ess, rtol=2e-3)   # north_star budget is 2 %
+
+
+def test_ess_1_reference_thresholds(mm):
+    # src/stats.rs:810-834
+    data = oracle.SmallRng(42).f32(4000).reshape(4, 1000, 1)
+    st = mm.RunStats.from_sample(data)
+    assert st.ess.min > 3800.0 and st.rhat.max < 1.01
+    assert abs(st.ess.min - 4110.47) < 5.0
+    assert "ESS in [" in str(st)
+
+
+def test_sharded_partials_sum_to_full(mm):
+    """The sharded protocol (partials per rank, summed, finalised) equals the single-call result."""
+    import ctypes as C
+
+    import torch
+
+    from mini_mcmc_b200 import _lib as L
+
+    rng = np.random.default_rng(5)
+    c, n, p = 10, 300, 40
+    x = _ar1(rng, c, n, p, 0.6, 1.0)
+    full_rhat, full_ess = mm.split_rhat_mean_ess(x)
+    plen = int(L.lib.mmc_stats_partial_len(C.c_int64(n), C.c_int64(p)))
+    total = torch.zeros(plen, dtype=torch.float64, device="cuda")
+    lags = 64
+    for lo, hi in ((0, 3), (3, 10)):
+        xs = torch.from_numpy(x[lo:hi].copy()).cuda()
+        part = torch.zeros(plen, dtype=torch.float64, device="cuda")
+        L.check(L.lib.mmc_stats_partial_dev(L.vp(xs), C.c_int64(hi - lo), C.c_int64(n), C.c_int64(p), C.c_int64(0),
+                                            C.c_int64(lags), L.vp(part), L.current_stream_ptr()))
+        total += part
+    host = total.cpu().numpy()
+    rhat = np.empty(p, dtype=np.float32)
+    ess = np.empty(p, dtype=np.float32)
+    rc = L.lib.mmc_stats_finalize(L.vp(host), C.c_int64(c), C.c_int64(n), C.c_int64(p), C.c_int64(lags), L.vp(rhat),
+                                  L.vp(ess))
+    assert rc == 0
+    np.testing.assert_allclose(rhat, full_rhat, rtol=1e-6)
+    np.testing.assert_allclose(ess, full_ess, rtol=1e-5)
+
+
+def test_basic_stats_matches_oracle(mm):
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=101).astype(np.float32)
+    got = mm.basic_stats("x", d)
+    exp = oracle.basic_stats(d)
+    for k in ("min", "median", "max", "mean", "std"):
+        assert abs(getattr(got, k) - exp[k]) <= 1e-6 * max(1.0, abs(exp[k]))
