@@ -10,9 +10,10 @@ from .distributions import (DenseGaussian, DiffableGaussian2D, Gaussian2D, Isotr
                             PoissonTarget, Rosenbrock2D, RosenbrockND, StandardNormalTarget)
 from .hmc import HMC
 from .metropolis_hastings import MetropolisHastings
+from .nuts import NUTS
 from .stats import BasicStats, RunStats, basic_stats, split_rhat_mean_ess
 
-__all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "Gaussian2D",
+__all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "NUTS", "Gaussian2D",
            "IsotropicGaussian", "PoissonTarget", "NonnegativeProposal", "RosenbrockND", "Rosenbrock2D",
            "DiffableGaussian2D", "DenseGaussian", "StandardNormalTarget", "RunStats", "BasicStats", "basic_stats",
            "split_rhat_mean_ess"]

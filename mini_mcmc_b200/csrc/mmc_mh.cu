@@ -21,7 +21,7 @@ struct mmc_mh {
     // Poisson tables
     int32_t table_len = 0;
     double *d_lnfact = nullptr;
-    uint64_t *d_thr_up = nullptr, *d_thr_dn = nullptr;
+    uint2 *d_lim = nullptr;  // [table_len][2]: accept iff bits <= lim[k][up]
     int32_t *d_error = nullptr;
     double ln_lambda = 0, ln_half = 0;
     // host-API staging
@@ -82,24 +82,29 @@ int build_poisson_tables(mmc_mh *h) {
         lnfact[k] = k < 2 ? 0.0 : acc;
         lp[k] = -lambda + (double)k * h->ln_lambda - lnfact[k];
     }
-    std::vector<uint64_t> up(len, 0), dn(len, 0);
+    // lim[k][dir] = (thr << 11) - 1 so that  u53 < thr  <=>  bits <= lim  (thr = 2^53 -> all ones = always).
+    // thr = 0 would wrap to "always"; it only occurs for moves that are never proposed (k = 0 down) and at
+    // the clamped table end, where the proposal equals the current state.
+    std::vector<uint2> lim(2 * len, make_uint2(0u, 0u));
+    auto encode = [](uint64_t thr) {
+        const uint64_t v = thr == 0 ? 0 : ((thr >= (1ULL << 53)) ? ~0ULL : (thr << 11) - 1);
+        return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+    };
     for (int64_t k = 0; k + 1 < len; ++k) {
         // x = k -> y = k + 1 : q_f = (k == 0 ? 0 : ln 1/2), q_b = ln 1/2
         const double qf = k == 0 ? 0.0 : h->ln_half, qb = h->ln_half;
-        up[k] = accept_threshold((lp[k + 1] + qb) - (lp[k] + qf));
+        lim[2 * k + 1] = encode(accept_threshold((lp[k + 1] + qb) - (lp[k] + qf)));
         if (k >= 1) {
             // x = k -> y = k - 1 : q_f = ln 1/2, q_b = (y == 0 ? 0 : ln 1/2)
             const double qb2 = (k - 1 == 0) ? 0.0 : h->ln_half;
-            dn[k] = accept_threshold((lp[k - 1] + qb2) - (lp[k] + h->ln_half));
+            lim[2 * k] = encode(accept_threshold((lp[k - 1] + qb2) - (lp[k] + h->ln_half)));
         }
     }
     MMC_CUDA(cudaMalloc(&h->d_lnfact, len * sizeof(double)));
-    MMC_CUDA(cudaMalloc(&h->d_thr_up, len * sizeof(uint64_t)));
-    MMC_CUDA(cudaMalloc(&h->d_thr_dn, len * sizeof(uint64_t)));
+    MMC_CUDA(cudaMalloc(&h->d_lim, 2 * len * sizeof(uint2)));
     MMC_CUDA(cudaMalloc(&h->d_error, sizeof(int32_t)));
     MMC_CUDA(cudaMemcpy(h->d_lnfact, lnfact.data(), len * sizeof(double), cudaMemcpyHostToDevice));
-    MMC_CUDA(cudaMemcpy(h->d_thr_up, up.data(), len * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    MMC_CUDA(cudaMemcpy(h->d_thr_dn, dn.data(), len * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaMemcpy(h->d_lim, lim.data(), 2 * len * sizeof(uint2), cudaMemcpyHostToDevice));
     MMC_CUDA(cudaMemset(h->d_error, 0, sizeof(int32_t)));
     return MMC_OK;
 }
@@ -158,8 +163,7 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     p.flip = rp ? rp->flip : nullptr;
     p.u = rp ? rp->u : nullptr;
     p.lnfact = h->d_lnfact;
-    p.thr_up = h->d_thr_up;
-    p.thr_dn = h->d_thr_dn;
+    p.lim = h->d_lim;
     p.table_len = h->table_len;
     p.lambda = h->target.params[0];
     p.ln_lambda = h->ln_lambda;
@@ -169,7 +173,15 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     p.step_base = h->step;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
-    p.key = seed_key(h->seed);
+    {
+        uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            p.rk[2 * r] = k0;
+            p.rk[2 * r + 1] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
     p.error_flag = h->d_error;
     const bool replay = rp && rp->flip && rp->u;
     MMC_REQUIRE(!rp || replay, "Poisson MH replay needs both flip and u tapes");
@@ -335,8 +347,7 @@ void mmc_mh_destroy(mmc_mh *h) {
     if (!h) return;
     cudaFree(h->d_state);
     cudaFree(h->d_lnfact);
-    cudaFree(h->d_thr_up);
-    cudaFree(h->d_thr_dn);
+    cudaFree(h->d_lim);
     cudaFree(h->d_error);
     cudaFree(h->d_out);
     for (auto p : h->d_replay) cudaFree(p);

@@ -1,0 +1,208 @@
+// NUTS C ABI (see include/minimcmc.h) — host side of K4.
+#include <vector>
+
+#include "mmc_nuts_inst.cuh"
+
+using namespace mmc;
+
+struct mmc_nuts {
+    mmc_target_desc target{};
+    int64_t chains = 0;
+    int32_t dim = 0;
+    double target_accept = 0.8;
+    int32_t scalar_dtype = MMC_F64;
+    int32_t max_depth = 10;
+    int64_t chain_offset = 0;
+    uint64_t seed = 0;
+    int32_t exact = 0;
+    float *d_pos = nullptr;
+    double *d_state = nullptr;            // [chains, 5]
+    unsigned long long *d_counters = nullptr;  // [8 + 32]
+    float *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaStream_t stream = nullptr;
+    float *d_out = nullptr;
+    size_t d_out_bytes = 0;
+    double *d_tape[3] = {nullptr, nullptr, nullptr};
+    size_t d_tape_bytes[3] = {0, 0, 0};
+};
+
+namespace {
+
+constexpr int kCounters = 8 + 32;
+
+template <class T>
+int grow(T **ptr, size_t *cap, size_t need) {
+    if (*cap >= need) return MMC_OK;
+    if (*ptr) MMC_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    MMC_CUDA(cudaMalloc((void **)ptr, need));
+    *cap = need;
+    return MMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmc_nuts_create(mmc_nuts **out, const mmc_target_desc *target, const float *init_host, int64_t chains,
+                    int32_t dim, double target_accept_p, int32_t scalar_dtype, int32_t max_depth) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(out && target && init_host && chains > 0 && dim > 0, "mmc_nuts_create: bad arguments");
+    MMC_REQUIRE(target->dim == dim, "target dim %d != dim %d", target->dim, dim);
+    MMC_REQUIRE(scalar_dtype == MMC_F32 || scalar_dtype == MMC_F64, "scalar dtype must be MMC_F32 or MMC_F64");
+    if (max_depth <= 0) max_depth = 10;
+    MMC_REQUIRE(max_depth <= 16, "max_depth %d > 16", max_depth);
+    mmc_nuts *h = new mmc_nuts();
+    h->target = *target;
+    h->chains = chains;
+    h->dim = dim;
+    h->target_accept = target_accept_p;
+    h->scalar_dtype = scalar_dtype;
+    h->max_depth = max_depth;
+    auto fail = [&](cudaError_t e, const char *what) {
+        int code = cuda_fail(e, what, __FILE__, __LINE__);
+        mmc_nuts_destroy(h);
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    const size_t bytes = (size_t)chains * dim * sizeof(float);
+    if ((e = cudaMalloc((void **)&h->d_pos, bytes)) != cudaSuccess) return fail(e, "cudaMalloc(positions)");
+    if ((e = cudaMemcpy(h->d_pos, init_host, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "memcpy");
+    // NUTSChain::new, src/nuts.rs:410-434: epsilon = -1 (unset), epsilon_bar = 1, h_bar = 0, mu = ln 10, m = 0
+    std::vector<double> st((size_t)chains * 5);
+    for (int64_t c = 0; c < chains; ++c) {
+        st[c * 5 + 0] = -1.0; st[c * 5 + 1] = 1.0; st[c * 5 + 2] = 0.0; st[c * 5 + 3] = std::log(10.0); st[c * 5 + 4] = 0.0;
+    }
+    if ((e = cudaMalloc((void **)&h->d_state, st.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(state)");
+    if ((e = cudaMemcpy(h->d_state, st.data(), st.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "memcpy");
+    if ((e = cudaMalloc((void **)&h->d_counters, kCounters * 8)) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
+    if ((e = cudaMemset(h->d_counters, 0, kCounters * 8)) != cudaSuccess) return fail(e, "memset");
+    *out = h;
+    return MMC_OK;
+}
+
+int mmc_nuts_set_seed(mmc_nuts *h, uint64_t seed) {
+    MMC_REQUIRE(h, "null handle");
+    h->seed = seed;
+    return MMC_OK;
+}
+
+int mmc_nuts_set_chain_offset(mmc_nuts *h, int64_t offset) {
+    MMC_REQUIRE(h && offset >= 0, "bad chain offset");
+    h->chain_offset = offset;
+    return MMC_OK;
+}
+
+int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact) {
+    MMC_REQUIRE(h, "null handle");
+    h->exact = exact ? 1 : 0;
+    return MMC_OK;
+}
+
+int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress, float *out_dev,
+                     const mmc_replay_nuts *rp, void *stream) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_nuts_run_dev: bad arguments");
+    MMC_REQUIRE(out_dev || n_collect == 0, "mmc_nuts_run_dev: out is null");
+    const bool replay = rp && rp->normals && rp->exps && rp->unifs;
+    MMC_REQUIRE(!rp || replay, "NUTS replay needs normals, exps and unifs tapes");
+    cudaStream_t s = (cudaStream_t)stream;
+    NutsParams p{};
+    p.positions = h->d_pos;
+    p.out = out_dev;
+    p.state = h->d_state;
+    if (replay) {
+        p.normals = rp->normals; p.exps = rp->exps; p.unifs = rp->unifs;
+        p.cap_normals = rp->cap_normals; p.cap_exps = rp->cap_exps; p.cap_unifs = rp->cap_unifs;
+    }
+    p.counters = h->d_counters;
+    p.chains = h->chains;
+    p.chain_offset = h->chain_offset;
+    p.n_collect = n_collect;
+    p.n_discard = n_discard;
+    p.progress = progress ? 1 : 0;
+    p.max_depth = h->max_depth;
+    p.D = h->dim;
+    p.target_accept = h->target_accept;
+    p.key = seed_key(h->seed);
+    NutsLaunch L{h->target, h->scalar_dtype == MMC_F64, replay, sm_count()};
+    auto dispatch = h->exact ? nuts_dispatch_exact : nuts_dispatch_fast;
+    int64_t grid = 0;
+    size_t scratch_floats = 0;
+    int rc = dispatch(L, p, &grid, &scratch_floats, true, s);
+    if (rc) return rc;
+    if ((rc = grow(&h->d_scratch, &h->scratch_bytes, scratch_floats * sizeof(float) + 16))) return rc;
+    p.scratch = h->d_scratch;
+    MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // next-chain ticket
+    return dispatch(L, p, &grid, &scratch_floats, false, s);
+}
+
+int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress, float *out_host,
+                 const mmc_replay_nuts *replay) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_nuts_run: bad arguments");
+    const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * sizeof(float);
+    int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 16);
+    if (rc) return rc;
+    mmc_replay_nuts dev_rp{};
+    const mmc_replay_nuts *rp = nullptr;
+    if (replay) {
+        MMC_REQUIRE(replay->normals && replay->exps && replay->unifs, "NUTS replay needs normals, exps and unifs");
+        const double *src[3] = {replay->normals, replay->exps, replay->unifs};
+        const int64_t cap[3] = {replay->cap_normals, replay->cap_exps, replay->cap_unifs};
+        for (int i = 0; i < 3; ++i) {
+            const size_t b = (size_t)h->chains * cap[i] * 8;
+            if ((rc = grow(&h->d_tape[i], &h->d_tape_bytes[i], b ? b : 8))) return rc;
+            MMC_CUDA(cudaMemcpyAsync(h->d_tape[i], src[i], b, cudaMemcpyHostToDevice, h->stream));
+        }
+        dev_rp = *replay;
+        dev_rp.normals = h->d_tape[0]; dev_rp.exps = h->d_tape[1]; dev_rp.unifs = h->d_tape[2];
+        rp = &dev_rp;
+    }
+    rc = mmc_nuts_run_dev(h, n_collect, n_discard, progress, h->d_out, rp, h->stream);
+    if (rc) return rc;
+    if (out_bytes) MMC_CUDA(cudaMemcpyAsync(out_host, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    MMC_CUDA(cudaStreamSynchronize(h->stream));
+    return MMC_OK;
+}
+
+int mmc_nuts_get_state(mmc_nuts *h, double *state_host) {
+    MMC_REQUIRE(h && state_host, "mmc_nuts_get_state: bad arguments");
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(state_host, h->d_state, (size_t)h->chains * 5 * 8, cudaMemcpyDeviceToHost));
+    return MMC_OK;
+}
+
+int mmc_nuts_get_positions(mmc_nuts *h, float *positions_host) {
+    MMC_REQUIRE(h && positions_host, "mmc_nuts_get_positions: bad arguments");
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(positions_host, h->d_pos, (size_t)h->chains * h->dim * sizeof(float), cudaMemcpyDeviceToHost));
+    return MMC_OK;
+}
+
+int mmc_nuts_get_counters(mmc_nuts *h, int64_t *n_grad, int64_t *n_transitions, int64_t *depth_hist, int32_t hist_len) {
+    MMC_REQUIRE(h, "null handle");
+    unsigned long long c[kCounters];
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    if (n_grad) *n_grad = (int64_t)c[1];
+    if (n_transitions) *n_transitions = (int64_t)c[2];
+    for (int i = 0; depth_hist && i < hist_len; ++i) depth_hist[i] = i < 32 ? (int64_t)c[8 + i] : 0;
+    return MMC_OK;
+}
+
+void mmc_nuts_destroy(mmc_nuts *h) {
+    if (!h) return;
+    cudaFree(h->d_pos);
+    cudaFree(h->d_state);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_scratch);
+    cudaFree(h->d_out);
+    for (auto p : h->d_tape) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,487 @@
+// K4: NUTS, one chain per warp (see include/minimcmc.h "NUTS").
+//
+// Reproduces NUTSChain::{init_chain, step, run, run_progress} (src/nuts.rs:457-691), build_tree (:764-946),
+// leapfrog (:979-996), stop_criterion (:963-977) and find_reasonable_epsilon (:695-761).
+//
+// Layout: the D-vector of a chain is blocked over the 32 lanes (lane l owns elements l*E .. l*E+E-1,
+// zero padded), so a leapfrog is E independent FMAs per lane plus two neighbour shuffles for the
+// Rosenbrock stencil, and every dot product (kinetic energy, U-turn test) is a 5-step butterfly.
+// Accept / U-turn / divergence decisions are warp-uniform, so the whole tree walk is divergence free
+// inside a warp; different chains (warps) take different numbers of leapfrogs without waiting for each
+// other (persistent warps pull chains from an atomic counter).
+//
+// build_tree is recursive in the reference; here it is the equivalent iterative binary-counter walk
+// (SURVEY.md appendix B1): after leaf #k the pending subtrees are merged once per trailing 1-bit of k,
+// drawing one f64 uniform per merge; a failed subtree (divergence or U-turn) still merges with every
+// pending sibling above it (set bits of k) and passes through unchanged where it is a first half, which is
+// exactly the RNG consumption and alpha / n_alpha accumulation of the recursion.  Only O(depth) states are
+// kept: per level the first leaf (x, p) and the current proposal x'.  Levels < kSmemLevels live in shared
+// memory, deeper (exponentially rarer) levels in an L2-resident per-warp scratch.
+#pragma once
+
+#include "mmc_common.cuh"
+#include "mmc_targets.cuh"
+
+namespace mmc {
+
+constexpr int kNutsSmemLevels = 3;
+constexpr int kNutsWarps = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <class A>
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = A::add(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- warp-form targets
+// interface: float logp_grad(const float (&x)[E], float (&g)[E], int lane) const  -> logp (same in all lanes)
+
+// RosenbrockND (src/distributions.rs:531-547) for any D <= 32 E.
+template <class A, int E>
+struct WRosenbrockND {
+    int D;
+    __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
+        const float xn = __shfl_down_sync(kFull, x[0], 1);
+        float t[E];
+        float acc = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane * E + e;
+            const bool valid = i + 1 < D;
+            const float xnext = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : xn;
+            const float tt = valid ? cms<A>(xnext, x[e], x[e]) : 0.0f;
+            const float u = valid ? A::sub(1.0f, x[e]) : 0.0f;
+            t[e] = tt;
+            acc = A::add(acc, A::mad(A::mul(tt, tt), 100.0f, A::mul(u, u)));
+            g[e] = A::mad(A::mul(400.0f, x[e]), tt, A::mul(2.0f, u));
+        }
+        float tprev = __shfl_up_sync(kFull, t[E - 1], 1);
+        if (lane == 0) tprev = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float tp = e == 0 ? tprev : t[e == 0 ? 0 : e - 1];
+            g[e] = A::add(A::mul(-200.0f, tp), g[e]);
+        }
+        return -warp_sum<A>(acc);
+    }
+};
+
+// StdNormal (src/nuts.rs:1024-1037) for any D <= 32 E (padding elements are zero).
+template <class A, int E>
+struct WStdNormal {
+    int D;
+    __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
+        float acc = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            acc = A::mad(A::mul(x[e], x[e]), 0.5f, acc);
+            g[e] = -x[e];
+        }
+        return -warp_sum<A>(acc);
+    }
+};
+
+// Any small thread-form target (kDim <= 4): every lane gathers the full vector and evaluates it.
+template <class T, int E>
+struct WSmall {
+    T t;
+    __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
+        constexpr int K = T::kDim;
+        float xf[K], gf[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) xf[i] = __shfl_sync(kFull, x[i % E], i / E);
+        const float lp = t.logp_grad(xf, gf);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            g[e] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (lane * E + e == i) g[e] = gf[i];
+        }
+        return lp;
+    }
+};
+
+// ---------------------------------------------------------------- scalar helpers (type T of the reference)
+__device__ __forceinline__ float s_exp(float v) { return expf(v); }
+__device__ __forceinline__ double s_exp(double v) { return exp(v); }
+__device__ __forceinline__ float s_log(float v) { return logf(v); }
+__device__ __forceinline__ double s_log(double v) { return log(v); }
+__device__ __forceinline__ float s_sqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double s_sqrt(double v) { return sqrt(v); }
+__device__ __forceinline__ float s_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double s_pow(double a, double b) { return pow(a, b); }
+
+struct NutsParams {
+    float *positions;       // [chains, D] in/out
+    float *out;             // [chains, n_collect, D]
+    double *state;          // [chains, 5] = epsilon, epsilon_bar, h_bar, mu, m   in/out
+    const double *normals, *exps, *unifs;  // replay tapes [chains, cap_*]
+    int64_t cap_normals, cap_exps, cap_unifs;
+    float *scratch;         // [resident warps][max_depth - kNutsSmemLevels][3][32 E]
+    unsigned long long *counters;  // [0] next chain, [1] n_grad, [2] n_transitions, [3] uniforms consumed, [8..] depth histogram
+    int64_t chains, chain_offset;
+    int64_t n_collect, n_discard;
+    int32_t progress, max_depth, D;
+    double target_accept;
+    uint2 key;
+};
+
+template <class Target, class A, class ST, int E, bool kReplay>
+struct NutsWarp {
+    const Target &tgt;
+    const NutsParams &p;
+    const int lane;
+    float *s_stack;      // shared: [kNutsSmemLevels][3][32 E] for this warp
+    float *g_stack;      // global scratch for deeper levels
+    // RNG state
+    uint64_t gchain = 0;
+    int64_t chain = 0;
+    uint32_t step_word = 0;
+    uint32_t q = 0;           // uniforms consumed in this step
+    uint32_t q_batch = 0xffffffffu;
+    uint4 ubatch;
+    int64_t cur_n = 0, cur_e = 0, cur_u = 0;  // replay cursors
+    unsigned long long n_grad = 0, n_unif = 0;
+
+    __device__ NutsWarp(const Target &t, const NutsParams &pp, int ln, float *ss, float *gs)
+        : tgt(t), p(pp), lane(ln), s_stack(ss), g_stack(gs) {}
+
+    __device__ __forceinline__ float *level_ptr(int lvl, int which) {
+        constexpr int V = 32 * E;
+        return lvl < kNutsSmemLevels ? s_stack + (lvl * 3 + which) * V + lane * E
+                                     : g_stack + ((lvl - kNutsSmemLevels) * 3 + which) * V + lane * E;
+    }
+
+    // ---- random draws (native Philox keying is documented in minimcmc.h)
+    __device__ __forceinline__ void draw_normals(float (&m)[E]) {
+        if (kReplay) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = lane * E + e;
+                m[e] = i < p.D ? (float)p.normals[chain * p.cap_normals + cur_n + i] : 0.0f;
+            }
+            cur_n += p.D;
+        } else {
+            if (E == 4) {
+                const uint4 w = philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step_word, (uint32_t)lane));
+                float n[4];
+                box_muller_f32(w.x, w.y, n[0], n[1]);
+                box_muller_f32(w.z, w.w, n[2], n[3]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) m[e] = (lane * E + e < p.D) ? n[e & 3] : 0.0f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = lane * E + e;
+                    const uint4 w = philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step_word, (uint32_t)(i >> 2)));
+                    float n0, n1;
+                    if ((i & 2) == 0) box_muller_f32(w.x, w.y, n0, n1); else box_muller_f32(w.z, w.w, n0, n1);
+                    m[e] = i < p.D ? ((i & 1) ? n1 : n0) : 0.0f;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ ST draw_exp1() {
+        if (kReplay) return (ST)p.exps[chain * p.cap_exps + cur_e++];
+        const uint4 w = philox_scalar_words(p.key, gchain, step_word);
+        return (ST)(-logf(u24_open(w.x)));
+    }
+    // next uniform of the step; f64 = 53-bit (tree merges), otherwise type T
+    __device__ __forceinline__ double draw_uniform(bool f64) {
+        ++n_unif;
+        if (kReplay) return p.unifs[chain * p.cap_unifs + cur_u++];
+        const uint32_t batch = q >> 6;
+        if (batch != q_batch) {  // 32 lanes x 2 uniforms per Philox batch
+            ubatch = philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step_word,
+                                                     kSubUnif + batch * 32 + (uint32_t)lane));
+            q_batch = batch;
+        }
+        const int src = (q >> 1) & 31;
+        const bool hi = q & 1;
+        const uint32_t lo = __shfl_sync(kFull, hi ? ubatch.z : ubatch.x, src);
+        const uint32_t hw = __shfl_sync(kFull, hi ? ubatch.w : ubatch.y, src);
+        ++q;
+        if (f64 || sizeof(ST) == 8) return u53_half_open(lo, hw);
+        return (double)u24_half_open(hw);
+    }
+
+    // ---- leapfrog, src/nuts.rs:979-996 (in place); returns logp'
+    __device__ __forceinline__ float leapfrog(float (&x)[E], float (&m)[E], float (&g)[E], ST eps) {
+        const float e = (float)eps;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            m[k] = A::mad(A::mul(g[k], e), 0.5f, m[k]);
+            x[k] = A::mad(m[k], e, x[k]);
+        }
+        const float lp = tgt.logp_grad(x, g, lane);
+        ++n_grad;
+#pragma unroll
+        for (int k = 0; k < E; ++k) m[k] = A::mad(A::mul(g[k], e), 0.5f, m[k]);
+        return lp;
+    }
+    __device__ __forceinline__ float sumsq(const float (&m)[E]) {
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < E; ++k) s = A::mad(m[k], m[k], s);
+        return warp_sum<A>(s);
+    }
+    // stop_criterion, src/nuts.rs:963-977 (true = keep going)
+    __device__ __forceinline__ bool keep_going(const float (&xm)[E], const float (&xp)[E], const float (&pm)[E],
+                                               const float (&pp)[E]) {
+        float dm = 0.0f, dp = 0.0f;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const float diff = A::sub(xp[k], xm[k]);
+            dm = A::mad(diff, pm[k], dm);
+            dp = A::mad(diff, pp[k], dp);
+        }
+        dm = warp_sum<A>(dm);
+        dp = warp_sum<A>(dp);
+        return dm >= 0.0f && dp >= 0.0f;
+    }
+    __device__ __forceinline__ bool all_finite(const float (&v)[E]) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < E; ++k) ok = ok && isfinite(v[k]);
+        return __all_sync(kFull, ok);
+    }
+
+    // find_reasonable_epsilon, src/nuts.rs:695-761
+    __device__ ST find_reasonable_epsilon(const float (&x0)[E], const float (&m0)[E]) {
+        float g0[E], x[E], m[E], g[E];
+        const ST half = (ST)0.5;
+        ST epsilon = (ST)1.0;
+        const float ulogp = tgt.logp_grad(x0, g0, lane);
+        ++n_grad;
+        auto leap = [&](ST e) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) { x[k] = x0[k]; m[k] = m0[k]; g[k] = g0[k]; }
+            return leapfrog(x, m, g, e);
+        };
+        float ulogp_prime = leap(epsilon);
+        ST k = (ST)1.0;
+        while (!isfinite(ulogp_prime) && !all_finite(g)) {
+            k = k * half;
+            ulogp_prime = leap(epsilon * k);
+        }
+        epsilon = half * k * epsilon;
+        const float pp0 = sumsq(m0);
+        float lap_f = A::sub(A::sub(ulogp_prime, ulogp), A::mul(A::sub(sumsq(m), pp0), 0.5f));
+        ST lap = (ST)(double)lap_f;
+        const ST a = lap > s_log(half) ? (ST)1.0 : (ST)-1.0;
+        while (a * lap > -a * s_log((ST)2.0)) {
+            epsilon = epsilon * s_pow((ST)2.0, a);
+            ulogp_prime = leap(epsilon);
+            lap_f = A::sub(A::sub(ulogp_prime, ulogp), A::mul(A::sub(sumsq(m), pp0), 0.5f));
+            lap = (ST)(double)lap_f;
+        }
+        return epsilon;
+    }
+
+    // One doubling = build_tree(edge, v, j), src/nuts.rs:764-946, iteratively.
+    // cx/cm/cg: the edge to extend (in) and the new edge (out).  Outputs the subtree proposal, n', s', alpha, n_alpha.
+    __device__ void doubling(float (&cx)[E], float (&cm)[E], float (&cg)[E], int v, int j, ST logu, ST eps, ST joint0,
+                             float (&prop)[E], long long &n_out, bool &s_out, ST &alpha_out, long long &nalpha_out) {
+        const ST veps = (ST)v * eps;
+        const uint32_t n_leaves = 1u << j;
+        float tfx[E], tfm[E];  // first leaf of the subtree currently being merged upward
+        long long tn = 0, tna = 0;
+        ST ta = (ST)0.0;
+        bool ts = true;
+        for (uint32_t leaf = 0; leaf < n_leaves; ++leaf) {
+            const float lp = leapfrog(cx, cm, cg, veps);
+            const float joint_f = A::sub(lp, A::mul(sumsq(cm), 0.5f));
+            const ST joint = (ST)(double)joint_f;
+            tn = (logu < joint) ? 1 : 0;
+            ts = (logu - (ST)1000.0) < joint;
+            const ST ex = s_exp(joint - joint0);
+            ta = ((ST)1.0 < ex || ex != ex) ? (ST)1.0 : ex;  // T::min(1, e): NaN -> 1
+            tna = 1;
+#pragma unroll
+            for (int k = 0; k < E; ++k) { tfx[k] = cx[k]; tfm[k] = cm[k]; prop[k] = cx[k]; }
+            int lvl = 0;
+            bool pushed = false;
+            while (true) {
+                while (lvl < j && ((leaf >> lvl) & 1u)) {
+                    // merge pending first half A = stack[lvl] with the later half T
+                    const float *afx = level_ptr(lvl, 0), *afm = level_ptr(lvl, 1), *apr = level_ptr(lvl, 2);
+                    const long long an = s_n[lvl], ana = s_na[lvl];
+                    const ST aa = (ST)s_a[lvl];
+                    const double u = draw_uniform(true);
+                    long long denom = an + tn;
+                    if (denom < 1) denom = 1;
+                    const bool take_b = u < ((double)tn / (double)denom);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) {
+                        tfx[k] = afx[k];
+                        tfm[k] = afm[k];
+                        if (!take_b) prop[k] = apr[k];
+                    }
+                    tn += an;
+                    // s' = s'_1 && s'_2 && stop_criterion(minus, plus); pending halves always have s' = true
+                    if (ts) ts = (v == 1) ? keep_going(tfx, cx, tfm, cm) : keep_going(cx, tfx, cm, tfm);
+                    ta = aa + ta;
+                    tna += ana;
+                    ++lvl;
+                }
+                if (lvl == j) break;
+                if (ts) {  // park the finished first half at this level and build the next leaf
+                    float *afx = level_ptr(lvl, 0), *afm = level_ptr(lvl, 1), *apr = level_ptr(lvl, 2);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) { afx[k] = tfx[k]; afm[k] = tfm[k]; apr[k] = prop[k]; }
+                    s_n[lvl] = tn; s_na[lvl] = tna; s_a[lvl] = (double)ta;
+                    pushed = true;
+                    break;
+                }
+                ++lvl;  // failed first half: the parent returns it unchanged (src/nuts.rs:858)
+            }
+            if (!pushed) break;  // whole subtree of depth j is complete (or failed and fully unwound)
+        }
+        n_out = tn; s_out = ts; alpha_out = ta; nalpha_out = tna;
+    }
+
+    // per-level scalars of the pending halves (warp-uniform, kept in registers of every lane)
+    long long s_n[16], s_na[16];
+    double s_a[16];
+};
+
+template <class Target, class A, class ST, int E, bool kReplay>
+__global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target tgt, const NutsParams p) {
+    extern __shared__ __align__(16) float nuts_smem[];
+    constexpr int V = 32 * E;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s_stack = nuts_smem + warp * kNutsSmemLevels * 3 * V;
+    const int64_t warp_slot = (int64_t)blockIdx.x * kNutsWarps + warp;
+    const int n_glob = p.max_depth > kNutsSmemLevels ? p.max_depth - kNutsSmemLevels : 0;
+    float *g_stack = p.scratch + warp_slot * (int64_t)n_glob * 3 * V;
+    NutsWarp<Target, A, ST, E, kReplay> w(tgt, p, lane, s_stack, g_stack);
+    unsigned long long my_depth_count = 0, n_trans = 0;
+
+    while (true) {
+        long long c = 0;
+        if (lane == 0) c = (long long)atomicAdd(&p.counters[0], 1ULL);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= p.chains) break;
+        w.chain = c;
+        w.gchain = (uint64_t)(c + p.chain_offset);
+        w.cur_n = w.cur_e = w.cur_u = 0;
+
+        float pos[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int i = lane * E + k;
+            pos[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
+        }
+        double *st = p.state + c * 5;
+        ST epsilon = (ST)st[0], epsilon_bar = (ST)st[1], h_bar = (ST)st[2], mu;
+        long long m = (long long)st[4];
+        const ST gamma = (ST)0.05, kappa = (ST)0.75, delta = (ST)p.target_accept;
+        const long long t_0 = 10;
+
+        auto store_draw = [&](int64_t slot) {
+            float *o = p.out + (c * p.n_collect + slot) * p.D;
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const int i = lane * E + k;
+                if (i < p.D) o[i] = pos[k];
+            }
+        };
+
+        // ---- init_chain, src/nuts.rs:528-545
+        if (p.n_collect > 0) store_draw(0);
+        {
+            float m0[E];
+            w.step_word = 0;
+            w.q = 0; w.q_batch = 0xffffffffu;
+            w.draw_normals(m0);
+            ST d = epsilon + (ST)1.0;
+            if (d < (ST)0.0) d = -d;
+            const ST tiny = sizeof(ST) == 8 ? (ST)2.220446049250313e-16 : (ST)1.1920929e-07;
+            if (d <= tiny) epsilon = w.find_reasonable_epsilon(pos, m0);
+            mu = s_log((ST)10.0 * epsilon);
+        }
+
+        const int64_t total = p.n_collect + p.n_discard;
+        const int64_t first = p.progress ? 0 : 1;
+        for (int64_t it = first; it < total; ++it) {
+            // ---- NUTSChain::step, src/nuts.rs:550-691
+            m += 1;
+            w.step_word = (uint32_t)m;
+            w.q = 0; w.q_batch = 0xffffffffu;
+            float mom0[E], grad[E];
+            w.draw_normals(mom0);
+            const float ulogp = tgt.logp_grad(pos, grad, lane);
+            ++w.n_grad;
+            const float joint_f = A::sub(ulogp, A::mul(w.sumsq(mom0), 0.5f));
+            const ST joint = (ST)(double)joint_f;
+            const ST logu = joint - w.draw_exp1();
+            float xm[E], pm[E], gm[E], xp[E], pp[E], gp[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                xm[k] = xp[k] = pos[k];
+                pm[k] = pp[k] = mom0[k];
+                gm[k] = gp[k] = grad[k];
+            }
+            int j = 0;
+            long long n = 1;
+            bool s = true;
+            ST alpha = (ST)0.0;
+            long long n_alpha = 0;
+            while (s) {
+                const ST u1 = (ST)w.draw_uniform(false);
+                const int v = (u1 < (ST)0.5) ? 1 : -1;
+                float prop[E];
+                long long n_prime;
+                bool s_prime;
+                if (v == -1) w.doubling(xm, pm, gm, v, j, logu, epsilon, joint, prop, n_prime, s_prime, alpha, n_alpha);
+                else w.doubling(xp, pp, gp, v, j, logu, epsilon, joint, prop, n_prime, s_prime, alpha, n_alpha);
+                const ST ratio = (ST)n_prime / (ST)n;
+                const ST tmp = ((ST)1.0 < ratio) ? (ST)1.0 : ratio;
+                const ST u2 = (ST)w.draw_uniform(false);
+                if (s_prime && (u2 < tmp)) {
+#pragma unroll
+                    for (int k = 0; k < E; ++k) pos[k] = prop[k];
+                }
+                n += n_prime;
+                s = s_prime && w.keep_going(xm, xp, pm, pp);
+                j += 1;
+                if (j >= p.max_depth) s = false;
+            }
+            if (lane == (j < 31 ? j : 31)) ++my_depth_count;
+            ++n_trans;
+            // dual averaging, src/nuts.rs:676-690
+            ST eta = (ST)1.0 / (ST)(m + t_0);
+            h_bar = ((ST)1.0 - eta) * h_bar + eta * (delta - alpha / (ST)n_alpha);
+            if (m <= p.n_discard) {
+                const ST _m = (ST)m;
+                epsilon = s_exp(mu - s_sqrt(_m) / gamma * h_bar);
+                eta = s_pow(_m, -kappa);
+                epsilon_bar = s_exp(((ST)1.0 - eta) * s_log(epsilon_bar) + eta * s_log(epsilon));
+            } else {
+                epsilon = epsilon_bar;
+            }
+            const int64_t idx = p.progress ? it : it;  // run: m-th step fills slot m - n_discard; run_progress: i - n_discard
+            if (idx >= p.n_discard) store_draw(idx - p.n_discard);
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int i = lane * E + k;
+            if (i < p.D) p.positions[c * p.D + i] = pos[k];
+        }
+        if (lane == 0) {
+            st[0] = (double)epsilon; st[1] = (double)epsilon_bar; st[2] = (double)h_bar; st[3] = (double)mu;
+            st[4] = (double)m;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&p.counters[1], w.n_grad);
+        atomicAdd(&p.counters[2], n_trans);
+        atomicAdd(&p.counters[3], w.n_unif);
+    }
+    if (my_depth_count) atomicAdd(&p.counters[8 + lane], my_depth_count);
+}
+
+}  // namespace mmc

@@ -1,0 +1,117 @@
+"""`NUTS` mirroring src/nuts.rs (new / set_seed / run / run_progress), backed by the one-chain-per-warp
+tree-doubling kernel of csrc/mmc_nuts.cuh through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class NUTS:
+    """NUTS::new(target, initial_positions [n_chains][D], target_accept_p), src/nuts.rs:123-129.
+
+    scalar_dtype is the reference's type parameter T (epsilon, joint, log u, alpha): "f64" in the
+    reference's golden tests, "f32" in examples/minimal_nuts.rs.  max_depth caps the number of tree
+    doublings (the reference is unbounded)."""
+
+    def __init__(self, target, initial_positions, target_accept_p: float, scalar_dtype: str = "f32",
+                 max_depth: int = 10):
+        init = np.ascontiguousarray(initial_positions, dtype=np.float32)
+        if init.ndim != 2:
+            raise ValueError("initial_positions must be [chains, dim]")
+        self.target = target
+        self.n_chains, self.dim = init.shape
+        self.max_depth = max_depth
+        if getattr(target, "dim", 0) == 0:
+            target.dim = self.dim
+        self._h = C.c_void_p()
+        tdesc = target.desc()
+        sd = {"f32": L.MMC_F32, "f64": L.MMC_F64}[scalar_dtype]
+        L.check(L.lib.mmc_nuts_create(C.byref(self._h), C.byref(tdesc), L.vp(init), C.c_int64(self.n_chains),
+                                      C.c_int32(self.dim), C.c_double(target_accept_p), C.c_int32(sd),
+                                      C.c_int32(max_depth)))
+
+    new = classmethod(lambda cls, target, initial_positions, target_accept_p, **kw:
+                      cls(target, initial_positions, target_accept_p, **kw))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            L.lib.mmc_nuts_destroy(self._h)
+            self._h = None
+
+    def set_seed(self, seed: int):
+        L.check(L.lib.mmc_nuts_set_seed(self._h, C.c_uint64(seed)))
+        return self
+
+    def set_chain_offset(self, offset: int):
+        L.check(L.lib.mmc_nuts_set_chain_offset(self._h, C.c_int64(offset)))
+        return self
+
+    def set_exact(self, exact: bool):
+        L.check(L.lib.mmc_nuts_set_exact(self._h, C.c_int32(int(exact))))
+        return self
+
+    @staticmethod
+    def _replay_struct(replay):
+        normals, exps, unifs = replay
+        return L.ReplayNUTS(L.vp(normals), normals.shape[1], L.vp(exps), exps.shape[1], L.vp(unifs), unifs.shape[1])
+
+    def _run(self, n_collect, n_discard, progress, replay, out):
+        if out is None:
+            out = np.empty((self.n_chains, n_collect, self.dim), dtype=np.float32)
+        rp = None
+        if replay is not None:
+            self._keep = tuple(np.ascontiguousarray(t, dtype=np.float64) for t in replay)
+            rp = self._replay_struct(self._keep)
+        L.check(L.lib.mmc_nuts_run(self._h, C.c_int64(n_collect), C.c_int64(n_discard), C.c_int32(progress), L.vp(out),
+                                   C.byref(rp) if rp is not None else None))
+        return out
+
+    def run(self, n_collect: int, n_discard: int, replay=None, out=None) -> np.ndarray:
+        """NUTS::run, src/nuts.rs:163-170 (+ NUTSChain::run :457-471: n_collect + n_discard - 1 steps, slot 0 of
+        a run without burn-in holds the starting position).  replay = (normals, exps, unifs) per-chain tapes."""
+        return self._run(n_collect, n_discard, 0, replay, out)
+
+    def run_device(self, n_collect: int, n_discard: int, progress: bool = True, replay=None, out=None):
+        import torch
+
+        if out is None:
+            out = torch.empty((self.n_chains, n_collect, self.dim), dtype=torch.float32, device="cuda")
+        rp = None
+        if replay is not None:
+            self._keep = replay
+            rp = self._replay_struct(replay)
+        L.check(L.lib.mmc_nuts_run_dev(self._h, C.c_int64(n_collect), C.c_int64(n_discard), C.c_int32(int(progress)),
+                                       L.vp(out), C.byref(rp) if rp is not None else None, L.current_stream_ptr()))
+        return out
+
+    def run_progress(self, n_collect: int, n_discard: int, replay=None, group=None):
+        """NUTS::run_progress, src/nuts.rs:194-338: n_collect + n_discard steps, returns (sample, RunStats);
+        the statistics are computed on the device (and all-reduced across ranks when sharded)."""
+        from .stats import RunStats
+
+        if replay is not None:
+            sample = self._run(n_collect, n_discard, 1, replay, None)
+        else:
+            sample = self.run_device(n_collect, n_discard, progress=True)
+        return sample, RunStats.from_sample(sample, group=group)
+
+    def state(self) -> np.ndarray:
+        """[chains, 5] = epsilon, epsilon_bar, h_bar, mu, m (NUTSChain fields, src/nuts.rs:361-390)."""
+        st = np.empty((self.n_chains, 5), dtype=np.float64)
+        L.check(L.lib.mmc_nuts_get_state(self._h, L.vp(st)))
+        return st
+
+    @property
+    def positions(self) -> np.ndarray:
+        out = np.empty((self.n_chains, self.dim), dtype=np.float32)
+        L.check(L.lib.mmc_nuts_get_positions(self._h, L.vp(out)))
+        return out
+
+    def counters(self):
+        g, t = C.c_int64(), C.c_int64()
+        hist = (C.c_int64 * 32)()
+        L.check(L.lib.mmc_nuts_get_counters(self._h, C.byref(g), C.byref(t), hist, 32))
+        return dict(n_grad=g.value, n_transitions=t.value, depth_hist=list(hist)[: self.max_depth + 1])

@@ -47,7 +47,15 @@ def hmc(chains=262144, L=50, n_collect=400, n_discard=50):
 
 
 def stats(c=65536, n=400, p=100):
+    import ctypes as C
+    from mini_mcmc_b200 import _lib as L
     x = torch.randn((c, n, p), device="cuda")
+    plen = int(L.lib.mmc_stats_partial_len(C.c_int64(n), C.c_int64(p)))
+    part = torch.zeros(plen, dtype=torch.float64, device="cuda")
+    for lag0 in (0, 16):
+        ms1, _ = ev_time(lambda: L.check(L.lib.mmc_stats_partial_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p),
+                         C.c_int64(lag0), C.c_int64(16), L.vp(part), L.current_stream_ptr())))
+        print(json.dumps(dict(k="stats_one_pass", lag0=lag0, ms=ms1, read_GBs=c * n * p * 4 / ms1 / 1e6)))
     ms, ts = ev_time(lambda: mm.split_rhat_mean_ess(x))
     print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
 

@@ -1,0 +1,136 @@
+"""Parity of the warp-per-chain CUDA NUTS (K4) against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+CHAIN_2 = [-1.168318748474121, -0.4077277183532715, -1.8463939428329468, 0.19176559150218964,
+           -1.0662782192230225, -0.3948383331298828]
+CHAIN_3 = [2.653707265853882, 5.560618877410889, 2.9760334491729736, 6.325948715209961, 2.187873125076294,
+           5.611990928649902, 2.1512224674224854, 5.416507720947266, 2.4165120124816895, 3.9120564460754395]
+
+
+@pytest.fixture(scope="module")
+def mm(cuda_device):
+    import mini_mcmc_b200 as m
+
+    return m
+
+
+def _record(otgt, init, delta, n_collect, n_discard, seed, **kw):
+    return oracle.nuts_run(otgt, init, delta, n_collect, n_discard, seed=seed, record=True, **kw)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_golden_chain_3_replayed_reference_stream(mm, exact):
+    """src/nuts.rs:1164-1222 (test_chain_3 / test_run_1): the reference's own SmallRng(42) draws (recorded by
+    the oracle) replayed into the CUDA kernel reproduce the reference's golden sample (rel 1e-5 / abs 1e-6)."""
+    init = [[-2.0, 1.0]]
+    rec = _record(oracle.diff_gaussian2d([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, 5, 5, 41)
+    s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype="f64",
+                max_depth=16).set_exact(exact)
+    got = s.run(5, 5, replay=rec["tapes"])
+    assert got.shape == (1, 5, 2)
+    np.testing.assert_allclose(got.reshape(-1), CHAIN_3, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(s.state()[0, :4], rec["state"][0, :4], rtol=1e-5)
+
+
+def test_golden_chain_2_and_chain_1(mm):
+    # src/nuts.rs:1138-1162 and :1123-1136
+    tgt = lambda: mm.DiffableGaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
+    otgt = oracle.diff_gaussian2d([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
+    rec = _record(otgt, [[0.0, 1.0]], 0.8, 3, 3, 41)
+    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64", max_depth=16).set_exact(True).run(3, 3, replay=rec["tapes"])
+    np.testing.assert_allclose(got.reshape(-1), CHAIN_2, rtol=1e-5, atol=1e-6)
+    rec = _record(otgt, [[0.0, 1.0]], 0.8, 1, 0, 41)
+    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64").run(1, 0, replay=rec["tapes"])
+    np.testing.assert_allclose(got.reshape(-1), [0.0, 1.0], rtol=1e-5, atol=1e-6)
+
+
+def test_find_reasonable_epsilon_kat(mm):
+    # src/nuts.rs:1049-1055: x = [0,1], p = [1,0], standard normal -> epsilon = 2.0; the first normals tape
+    # entries are the init_chain momentum.
+    normals = np.array([[1.0, 0.0, 0.3, -0.2]])
+    exps = np.array([[0.5]])
+    unifs = np.full((1, 64), 0.25)
+    s = mm.NUTS(mm.StandardNormalTarget(), [[0.0, 1.0]], 0.8, scalar_dtype="f64")
+    s.run(1, 0, replay=(normals, exps, unifs))
+    st = s.state()[0]
+    assert st[0] == 2.0 and abs(st[3] - np.log(20.0)) < 1e-12 and st[4] == 0
+
+
+@pytest.mark.parametrize("progress", [False, True])
+@pytest.mark.parametrize("scalar", ["f64", "f32"])
+def test_multi_chain_replay_matches_oracle(mm, progress, scalar):
+    """Many chains, run and run_progress semantics, both scalar types: the iterative device tree must
+    consume the tapes exactly like the recursive reference (same draws, same accepted states)."""
+    rng = np.random.default_rng(5)
+    chains, n_collect, n_discard = 64, 12, 8
+    init = (rng.normal(size=(chains, 2)) + [1.0, 2.0]).astype(np.float32)
+    otgt = oracle.diff_gaussian2d([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]])
+    rec = _record(otgt, init, 0.8, n_collect, n_discard, 7, progress=progress, scalar_f32=(scalar == "f32"))
+    s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype=scalar,
+                max_depth=16).set_exact(True)
+    got = s._run(n_collect, n_discard, int(progress), rec["tapes"], None)
+    ok = np.isclose(got, rec["out"], rtol=1e-4, atol=1e-5).all(axis=(1, 2))
+    assert ok.mean() >= 0.95, f"only {ok.mean():.3f} of chains follow the oracle"
+    st = s.state()
+    np.testing.assert_allclose(st[ok, 4], rec["state"][ok, 4])
+    np.testing.assert_allclose(st[ok, 0], rec["state"][ok, 0], rtol=1e-3)
+    c = s.counters()
+    assert c["n_transitions"] == chains * (n_collect + n_discard - (0 if progress else 1))
+    assert abs(c["n_grad"] - rec["n_grad"].sum()) <= 0.05 * rec["n_grad"].sum()
+
+
+@pytest.mark.parametrize("D", [2, 10, 100])
+def test_rosenbrock_nd_replay_matches_oracle(mm, D):
+    """RosenbrockND as a GradientTarget (config C5 widens examples/minimal_nuts.rs to D = 100): both lane
+    layouts (E = 1 for D <= 32, E = 4 above)."""
+    rng = np.random.default_rng(D)
+    chains, n_collect, n_discard = 24, 6, 6
+    init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
+    rec = _record(oracle.rosenbrock_nd(D), init, 0.95, n_collect, n_discard, 3, progress=True, scalar_f32=True,
+                  max_depth=8, cap_unifs=40000)
+    s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=8).set_exact(True)
+    got = s._run(n_collect, n_discard, 1, rec["tapes"], None)
+    # f32 reductions are ordered differently on the device (butterfly vs sequential), so individual chains may
+    # legitimately take a different branch at a near-tie; most must agree to 1e-4
+    ok = np.isclose(got, rec["out"], rtol=1e-3, atol=1e-4).all(axis=(1, 2))
+    assert ok.mean() >= 0.75, f"only {ok.mean():.3f} of chains follow the oracle"
+    first = np.isclose(got[:, 0], rec["out"][:, 0], rtol=1e-3, atol=1e-4).all(axis=1)
+    assert first.mean() >= 0.9
+
+
+def test_native_nuts_distribution_and_adaptation(mm):
+    """Native Philox path on the golden Gaussian: posterior moments within Monte-Carlo error, step size
+    adapted so that the acceptance statistic approaches the target, Rhat ~ 1 (device stats)."""
+    chains = 2048
+    rng = np.random.default_rng(0)
+    init = rng.normal(size=(chains, 2)).astype(np.float32)
+    s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype="f32").set_seed(11)
+    sample, stats = s.run_progress(200, 200)
+    x = sample.cpu().numpy().reshape(-1, 2).astype(np.float64)
+    assert np.abs(x.mean(axis=0) - [1.0, 2.0]).max() < 0.05
+    assert np.abs(np.cov(x.T) - [[1.0, 2.0], [2.0, 5.0]]).max() < 0.25
+    assert abs(stats.rhat.mean - 1.0) < 0.02
+    st = s.state()
+    assert (st[:, 4] == 400).all() and (st[:, 0] > 0.01).all() and (st[:, 0] < 5.0).all()
+    c = s.counters()
+    assert c["n_transitions"] == chains * 400 and sum(c["depth_hist"]) == chains * 400
+    # GPU-count invariance: two shards with chain offsets reproduce the same draws
+    a = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[:1000], 0.8).set_seed(11)
+    b = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[1000:], 0.8).set_seed(11).set_chain_offset(1000)
+    both = np.concatenate([a.run_device(20, 20).cpu().numpy(), b.run_device(20, 20).cpu().numpy()])
+    full = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8).set_seed(11)
+    np.testing.assert_array_equal(both, full.run_device(20, 20).cpu().numpy())
+
+
+def test_minimal_nuts_example_shape(mm):
+    # examples/minimal_nuts.rs: Rosenbrock2D(1, 100), 4 chains, delta = 0.95, run_progress(400, 400) -> [4, 400, 2]
+    init = mm.init_det(4, 2).astype(np.float32)
+    s = mm.NUTS(mm.Rosenbrock2D(1.0, 100.0), init, 0.95).set_seed(42)
+    sample, stats = s.run_progress(400, 400)
+    assert tuple(sample.shape) == (4, 400, 2)
+    assert np.isfinite(sample.cpu().numpy()).all() and np.isfinite(stats.ess.min)
