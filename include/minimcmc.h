@@ -24,8 +24,10 @@
  *   counter = (global_chain_lo, global_chain_hi, step_word, sub).  `global_chain` = local chain index +
  *   the handle's chain offset, `step` counts transitions since the handle was seeded, so results do not
  *   depend on how chains are sharded over GPUs.
- *     Poisson MH : step_word = step >> 1, sub = 0; step parity selects words (0,1) or (2,3);
- *                  bits = w_lo | w_hi << 32; flip = bits & 1; u = (bits >> 11) * 2^-53.
+ *     Poisson MH : step_word = step >> 2; W = call(sub 0), V = call(sub 1), i = step & 3:
+ *                  flip = W[i] >> 31;  u = ((W[i] & 0x7fffffff) << 22 | V[i] >> 10) * 2^-53.
+ *                  (V only matters when the top 31 bits tie with the accept threshold, so the kernel evaluates
+ *                  it lazily: one Philox call per four transitions, still the exact 53-bit test.)
  *     MH (f64)   : step_word = step; sub 0 words (0,1) -> accept uniform (53 bit); sub 1 + j ->
  *                  Box-Muller pair of proposal normals (2j, 2j+1), words (0,1) -> u1, (2,3) -> u2.
  *     HMC (f32)  : step_word = step; sub j -> momenta 4j..4j+3 (Box-Muller on words (0,1), (2,3));

@@ -1,6 +1,7 @@
 // Metropolis-Hastings C ABI (see include/minimcmc.h) — host side of K1.
 // Compiled with -fmad=false (see mmc_mh.cuh).
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mmc_mh.cuh"
@@ -17,6 +18,7 @@ struct mmc_mh {
     int64_t step = 0;  // transitions since the last seed()
     uint64_t seed = 0;
     int32_t accept_mode = 1;
+    int32_t tile_u8 = 128, tile_u16 = 64;  // staging-tile steps (tuned on B200)
     void *d_state = nullptr;
     // Poisson tables
     int32_t table_len = 0;
@@ -82,14 +84,9 @@ int build_poisson_tables(mmc_mh *h) {
         lnfact[k] = k < 2 ? 0.0 : acc;
         lp[k] = -lambda + (double)k * h->ln_lambda - lnfact[k];
     }
-    // lim[k][dir] = (thr << 11) - 1 so that  u53 < thr  <=>  bits <= lim  (thr = 2^53 -> all ones = always).
-    // thr = 0 would wrap to "always"; it only occurs for moves that are never proposed (k = 0 down) and at
-    // the clamped table end, where the proposal equals the current state.
+    // table entry [k][dir] = (thr >> 22, thr & (2^22 - 1)):  u53 < thr  <=>  u31 < thr_hi || (u31 == thr_hi && u22 < thr_lo)
     std::vector<uint2> lim(2 * len, make_uint2(0u, 0u));
-    auto encode = [](uint64_t thr) {
-        const uint64_t v = thr == 0 ? 0 : ((thr >= (1ULL << 53)) ? ~0ULL : (thr << 11) - 1);
-        return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
-    };
+    auto encode = [](uint64_t thr) { return make_uint2((uint32_t)(thr >> 22), (uint32_t)(thr & 0x3fffffu)); };
     for (int64_t k = 0; k + 1 < len; ++k) {
         // x = k -> y = k + 1 : q_f = (k == 0 ? 0 : ln 1/2), q_b = ln 1/2
         const double qf = k == 0 ? 0.0 : h->ln_half, qb = h->ln_half;
@@ -188,16 +185,29 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     const int block = kPoisWarps * 32;
     const int64_t warps = (h->chains + 31) / 32;
     const unsigned grid = (unsigned)((warps + kPoisWarps - 1) / kPoisWarps);
-    const size_t smem = (size_t)h->table_len * 16 + (size_t)kPoisWarps * 32 * kPoisPitch * sizeof(uint16_t);
-    auto launch = [&](auto kernel) -> int {
+    auto launch = [&](auto kernel, size_t tile_bytes) -> int {
+        const size_t smem = (size_t)h->table_len * 16 + (size_t)kPoisWarps * tile_bytes;
         MMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, block, smem, stream>>>(p);
         MMC_CUDA(cudaGetLastError());
         return MMC_OK;
     };
     const bool thr = h->accept_mode != 0;
-    if (replay) return thr ? launch(mh_poisson_kernel<true, true>) : launch(mh_poisson_kernel<true, false>);
-    return thr ? launch(mh_poisson_kernel<false, true>) : launch(mh_poisson_kernel<false, false>);
+    const size_t tb64 = PoisTile<64, uint16_t>::kWarpBytes;
+    if (replay) return thr ? launch(mh_poisson_kernel<true, true>, tb64) : launch(mh_poisson_kernel<true, false>, tb64);
+    if (!thr) return launch(mh_poisson_kernel<false, false>, tb64);
+    // native threshold path (the C2 hot loop): staging-tile shape selectable for tuning
+    int tile = h->table_len <= 256 ? h->tile_u8 : h->tile_u16;
+    if (const char *e = getenv("MMC_POIS_TILE")) tile = atoi(e);
+    const bool u8 = h->table_len <= 256 && !getenv("MMC_POIS_U16");
+    if (u8) {
+        if (tile >= 256) return launch(mh_poisson_kernel<false, true, 256, uint8_t>, PoisTile<256, uint8_t>::kWarpBytes);
+        if (tile >= 128) return launch(mh_poisson_kernel<false, true, 128, uint8_t>, PoisTile<128, uint8_t>::kWarpBytes);
+        return launch(mh_poisson_kernel<false, true, 64, uint8_t>, PoisTile<64, uint8_t>::kWarpBytes);
+    }
+    if (tile >= 256) return launch(mh_poisson_kernel<false, true, 256, uint16_t>, PoisTile<256, uint16_t>::kWarpBytes);
+    if (tile >= 128) return launch(mh_poisson_kernel<false, true, 128, uint16_t>, PoisTile<128, uint16_t>::kWarpBytes);
+    return launch(mh_poisson_kernel<false, true, 64, uint16_t>, tb64);
 }
 
 int check_error_flag(mmc_mh *h, cudaStream_t stream) {

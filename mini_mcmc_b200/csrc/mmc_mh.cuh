@@ -157,21 +157,24 @@ __global__ void mh_cont_export_tape_kernel(uint2 key, int64_t chains, int64_t ch
 // PoissonTarget + NonnegativeProposal, examples/poisson_mh.rs:10-89.
 //
 // Draw write-out is the HBM-bound part (8 B per collected transition): each warp stages T steps of its
-// 32 chains in shared memory and emits them as contiguous 256 B row segments (full 32 B sectors)
-// instead of 32 strided 8 B stores per step.
+// 32 chains in shared memory and emits them as contiguous row segments (full 32 B sectors) instead of 32
+// strided 8 B stores per step.
 //
-// A transition consumes one 64-bit word `bits`: flip = bits & 1, u = (bits >> 11) * 2^-53.
-//   threshold mode: accept  <=>  u53 < thr[x][dir]  <=>  bits <= lim[x][dir] = (thr << 11) - 1, where thr is
-//     the host-built count of 53-bit uniforms satisfying (lp'+q_b)-(lp+q_f) > ln(u) (mmc_mh.cu).
-//   log mode: evaluates that predicate in f64 on the device.
-// One Philox4x32-10 call feeds two consecutive steps (global step parity picks the word pair).
+// RNG contract (minimcmc.h): global step s of a chain uses word i = s & 3 of two Philox calls,
+//   W = philox(key, (chain, s >> 2, sub 0)),  V = philox(key, (chain, s >> 2, sub 1)):
+//   flip = W[i] >> 31;  u53 = (W[i] & 0x7fffffff) << 22 | V[i] >> 10;  u = u53 * 2^-53.
+// The accept test u53 < thr is decided by the top 31 bits except on a tie (probability 2^-31), so V is
+// evaluated lazily: one Philox call feeds FOUR transitions and the result is still the exact 53-bit test.
+//   threshold mode: thr[x][dir] is the host-built count of 53-bit uniforms satisfying
+//     (lp'+q_b)-(lp+q_f) > ln(u) (mmc_mh.cu), split as thr_hi = thr >> 22, thr_lo = thr & (2^22 - 1).
+//   log mode: evaluates that predicate in f64 on the device (needs V every step).
 struct MhPoissonParams {
     uint64_t *state;        // [chains] in/out
     uint64_t *out;          // [chains, n_collect]
     const uint8_t *flip;    // replay [chains, steps]
     const double *u;        // replay [chains, steps]
     const double *lnfact;   // [table_len]  sum_{i<=k} ln i, built by the host libm in the reference's order
-    const uint2 *lim;       // [table_len][2] (lo, hi) of lim[k][0] = down, lim[k][1] = up
+    const uint2 *lim;       // [table_len][2] (thr_hi, thr_lo) of [k][0] = down, [k][1] = up
     int32_t table_len;
     double lambda, ln_lambda, ln_half;
     int64_t chains, chain_offset, step_base, n_collect, n_discard;
@@ -179,9 +182,14 @@ struct MhPoissonParams {
     int32_t *error_flag;    // set to 1 when a chain reaches the end of the table
 };
 
-constexpr int kPoisTile = 64;              // steps staged per write-out
-constexpr int kPoisPitch = kPoisTile + 2;  // halfwords; 33 words -> conflict-free rows
 constexpr int kPoisWarps = 8;
+// staging tile of one warp: 32 rows x T columns of Elem, row pitch padded by 4 bytes (odd number of words ->
+// conflict-free row-per-lane stores and column-per-lane loads)
+template <int T, class Elem>
+struct PoisTile {
+    static constexpr int kPitch = T + 4 / (int)sizeof(Elem);          // elements
+    static constexpr size_t kWarpBytes = (size_t)32 * kPitch * sizeof(Elem);
+};
 
 // Philox4x32-10 with the round keys read straight from the kernel-parameter constant bank.
 __device__ __forceinline__ uint4 philox_rk(const uint32_t (&rk)[20], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
@@ -196,14 +204,19 @@ __device__ __forceinline__ uint4 philox_rk(const uint32_t (&rk)[20], uint32_t c0
     }
     return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t i) {
+    return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
+}
 
-template <bool kReplay, bool kThreshold>
+template <bool kReplay, bool kThreshold, int T = 64, class Elem = uint16_t>
 __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __grid_constant__ MhPoissonParams p) {
+    constexpr int kPoisTile = T;
+    constexpr int kPoisPitch = PoisTile<T, Elem>::kPitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [table_len][2] uint2 (threshold) or [table_len] f64 (log mode), then the warp tiles
     uint2 *s_lim = reinterpret_cast<uint2 *>(smem_raw);
     double *s_lnf = reinterpret_cast<double *>(smem_raw);
-    uint16_t *tiles = reinterpret_cast<uint16_t *>(smem_raw + (size_t)p.table_len * 16);
+    Elem *tiles = reinterpret_cast<Elem *>(smem_raw + (size_t)p.table_len * 16);
     if (kThreshold) {
         for (int i = threadIdx.x; i < 2 * p.table_len; i += blockDim.x) s_lim[i] = p.lim[i];
     } else {
@@ -212,8 +225,8 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t *tile = tiles + warp * 32 * kPoisPitch;
-    uint16_t *my_row = tile + lane * kPoisPitch;
+    Elem *tile = tiles + warp * 32 * kPoisPitch;
+    Elem *my_row = tile + lane * kPoisPitch;
     const int64_t chain0 = ((int64_t)blockIdx.x * kPoisWarps + warp) * 32;
     if (chain0 >= p.chains) return;
     const int64_t c = chain0 + lane;
@@ -229,16 +242,20 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         x = x0 >= kmax ? kmax : (uint32_t)x0;
     }
 
-    auto transition = [&](uint32_t lo, uint32_t hi) {
+    // One transition from the first-level word w; `low22()` yields the lazily evaluated low bits of u53.
+    auto transition = [&](uint32_t w, auto low22) {
         // NonnegativeProposal::sample, examples/poisson_mh.rs:34-47: 0 -> 1, else +-1 by the flip
-        const uint32_t up = (lo & 1u) | (uint32_t)(x == 0);
+        const uint32_t up = (w >> 31) | (uint32_t)(x == 0);
         const uint32_t y = min(x + 2u * up - 1u, kmax);
+        const uint32_t u31 = w & 0x7fffffffu;
         bool acc;
         if (kThreshold) {
-            const uint2 lim = s_lim[2u * x + up];
-            acc = (hi < lim.y) || (hi == lim.y && lo <= lim.x);
+            const uint2 thr = s_lim[2u * x + up];
+            acc = u31 < thr.x;
+            if (u31 == thr.x) acc = low22() < thr.y;  // tie in the top 31 bits: probability 2^-31
         } else {
-            const double u = (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+            const uint64_t u53 = ((uint64_t)u31 << 22) | low22();
+            const double u = (double)u53 * (1.0 / 9007199254740992.0);
             // PoissonTarget::unnorm_logp, examples/poisson_mh.rs:19-25: -lambda + k ln(lambda) - ln k!
             const double cur_lp = (-p.lambda + (double)x * p.ln_lambda) - s_lnf[x];
             const double prop_lp = (-p.lambda + (double)y * p.ln_lambda) - s_lnf[y];
@@ -252,9 +269,10 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         xmax = max(xmax, x);
     };
 
-    // ---- staging tile: column j holds global step G + j, G even, so that a Philox pair is one 32-bit store
+    // ---- staging tile: column j holds global step G + j with G a multiple of 4, so the four steps of one
+    // Philox call land in one aligned shared-memory store
     const uint64_t g_first = (uint64_t)(p.step_base + p.n_discard);  // global index of the first collected step
-    int col_lo = (int)(g_first & 1);   // first valid column of the current tile (1 only for an odd start)
+    int col_lo = (int)(g_first & 3);   // first valid column of the current tile (non-zero only for an unaligned start)
     int tpos = col_lo;                 // next column to fill
     int64_t t_base = -(int64_t)col_lo; // collected index of column 0
     // 16-byte stores need (chain * n_collect + t_base) even for every chain of the warp
@@ -263,23 +281,20 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         __syncwarp();
         const int nrows = (int)((p.chains - chain0 < 32) ? (p.chains - chain0) : 32);
         uint64_t *row = p.out + chain0 * p.n_collect + t_base;
-        const uint16_t *trow = tile;
+        const Elem *trow = tile;
         if (vec_ok && (tpos % 2 == 0)) {
             for (int r = 0; r < nrows; ++r) {
-                if (2 * lane < tpos) {
-                    const uint32_t v = *reinterpret_cast<const uint32_t *>(trow + 2 * lane);
-                    const ulonglong2 o = make_ulonglong2((unsigned long long)(v & 0xffffu), (unsigned long long)(v >> 16));
-                    __stcs(reinterpret_cast<ulonglong2 *>(row + 2 * lane), o);
+                for (int col = 2 * lane; col < tpos; col += 64) {
+                    const ulonglong2 o = make_ulonglong2((unsigned long long)trow[col], (unsigned long long)trow[col + 1]);
+                    __stcs(reinterpret_cast<ulonglong2 *>(row + col), o);
                 }
                 row += p.n_collect;
                 trow += kPoisPitch;
             }
         } else {
             for (int r = 0; r < nrows; ++r) {
-                if (lane >= col_lo && lane < tpos)
-                    __stcs(reinterpret_cast<unsigned long long *>(row + lane), (unsigned long long)trow[lane]);
-                if (lane + 32 < tpos)
-                    __stcs(reinterpret_cast<unsigned long long *>(row + lane + 32), (unsigned long long)trow[lane + 32]);
+                for (int col = lane; col < tpos; col += 32)
+                    if (col >= col_lo) __stcs(reinterpret_cast<unsigned long long *>(row + col), (unsigned long long)trow[col]);
                 row += p.n_collect;
                 trow += kPoisPitch;
             }
@@ -290,15 +305,8 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         col_lo = 0;
     };
     auto emit1 = [&]() {
-        my_row[tpos] = (uint16_t)x;
+        my_row[tpos] = (Elem)x;
         if (++tpos == kPoisTile) flush();
-    };
-
-    auto replay_bits = [&](int64_t s, uint32_t &lo, uint32_t &hi) {
-        const double u = p.u[cc * steps + s];
-        const uint64_t bits = ((uint64_t)(u * 9007199254740992.0) << 11) | (uint64_t)(p.flip[cc * steps + s] & 1);
-        lo = (uint32_t)bits;
-        hi = (uint32_t)(bits >> 32);
     };
 
     // steps [s0, s1) of this run; kEmit selects the collect phase
@@ -307,37 +315,47 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         int64_t s = s0;
         if (kReplay) {
             for (; s < s1; ++s) {
-                uint32_t lo, hi;
-                replay_bits(s, lo, hi);
-                transition(lo, hi);
+                const double u = p.u[cc * steps + s];
+                const uint64_t u53 = (uint64_t)(u * 9007199254740992.0);
+                const uint32_t w = ((uint32_t)(p.flip[cc * steps + s] & 1) << 31) | (uint32_t)(u53 >> 22);
+                transition(w, [&]() { return (uint32_t)(u53 & 0x3fffffu); });
                 if (kEmit) emit1();
             }
             return;
         }
         const uint64_t g0 = (uint64_t)p.step_base;
-        if (s < s1 && ((g0 + s) & 1)) {  // odd first step: second half of its Philox pair
-            const uint4 w = philox_rk(p.rk, gc_lo, gc_hi, (uint32_t)((g0 + s) >> 1), 0u);
-            transition(w.z, w.w);
+        auto single = [&]() {  // unaligned head / tail steps
+            const uint64_t gs = g0 + s;
+            const uint32_t quad = (uint32_t)(gs >> 2), i = (uint32_t)(gs & 3);
+            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, quad, 0u);
+            transition(pick(W, i), [&]() { return pick(philox_rk(p.rk, gc_lo, gc_hi, quad, 1u), i) >> 10; });
             if (kEmit) emit1();
             ++s;
-        }
-        uint32_t pair = (uint32_t)((g0 + s) >> 1);
-        for (; s + 1 < s1; s += 2, ++pair) {
-            const uint4 w = philox_rk(p.rk, gc_lo, gc_hi, pair, 0u);
-            transition(w.x, w.y);
+        };
+        while (s < s1 && ((g0 + s) & 3)) single();
+        uint32_t quad = (uint32_t)((g0 + s) >> 2);
+        for (; s + 3 < s1; s += 4, ++quad) {
+            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, quad, 0u);
+            transition(W.x, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).x >> 10; });
             const uint32_t xa = x;
-            transition(w.z, w.w);
-            if (kEmit) {  // tpos is even here: one 32-bit shared store for both steps
-                *reinterpret_cast<uint32_t *>(my_row + tpos) = xa | (x << 16);
-                tpos += 2;
+            transition(W.y, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).y >> 10; });
+            const uint32_t xb = x;
+            transition(W.z, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).z >> 10; });
+            const uint32_t xc = x;
+            transition(W.w, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).w >> 10; });
+            if (kEmit) {  // tpos is a multiple of 4 here: aligned packed store(s) for the four steps
+                if (sizeof(Elem) == 1) {
+                    *reinterpret_cast<uint32_t *>(my_row + tpos) = xa | (xb << 8) | (xc << 16) | (x << 24);
+                } else {
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(my_row + tpos);  // 4-byte aligned (pitch is odd in words)
+                    dst[0] = xa | (xb << 16);
+                    dst[1] = xc | (x << 16);
+                }
+                tpos += 4;
                 if (tpos == kPoisTile) flush();
             }
         }
-        if (s < s1) {
-            const uint4 w = philox_rk(p.rk, gc_lo, gc_hi, pair, 0u);
-            transition(w.x, w.y);
-            if (kEmit) emit1();
-        }
+        while (s < s1) single();
     };
     run_steps(0, p.n_discard, std::false_type{});
     run_steps(p.n_discard, steps, std::true_type{});

@@ -8,8 +8,7 @@
 // Device part: ONE streaming pass over the draws per block of 16 lags.  A thread owns one
 // (split chain, parameter) series; the 32 lanes of a warp own 32 adjacent parameters so every load is a
 // contiguous 128 B row segment; the last 16 values live in a register ring so each draw is read once.
-// Series are shifted by their first draw (not the mean) so one pass suffices; the exact centring is
-// applied algebraically afterwards.  Cross-chain sums are accumulated in f64 registers by a persistent
+// Cross-chain sums are accumulated in f64 registers by a persistent
 // grid and flushed with one f64 atomic per (CTA, parameter, row).
 // Only lags the Geyer truncation actually consumes are computed (the reference computes all N by FFT
 // and then discards everything after the first non-positive pair); results differ from the FFT path
@@ -30,7 +29,12 @@ constexpr int kLagBlock = 16;
 constexpr int kStatsWarps = 4;
 
 // partial layout: [2 + N][p] doubles: row 0 = sum_j m_j, row 1 = sum_j m_j^2, row 2 + t = sum_j acov_j(t)
-__global__ void __launch_bounds__(kStatsWarps * 32)
+//
+// Per series: loop 1 sums the draws (mean, src/stats.rs:586), loop 2 re-reads them (L2 hits: the chain block was
+// just streamed) and accumulates sum_t d_t d_{t-lag} for 16 lags with the last 16 centred values in a register
+// ring.  All loads are unconditional (indices clamped, contributions masked) so 16 are in flight per thread.
+template <bool kFirst>
+__global__ void __launch_bounds__(kStatsWarps * 32, 4)
 stats_pass_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int64_t p, int64_t lag0, int nlag,
                   double *__restrict__ partial) {
     const int lane = threadIdx.x & 31;
@@ -40,6 +44,7 @@ stats_pass_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, 
     const int64_t b = warp_global % nb;          // this warp's parameter block (fixed for its lifetime)
     const int64_t q = b * 32 + lane;
     const bool q_ok = q < p;
+    const int64_t qc = q_ok ? q : p - 1;         // out-of-range lanes shadow the last parameter (never flushed)
     const int64_t half = n / 2, N = half, C = 2 * c_local;
     const int64_t chain_stride = n_warps / nb;   // host guarantees n_warps % nb == 0
     const float inv_n = 1.0f / (float)N;
@@ -52,56 +57,55 @@ stats_pass_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, 
         // splitcat, src/stats.rs:396-402: split chain j < c is the first half of chain j, j >= c the last half of j - c
         const int64_t chain = j < c_local ? j : j - c_local;
         const int64_t row0 = j < c_local ? 0 : n - half;
-        const float *base = sample + ((chain * n + row0) * p + q);
-        if (!q_ok) continue;
-        const float k = __ldg(base);
-        float S1 = 0.0f, P[kLagBlock], ring[kLagBlock];
+        const float *base = sample + ((chain * n + row0) * p + qc);
+        // ---- loop 1: mean
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int64_t t0 = 0;
+        for (; t0 + kLagBlock <= N; t0 += kLagBlock) {
+            float v[kLagBlock];
+#pragma unroll
+            for (int u = 0; u < kLagBlock; ++u) v[u] = __ldg(base + (t0 + u) * p);
+#pragma unroll
+            for (int u = 0; u < kLagBlock; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
+        }
+        for (; t0 < N; ++t0) s0 += __ldg(base + t0 * p);
+        const float m = ((s0 + s1) + (s2 + s3)) * inv_n;
+        // ---- loop 2: centred lagged products, lags lag0 .. lag0 + 15
+        float P[kLagBlock], ring[kLagBlock];
 #pragma unroll
         for (int i = 0; i < kLagBlock; ++i) { P[i] = 0.0f; ring[i] = 0.0f; }
-        for (int64_t t0 = 0; t0 < N; t0 += kLagBlock) {
+        for (t0 = 0; t0 < N; t0 += kLagBlock) {
             float a[kLagBlock], bb[kLagBlock];
 #pragma unroll
             for (int u = 0; u < kLagBlock; ++u) {
                 const int64_t t = t0 + u;
-                a[u] = t < N ? __ldg(base + t * p) - k : 0.0f;
-                if (lag0 == 0) bb[u] = a[u];
-                else bb[u] = (t < N && t >= lag0) ? __ldg(base + (t - lag0) * p) - k : 0.0f;
+                const int64_t tc = t < N ? t : N - 1;
+                const float va = __ldg(base + tc * p);
+                a[u] = t < N ? va - m : 0.0f;
+                if (kFirst) {
+                    bb[u] = a[u];
+                } else {
+                    const int64_t tb = tc - lag0;
+                    const float vb = __ldg(base + (tb > 0 ? tb : 0) * p);
+                    bb[u] = (t < N && tb >= 0) ? vb - m : 0.0f;
+                }
             }
 #pragma unroll
             for (int u = 0; u < kLagBlock; ++u) {
                 ring[u] = bb[u];  // b_t at slot t mod 16
-                S1 += a[u];
 #pragma unroll
                 for (int i = 0; i < kLagBlock; ++i) P[i] = fmaf(a[u], ring[(u - i) & (kLagBlock - 1)], P[i]);
             }
         }
-        const float mean_shift = S1 * inv_n;  // delta = m - k
-        const float m = k + mean_shift;
-        if (lag0 == 0) {
+        if (kFirst) {
             acc_m += (double)m;
             acc_m2 += (double)m * (double)m;
         }
-        // exact centring: sum_{t>=lag} (d_t - delta)(d_{t-lag} - delta)
-        //   = P_lag - delta (S1 - head_lag + S1 - tail_lag) + (N - lag) delta^2
-        float head = 0.0f, tail = 0.0f;
-        for (int64_t t = 0; t < lag0 && t < N; ++t) {
-            head += __ldg(base + t * p) - k;
-            tail += __ldg(base + (N - 1 - t) * p) - k;
-        }
 #pragma unroll
-        for (int i = 0; i < kLagBlock; ++i) {
-            const int64_t lag = lag0 + i;
-            if (i < nlag && lag < N) {
-                const float centred = P[i] - mean_shift * ((S1 - head) + (S1 - tail)) +
-                                      (float)(N - lag) * mean_shift * mean_shift;
-                acc_cov[i] += (double)(centred * inv_n);
-                head += __ldg(base + lag * p) - k;
-                tail += __ldg(base + (N - 1 - lag) * p) - k;
-            }
-        }
+        for (int i = 0; i < kLagBlock; ++i) acc_cov[i] += (double)(P[i] * inv_n);
     }
     if (q_ok) {
-        if (lag0 == 0) {
+        if (kFirst) {
             atomicAdd(partial + q, acc_m);
             atomicAdd(partial + p + q, acc_m2);
         }
@@ -115,12 +119,15 @@ int launch_pass(const float *sample, int64_t c_local, int64_t n, int64_t p, int6
                 cudaStream_t stream) {
     const int64_t nb = (p + 31) / 32;
     // persistent grid: ~8 CTAs per SM, rounded so that the warp count is a multiple of the parameter blocks
-    int64_t warps = (int64_t)sm_count() * 8 * kStatsWarps;
+    int64_t warps = (int64_t)sm_count() * 4 * kStatsWarps;
     const int64_t work = 2 * c_local * nb;
     if (warps > work) warps = work;
     warps = ((warps + nb * kStatsWarps - 1) / (nb * kStatsWarps)) * (nb * kStatsWarps);
     const unsigned grid = (unsigned)(warps / kStatsWarps);
-    stats_pass_kernel<<<grid, kStatsWarps * 32, 0, stream>>>(sample, c_local, n, p, lag0, nlag, partial);
+    if (lag0 == 0)
+        stats_pass_kernel<true><<<grid, kStatsWarps * 32, 0, stream>>>(sample, c_local, n, p, lag0, nlag, partial);
+    else
+        stats_pass_kernel<false><<<grid, kStatsWarps * 32, 0, stream>>>(sample, c_local, n, p, lag0, nlag, partial);
     MMC_CUDA(cudaGetLastError());
     return MMC_OK;
 }

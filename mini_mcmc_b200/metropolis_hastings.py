@@ -87,6 +87,12 @@ class MetropolisHastings:
         sample = self.run(n_collect, n_discard)
         return sample, RunStats.from_sample(sample)
 
+    def set_state(self, state):
+        st = np.ascontiguousarray(state, dtype=self._np_dtype)
+        assert st.shape == (self.n_chains, self.dim)
+        L.check(L.lib.mmc_mh_set_state(self._h, L.vp(st)))
+        return self
+
     def current_state(self) -> np.ndarray:
         st = np.empty((self.n_chains, self.dim), dtype=self._np_dtype)
         L.check(L.lib.mmc_mh_get_state(self._h, L.vp(st)))

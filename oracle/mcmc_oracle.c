@@ -212,8 +212,9 @@ ORC_API int orc_mh_poisson_run_replay(double lambda, uint64_t *state, int64_t ch
 }
 
 /* Twin of the CUDA path's native Philox keying (include/minimcmc.h "RNG contract"):
- * key = seed, ctr = (chain_lo, chain_hi, step>>1, 0); step parity selects words (0,1) / (2,3);
- * bits = w_lo | w_hi<<32; flip = bits & 1; u = (bits >> 11) * 2^-53. */
+ * key = seed; global step s uses word i = s & 3 of W = philox(ctr = (chain_lo, chain_hi, s >> 2, 0)) and
+ * V = philox(ctr = (.., s >> 2, 1)):  flip = W[i] >> 31;  u53 = (W[i] & 0x7fffffff) << 22 | V[i] >> 10;
+ * u = u53 * 2^-53. */
 ORC_API int orc_mh_poisson_run_philox(double lambda, uint64_t *state, int64_t chains, int64_t chain_offset,
                                       int64_t step_base, int64_t n_collect, int64_t n_discard, uint64_t seed,
                                       uint64_t *out) {
@@ -225,13 +226,15 @@ ORC_API int orc_mh_poisson_run_philox(double lambda, uint64_t *state, int64_t ch
         const uint64_t gc = (uint64_t)(c + chain_offset);
         for (int64_t i = 0; i < steps; ++i) {
             const uint64_t gs = (uint64_t)(step_base + i);
-            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 1), 0u};
-            uint32_t w[4];
+            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 2), 0u};
+            uint32_t w[4], v[4];
             orc_philox4x32_10(key, ctr, w);
-            const int h = (int)(gs & 1) * 2;
-            uint64_t bits = (uint64_t)w[h] | ((uint64_t)w[h + 1] << 32);
-            int flip = (int)(bits & 1);
-            double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+            ctr[3] = 1u;
+            orc_philox4x32_10(key, ctr, v);
+            const int h = (int)(gs & 3);
+            int flip = (int)(w[h] >> 31);
+            uint64_t u53 = ((uint64_t)(w[h] & 0x7fffffffu) << 22) | (uint64_t)(v[h] >> 10);
+            double u = (double)u53 * (1.0 / 9007199254740992.0);
             x = orc_mh_poisson_step(lambda, x, flip, u);
             if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
         }

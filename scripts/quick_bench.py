@@ -64,9 +64,17 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["poisson", "hmc", "stats"]
     print(torch.cuda.get_device_name(0))
     if "poisson" in which:
-        poisson(mode=1)
+        for u16 in (False, True):
+            for tile in (64, 128, 256):
+                os.environ["MMC_POIS_TILE"] = str(tile)
+                if u16:
+                    os.environ["MMC_POIS_U16"] = "1"
+                print("tile", tile, "u16", u16)
+                poisson(mode=1)
+        os.environ.pop("MMC_POIS_TILE")
+        os.environ.pop("MMC_POIS_U16")
         poisson(mode=0)
-        poisson(n_collect=10000, n_discard=0, mode=1)
+        poisson(n_collect=0, n_discard=10000, mode=1)
     if "hmc" in which:
         hmc()
     if "stats" in which:
