@@ -209,16 +209,21 @@ __device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t i) {
 }
 
 template <bool kReplay, bool kThreshold, int T = 64, class Elem = uint16_t>
-__global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __grid_constant__ MhPoissonParams p) {
+__global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __grid_constant__ MhPoissonParams p) {
     constexpr int kPoisTile = T;
     constexpr int kPoisPitch = PoisTile<T, Elem>::kPitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [table_len][2] uint2 (threshold) or [table_len] f64 (log mode), then the warp tiles
-    uint2 *s_lim = reinterpret_cast<uint2 *>(smem_raw);
+    uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw);  // [2 table_len] thr >> 22   (one word per entry:
+    uint32_t *s_lo = s_hi + 2 * p.table_len;                  // [2 table_len] thr & 2^22-1  bank-conflict free)
     double *s_lnf = reinterpret_cast<double *>(smem_raw);
     Elem *tiles = reinterpret_cast<Elem *>(smem_raw + (size_t)p.table_len * 16);
     if (kThreshold) {
-        for (int i = threadIdx.x; i < 2 * p.table_len; i += blockDim.x) s_lim[i] = p.lim[i];
+        for (int i = threadIdx.x; i < 2 * p.table_len; i += blockDim.x) {
+            const uint2 t = p.lim[i];
+            s_hi[i] = t.x;
+            s_lo[i] = t.y;
+        }
     } else {
         for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) s_lnf[i] = p.lnfact[i];
     }
@@ -250,9 +255,9 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         const uint32_t u31 = w & 0x7fffffffu;
         bool acc;
         if (kThreshold) {
-            const uint2 thr = s_lim[2u * x + up];
-            acc = u31 < thr.x;
-            if (u31 == thr.x) acc = low22() < thr.y;  // tie in the top 31 bits: probability 2^-31
+            const uint32_t hi = s_hi[2u * x + up];
+            acc = u31 < hi;
+            if (u31 == hi) acc = low22() < s_lo[2u * x + up];  // tie in the top 31 bits: probability 2^-31
         } else {
             const uint64_t u53 = ((uint64_t)u31 << 22) | low22();
             const double u = (double)u53 * (1.0 / 9007199254740992.0);
@@ -267,6 +272,16 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         }
         x = acc ? y : x;
         xmax = max(xmax, x);
+    };
+    // Branch-free fast transition (threshold mode): decides on the top 31 bits and records whether a tie
+    // occurred; the caller replays the whole quad through `transition` in that (2^-29 per quad) case.
+    auto fast = [&](uint32_t w, bool &tie) {
+        const uint32_t up = (w >> 31) | (uint32_t)(x == 0);
+        const uint32_t y = min(x + 2u * up - 1u, kmax);
+        const uint32_t u31 = w & 0x7fffffffu;
+        const uint32_t hi = s_hi[2u * x + up];
+        tie = tie || (u31 == hi);
+        x = (u31 < hi) ? y : x;
     };
 
     // ---- staging tile: column j holds global step G + j with G a multiple of 4, so the four steps of one
@@ -283,10 +298,25 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         uint64_t *row = p.out + chain0 * p.n_collect + t_base;
         const Elem *trow = tile;
         if (vec_ok && (tpos % 2 == 0)) {
+            // every warp-wide store instruction covers one contiguous 512 B run of a row (full 32 B sectors):
+            // lane l widens columns (2l, 2l+1) of each 64-column group into one 16-byte streaming store
+#pragma unroll 4
             for (int r = 0; r < nrows; ++r) {
-                for (int col = 2 * lane; col < tpos; col += 64) {
-                    const ulonglong2 o = make_ulonglong2((unsigned long long)trow[col], (unsigned long long)trow[col + 1]);
-                    __stcs(reinterpret_cast<ulonglong2 *>(row + col), o);
+#pragma unroll
+                for (int g = 0; g < kPoisTile / 64; ++g) {
+                    const int col = 64 * g + 2 * lane;
+                    if (col < tpos) {
+                        uint32_t a, b;
+                        if (sizeof(Elem) == 1) {
+                            const uint32_t v = *reinterpret_cast<const uint16_t *>(trow + col);
+                            a = v & 0xffu; b = v >> 8;
+                        } else {
+                            const uint32_t v = *reinterpret_cast<const uint32_t *>(trow + col);
+                            a = v & 0xffffu; b = v >> 16;
+                        }
+                        __stcs(reinterpret_cast<ulonglong2 *>(row + col),
+                               make_ulonglong2((unsigned long long)a, (unsigned long long)b));
+                    }
                 }
                 row += p.n_collect;
                 trow += kPoisPitch;
@@ -336,13 +366,30 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
         uint32_t quad = (uint32_t)((g0 + s) >> 2);
         for (; s + 3 < s1; s += 4, ++quad) {
             const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, quad, 0u);
-            transition(W.x, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).x >> 10; });
-            const uint32_t xa = x;
-            transition(W.y, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).y >> 10; });
-            const uint32_t xb = x;
-            transition(W.z, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).z >> 10; });
-            const uint32_t xc = x;
-            transition(W.w, [&]() { return philox_rk(p.rk, gc_lo, gc_hi, quad, 1u).w >> 10; });
+            uint32_t xa, xb, xc;
+            if (kThreshold) {
+                const uint32_t x_in = x;
+                bool tie = false;
+                fast(W.x, tie); xa = x;
+                fast(W.y, tie); xb = x;
+                fast(W.z, tie); xc = x;
+                fast(W.w, tie);
+                if (tie) {  // exact 53-bit replay of this quad
+                    x = x_in;
+                    const uint4 V = philox_rk(p.rk, gc_lo, gc_hi, quad, 1u);
+                    transition(W.x, [&]() { return V.x >> 10; }); xa = x;
+                    transition(W.y, [&]() { return V.y >> 10; }); xb = x;
+                    transition(W.z, [&]() { return V.z >> 10; }); xc = x;
+                    transition(W.w, [&]() { return V.w >> 10; });
+                }
+                xmax = max(xmax, x + 3);  // x moves by at most 1 per step: bounds the excursion inside the quad
+            } else {
+                const uint4 V = philox_rk(p.rk, gc_lo, gc_hi, quad, 1u);
+                transition(W.x, [&]() { return V.x >> 10; }); xa = x;
+                transition(W.y, [&]() { return V.y >> 10; }); xb = x;
+                transition(W.z, [&]() { return V.z >> 10; }); xc = x;
+                transition(W.w, [&]() { return V.w >> 10; });
+            }
             if (kEmit) {  // tpos is a multiple of 4 here: aligned packed store(s) for the four steps
                 if (sizeof(Elem) == 1) {
                     *reinterpret_cast<uint32_t *>(my_row + tpos) = xa | (xb << 8) | (xc << 16) | (x << 24);
@@ -361,7 +408,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32) mh_poisson_kernel(const __gri
     run_steps(p.n_discard, steps, std::true_type{});
     if (tpos > col_lo) flush();
     if (active) p.state[c] = x;
-    if (xmax >= kmax) *p.error_flag = 1;
+    if (xmax >= kmax) *p.error_flag = 1;  // (conservative by 3 inside aligned quads)
 }
 
 }  // namespace mmc
