@@ -59,22 +59,40 @@ def split_rhat_mean_ess(sample, group=None):
         L.check(L.lib.mmc_split_rhat_ess_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), L.vp(rhat), L.vp(ess),
                                              L.current_stream_ptr()))
         return rhat, ess
-    c_total = torch.tensor([c], dtype=torch.int64, device="cuda")
+    def device_partial(partial, lag0, n_lags):
+        L.check(L.lib.mmc_stats_partial_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), C.c_int64(lag0),
+                                            C.c_int64(n_lags), L.vp(partial), L.current_stream_ptr()))
+
+    return sharded_split_rhat_ess(device_partial, c, n, p, group, torch.device("cuda"))
+
+
+def sharded_split_rhat_ess(partial_fn, c_local, n, p, group, device):
+    """Host side of the sharded diagnostics (one process per GPU).
+
+    partial_fn(partial, lag0, n_lags) fills rows [2 + lag0, 2 + lag0 + n_lags) (and rows 0-1 when lag0 == 0) of
+    the f64 [2 + n/2, p] `partial` tensor with this rank's sums over its LOCAL split chains.  The partials are
+    summed over ranks with one all-reduce per block of lags (the only collective of the engine) and every rank
+    finalises redundantly; lag blocks grow geometrically until the Geyer truncation has terminated."""
+    import torch
+    import torch.distributed as dist
+
+    c_total = torch.tensor([c_local], dtype=torch.int64, device=device)
     dist.all_reduce(c_total, group=group)
     c_total = int(c_total.item())
     N = n // 2
     plen = int(L.lib.mmc_stats_partial_len(C.c_int64(n), C.c_int64(p)))
-    partial = torch.zeros(plen, dtype=torch.float64, device="cuda")
+    partial = torch.zeros(plen, dtype=torch.float64, device=device)
+    rhat = np.empty(p, dtype=np.float32)
+    ess = np.empty(p, dtype=np.float32)
     have, block = 0, 16
     while have < N:
         want = min(block, N - have)
-        L.check(L.lib.mmc_stats_partial_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), C.c_int64(have),
-                                            C.c_int64(want), L.vp(partial), L.current_stream_ptr()))
+        partial_fn(partial, have, want)
         lo = 0 if have == 0 else (2 + have) * p
         hi = (2 + have + want) * p
-        dist.all_reduce(partial[lo:hi], group=group)  # the only collective of the whole engine
+        dist.all_reduce(partial[lo:hi], group=group)
         have += want
-        host = partial.cpu().numpy()
+        host = np.ascontiguousarray(partial.cpu().numpy())
         rc = L.lib.mmc_stats_finalize(L.vp(host), C.c_int64(c_total), C.c_int64(n), C.c_int64(p), C.c_int64(have),
                                       L.vp(rhat), L.vp(ess))
         if rc < 0:
