@@ -130,7 +130,7 @@ def run_reference_arm(args):
 
     import oracle
 
-    cores = oracle.num_threads()
+    cores = oracle.use_all_cores()
     sample_chains = args.ref_chains
     state = np.zeros(sample_chains, dtype=np.uint64)
     out = np.empty((sample_chains, N_COLLECT, 1), dtype=np.uint64)
@@ -284,6 +284,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
+        oracle.use_all_cores()
         sc = args.ref_chains
         st = np.zeros(sc, dtype=np.uint64)
         buf = np.empty((sc, N_COLLECT, 1), dtype=np.uint64)

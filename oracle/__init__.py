@@ -67,6 +67,13 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 # ------------------------------------------------------------------ RNG
 class SmallRng:
     """rand 0.9 SmallRng (xoshiro256++) with the rand / rand_distr sampling routines the reference uses."""

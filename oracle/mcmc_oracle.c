@@ -45,6 +45,13 @@ ORC_API int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU-baseline legs ask for all host cores explicitly. */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 ORC_API void orc_smallrng_seed_state(uint64_t seed, uint64_t *state4) {
     orc_smallrng r;
     orc_smallrng_seed(&r, seed);

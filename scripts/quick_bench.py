@@ -60,6 +60,30 @@ def stats(c=65536, n=400, p=100):
     print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
 
 
+def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32"):
+    init = mm.init_device(chains, D, 42).cpu().numpy()
+    s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype=scalar, max_depth=10).set_seed(7)
+    out = torch.empty((chains, n_collect, D), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    s.run_device(n_collect, n_discard, progress=True, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    c = s.counters()
+    st = s.state()
+    t0 = time.perf_counter()
+    rhat, ess = mm.split_rhat_mean_ess(out)
+    torch.cuda.synchronize()
+    stats_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps(dict(k="nuts_rosen", chains=chains, D=D, scalar=scalar, ms=ms, n_grad=c["n_grad"],
+                          grad_evals_per_s=c["n_grad"] / ms * 1e3, transitions_per_s=c["n_transitions"] / ms * 1e3,
+                          tflops=c["n_grad"] * 2285 / ms / 1e9, depth_hist=c["depth_hist"],
+                          eps_median=float(np.median(st[:, 0])), stats_ms=stats_ms, ess_min=float(ess.min()),
+                          ess_per_s=float(ess.min()) / ms * 1e3, rhat_max=float(rhat.max()), rhat_min=float(rhat.min()))))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["poisson", "hmc", "stats"]
     print(torch.cuda.get_device_name(0))
@@ -79,3 +103,7 @@ if __name__ == "__main__":
         hmc()
     if "stats" in which:
         stats()
+    if "nuts" in which:
+        nuts(chains=8192)
+        nuts()
+        nuts(scalar="f64")
