@@ -155,6 +155,9 @@ int mmc_hmc_create(mmc_hmc **h, const mmc_target_desc *target, const float *init
 int mmc_hmc_set_seed(mmc_hmc *h, uint64_t seed);
 int mmc_hmc_set_chain_offset(mmc_hmc *h, int64_t offset);
 int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact);
+/* dense Gaussian target only: gradient GEMM on 0 = FP32 SIMT tiles, 1 = tcgen05 tensor cores (3xTF32 split, fp32
+ * accumulation in TMEM).  exact = 1 always selects the FP32 path. */
+int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path);
 int mmc_hmc_step(mmc_hmc *h);
 int mmc_hmc_run(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, const mmc_replay_hmc *replay);
 int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_dev,

@@ -1,0 +1,34 @@
+// K3: HMC on a D-dimensional Gaussian with dense covariance (BASELINE config C4).
+// The D-dim generalisation of DiffableGaussian2D::unnorm_logp_batch (src/distributions.rs:262-288) inside
+// HMC::step / leapfrog (src/hmc.rs:304-431): per gradient evaluation Z = (X - mu) Sigma^-1 over all chains is one
+// [chains x D] x [D x D] GEMM; logp = norm_const - 0.5 rowsum(Z o (X - mu)), grad = -Z (symmetric precision).
+#pragma once
+
+#include "mmc_common.cuh"
+
+namespace mmc {
+
+struct DenseState;  // device buffers of the dense-Gaussian HMC path (mmc_dense.cu)
+
+struct DenseRunArgs {
+    float *positions;        // [chains, D] in/out
+    float *out;              // [chains, n_collect, D] or nullptr
+    const float *momenta;    // replay [steps, chains, D] or nullptr
+    const float *u;          // replay [steps, chains]
+    float *trace;            // optional [steps, chains, 4]
+    unsigned long long *accept_count;
+    int64_t chains, chain_offset, step_base, n_collect, n_discard;
+    float eps;
+    int n_leapfrog;
+    uint64_t seed;
+    int gemm_path;           // 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tensor-core tiles
+};
+
+int dense_create(DenseState **st, const mmc_target_desc *target, int64_t chains);
+void dense_destroy(DenseState *st);
+int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream);
+// native-mode draws (momenta [steps, chains, D], u [steps, chains]) as the dense path consumes them
+int dense_export_tape(int64_t chains, int D, int64_t chain_offset, uint64_t seed, int64_t step_base, int64_t steps,
+                      float *momenta, float *u, cudaStream_t stream);
+
+}  // namespace mmc

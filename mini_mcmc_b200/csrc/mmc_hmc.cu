@@ -1,6 +1,7 @@
 // HMC C ABI (see include/minimcmc.h) — host side of K2 and the built-in target dispatch.
 #include <cmath>
 
+#include "mmc_dense.cuh"
 #include "mmc_hmc.cuh"
 #include "mmc_targets.cuh"
 
@@ -16,6 +17,8 @@ struct mmc_hmc {
     int64_t step = 0;
     uint64_t seed = 0;
     int32_t exact = 0;
+    int32_t gemm_path = 0;       // dense Gaussian: 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32
+    DenseState *dense = nullptr;  // only for MMC_T_DENSE_GAUSSIAN
     float *d_pos = nullptr;
     unsigned long long *d_accept = nullptr;
     int64_t total_transitions = 0;
@@ -133,6 +136,12 @@ int mmc_hmc_create(mmc_hmc **out, const mmc_target_desc *target, const float *in
     if ((e = cudaMemcpy(h->d_pos, init_host, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "memcpy");
     if ((e = cudaMalloc((void **)&h->d_accept, 8)) != cudaSuccess) return fail(e, "cudaMalloc(counter)");
     if ((e = cudaMemset(h->d_accept, 0, 8)) != cudaSuccess) return fail(e, "memset");
+    if (target->kind == MMC_T_DENSE_GAUSSIAN) {
+        rc = dense_create(&h->dense, target, chains);
+        if (rc) { mmc_hmc_destroy(h); return rc; }
+        h->target.vec = nullptr;  // host pointers are not kept
+        h->target.mat = nullptr;
+    }
     *out = h;
     return MMC_OK;
 }
@@ -156,11 +165,40 @@ int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact) {
     return MMC_OK;
 }
 
+int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
+    MMC_REQUIRE(h && (path == 0 || path == 1), "gemm path must be 0 (FP32 SIMT) or 1 (tcgen05 3xTF32)");
+    h->gemm_path = path;
+    return MMC_OK;
+}
+
 int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_dev, const mmc_replay_hmc *rp,
                     void *stream) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_hmc_run_dev: bad arguments");
     const bool replay = rp && rp->momenta && rp->u;
     MMC_REQUIRE(!rp || replay, "HMC replay needs both momenta and u tapes");
+    if (h->dense) {
+        DenseRunArgs a{};
+        a.positions = h->d_pos;
+        a.out = n_collect > 0 ? out_dev : nullptr;
+        a.momenta = replay ? rp->momenta : nullptr;
+        a.u = replay ? rp->u : nullptr;
+        a.trace = rp ? rp->trace : nullptr;
+        a.accept_count = h->d_accept;
+        a.chains = h->chains;
+        a.chain_offset = h->chain_offset;
+        a.step_base = h->step;
+        a.n_collect = n_collect;
+        a.n_discard = n_discard;
+        a.eps = (float)h->step_size;
+        a.n_leapfrog = h->n_leapfrog;
+        a.seed = h->seed;
+        a.gemm_path = h->exact ? 0 : h->gemm_path;
+        int rc = dense_run(h->dense, a, (cudaStream_t)stream);
+        if (rc) return rc;
+        h->step += n_collect + n_discard;
+        h->total_transitions += (n_collect + n_discard) * h->chains;
+        return MMC_OK;
+    }
     HmcParams p{};
     p.positions = h->d_pos;
     p.out = n_collect > 0 ? out_dev : nullptr;
@@ -252,6 +290,8 @@ int mmc_hmc_export_tape_dev(mmc_hmc *h, int64_t step_base, int64_t steps, float 
                             void *stream) {
     MMC_REQUIRE(h && momenta_dev && u_dev && steps > 0, "mmc_hmc_export_tape_dev: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->dense)
+        return dense_export_tape(h->chains, h->dim, h->chain_offset, h->seed, step_base, steps, momenta_dev, u_dev, s);
     switch (h->dim) {
     case 1: return export_tape<1>(h, step_base, steps, momenta_dev, u_dev, s);
     case 2: return export_tape<2>(h, step_base, steps, momenta_dev, u_dev, s);
@@ -267,6 +307,7 @@ int mmc_hmc_export_tape_dev(mmc_hmc *h, int64_t step_base, int64_t steps, float 
 
 void mmc_hmc_destroy(mmc_hmc *h) {
     if (!h) return;
+    dense_destroy(h->dense);
     cudaFree(h->d_pos);
     cudaFree(h->d_accept);
     cudaFree(h->d_out);

@@ -45,6 +45,11 @@ class HMC:
         L.check(L.lib.mmc_hmc_set_exact(self._h, C.c_int32(int(exact))))
         return self
 
+    def set_gemm_path(self, path: int):
+        """Dense Gaussian target: 0 = FP32 SIMT GEMM tiles, 1 = tcgen05 tensor cores (3xTF32)."""
+        L.check(L.lib.mmc_hmc_set_gemm_path(self._h, C.c_int32(path)))
+        return self
+
     def step(self):
         L.check(L.lib.mmc_hmc_step(self._h))
 

@@ -60,6 +60,23 @@ def stats(c=65536, n=400, p=100):
     print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
 
 
+def dense(chains=4096, D=1024, L=50, steps=4, path=0):
+    rng = np.random.default_rng(42)
+    A = rng.normal(size=(D, D))
+    cov = A @ A.T / D + np.eye(D)
+    mean = rng.normal(size=D)
+    tgt = mm.DenseGaussian(mean, cov)
+    init = (rng.normal(size=(chains, D))).astype(np.float32)
+    h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_gemm_path(path)
+    out = torch.empty((chains, steps, D), dtype=torch.float32, device="cuda")
+    ms, ts = ev_time(lambda: h.run_device(steps, 0, out=out), warm=1, reps=2)
+    ge = chains * steps * (L + 1)
+    acc, tot = h.accept_counts()
+    print(json.dumps(dict(k="dense_hmc", path=path, chains=chains, D=D, L=L, ms=ms, all=ts, grad_evals_per_s=ge / ms * 1e3,
+                          tflops_fp32_equiv=ge * (2 * D * D + 4 * D) / ms / 1e9, us_per_leapfrog=ms * 1e3 / (steps * (L + 1)),
+                          accept=acc / max(tot, 1))))
+
+
 def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32"):
     init = mm.init_device(chains, D, 42).cpu().numpy()
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype=scalar, max_depth=10).set_seed(7)
@@ -103,6 +120,14 @@ if __name__ == "__main__":
         hmc()
     if "stats" in which:
         stats()
+    if "dense" in which:
+        dense(path=0)
+        dense(chains=32768, steps=2, path=0)
+        try:
+            dense(path=1)
+            dense(chains=32768, steps=2, path=1)
+        except Exception as e:
+            print("tc path:", e)
     if "nuts" in which:
         nuts(chains=8192)
         nuts()

@@ -1,0 +1,83 @@
+"""Config C4: HMC on a dense-covariance Gaussian (D-dim generalisation of DiffableGaussian2D,
+src/distributions.rs:262-288) — CUDA GEMM paths against the oracle under replayed momenta/uniforms."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mm(cuda_device):
+    import mini_mcmc_b200 as m
+
+    return m
+
+
+def make_problem(D, seed=42):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(D, D))
+    cov = A @ A.T / D + np.eye(D)
+    mean = rng.normal(size=D)
+    return mean, cov
+
+
+def tc_available(mm):
+    try:
+        mean, cov = make_problem(128)
+        h = mm.HMC(mm.DenseGaussian(mean, cov), np.zeros((128, 128), dtype=np.float32), 0.05, 1).set_gemm_path(1)
+        h.run(1, 0)
+        return True
+    except Exception:
+        return False
+
+
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3)])
+def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
+    if path == 1 and not tc_available(mm):
+        pytest.skip("tcgen05 path not built")
+    mean, cov = make_problem(D)
+    tgt = mm.DenseGaussian(mean, cov)
+    otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
+    rng = np.random.default_rng(D + L)
+    steps = 2
+    init = (rng.normal(size=(chains, D)) + mean).astype(np.float32)
+    mom = rng.normal(size=(steps, chains, D)).astype(np.float32)
+    u = rng.random((steps, chains)).astype(np.float32)
+    exp, exp_pos, exp_tr = oracle.hmc_run_replay(otgt, init, 0.05, L, steps, 0, mom, u, want_trace=True)
+    h = mm.HMC(tgt, init, 0.05, L).set_gemm_path(path)
+    trace = np.zeros((steps, chains, 4), dtype=np.float32)
+    got = h.run(steps, 0, replay=dict(momenta=mom, u=u), trace=trace)
+    # log-probs are O(D); 1e-5 relative (north_star fp32 tolerance)
+    scale = np.abs(exp_tr[..., :2]).max()
+    assert np.abs(trace[..., :2] - exp_tr[..., :2]).max() <= 2e-5 * scale
+    margin = np.abs(exp_tr[..., 2] - np.log(np.maximum(u, 1e-38)))
+    differ = trace[..., 3] != exp_tr[..., 3]
+    assert not (differ & (margin > 2e-3 * max(1.0, scale * 1e-2))).any()
+    same = ~differ.any(axis=0)
+    assert same.mean() > 0.97
+    np.testing.assert_allclose(got[same], exp[same], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(h.positions[same], exp_pos[same], rtol=1e-5, atol=2e-5)
+
+
+def test_dense_hmc_native_tape_and_moments(mm):
+    D, chains, L = 128, 512, 8
+    mean, cov = make_problem(D, seed=3)
+    tgt = mm.DenseGaussian(mean, cov)
+    init = np.tile(mean.astype(np.float32), (chains, 1))
+    h = mm.HMC(tgt, init, 0.15, L).set_seed(5).set_chain_offset(1000)
+    mom, u = h.export_tape(0, 3)
+    got = h.run(3, 0)
+    otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
+    exp, _, _ = oracle.hmc_run_replay(otgt, init, 0.15, L, 3, 0, mom.cpu().numpy(), u.cpu().numpy())
+    ok = np.isclose(got, exp, rtol=1e-4, atol=1e-4).all(axis=(1, 2))
+    assert ok.mean() > 0.97
+    # long native run: posterior mean / variance within Monte-Carlo error
+    s = h.run(200, 100)
+    flat = s.reshape(-1, D).astype(np.float64)
+    assert np.abs(flat.mean(axis=0) - mean).max() < 0.08
+    assert np.abs(flat.var(axis=0) / np.diag(cov) - 1.0).max() < 0.15
+    acc, tot = h.accept_counts()
+    assert acc / tot > 0.6
