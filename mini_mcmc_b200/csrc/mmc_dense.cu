@@ -15,22 +15,6 @@
 
 namespace mmc {
 
-struct DenseState {
-    int D = 0;
-    int64_t chains = 0;
-    float norm_const = 0.f;
-    float *d_mean = nullptr;      // [D]
-    float *d_prec = nullptr;      // [D, D] row-major, symmetric
-    float *d_delta[2] = {nullptr, nullptr};  // [chains, D] ping-pong
-    float *d_mom = nullptr;       // [chains, D]
-    float *d_scal = nullptr;      // [6, chains]: ke_cur, quad_cur, ke_prop, quad_prop, u, (spare)
-    // tensor-core path operands (hi/lo TF32 splits), see mmc_dense_tc.cu
-    float *d_prec_split = nullptr;            // [2, D, D]
-    float *d_delta_split[2] = {nullptr, nullptr};  // [2][2, chains, D]
-    void *tc = nullptr;
-};
-
-enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };
 
 // ---------------------------------------------------------------- begin / accept
 __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *__restrict__ mean, float *__restrict__ delta,
@@ -74,7 +58,7 @@ __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *_
 }
 
 __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__restrict__ mean, const float *__restrict__ delta,
-                                    const float *__restrict__ scal, float norm_const, float *__restrict__ out,
+                                    const float *__restrict__ delta_lo, const float *__restrict__ scal, float norm_const, float *__restrict__ out,
                                     float *__restrict__ trace, unsigned long long *accept_count, int64_t chains, int D,
                                     int64_t n_collect, int64_t slot, int64_t local_step) {
     const int lane = threadIdx.x & 31;
@@ -90,7 +74,11 @@ __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__rest
         const int i = 4 * j;
         float4 x = *reinterpret_cast<const float4 *>(pos + c * D + i);
         if (acc) {
-            const float4 d = *reinterpret_cast<const float4 *>(delta + c * D + i);
+            float4 d = *reinterpret_cast<const float4 *>(delta + c * D + i);
+            if (delta_lo) {  // tensor-core path keeps Delta as an exact hi + lo split
+                const float4 l = *reinterpret_cast<const float4 *>(delta_lo + c * D + i);
+                d = make_float4(d.x + l.x, d.y + l.y, d.z + l.z, d.w + l.w);
+            }
             const float4 m = *reinterpret_cast<const float4 *>(mean + i);
             x = make_float4(d.x + m.x, d.y + m.y, d.z + m.z, d.w + m.w);
             *reinterpret_cast<float4 *>(pos + c * D + i) = x;
@@ -217,6 +205,7 @@ __global__ void __launch_bounds__(256) dense_gemm_simt_kernel(const float *__res
 
 int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode, cudaStream_t stream);  // mmc_dense_tc.cu
 int dense_tc_prepare(DenseState *st);
+int dense_tc_split_delta(DenseState *st, cudaStream_t stream);
 void dense_tc_destroy(DenseState *st);
 
 // ---------------------------------------------------------------- host driver
@@ -278,6 +267,10 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
     for (int64_t s = 0; s < steps; ++s) {
         dense_begin_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, st->d_delta[0], st->d_mom, st->d_scal,
                                                       a.momenta, a.u, M, D, a.chain_offset, (uint32_t)(a.step_base + s), s, key);
+        if (a.gemm_path == 1) {
+            int rc = dense_tc_split_delta(st, stream);
+            if (rc) return rc;
+        }
         int cur = 0;
         for (int l = 0; l <= a.n_leapfrog; ++l) {
             const int mode = l == 0 ? kModeFirst : (l == a.n_leapfrog ? kModeLast : kModeMid);
@@ -291,7 +284,9 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
             if (mode != kModeLast) cur ^= 1;
         }
         const bool collect = s >= a.n_discard && a.out;
-        dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, st->d_delta[cur], st->d_scal, st->norm_const,
+        const float *fin = a.gemm_path == 1 ? st->d_delta_split[cur] : st->d_delta[cur];
+        const float *fin_lo = a.gemm_path == 1 ? st->d_delta_split[cur] + (size_t)M * D : nullptr;
+        dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, fin, fin_lo, st->d_scal, st->norm_const,
                                                        collect ? a.out : nullptr, a.trace, a.accept_count, M, D, a.n_collect,
                                                        collect ? s - a.n_discard : 0, s);
     }

@@ -8,7 +8,23 @@
 
 namespace mmc {
 
-struct DenseState;  // device buffers of the dense-Gaussian HMC path (mmc_dense.cu)
+// device buffers of the dense-Gaussian HMC path
+struct DenseState {
+    int D = 0;
+    int64_t chains = 0;
+    float norm_const = 0.f;
+    float *d_mean = nullptr;      // [D]
+    float *d_prec = nullptr;      // [D, D] row-major, symmetric
+    float *d_delta[2] = {nullptr, nullptr};  // [chains, D] ping-pong (FP32 path)
+    float *d_mom = nullptr;       // [chains, D]
+    float *d_scal = nullptr;      // [6, chains]: ke_cur, quad_cur, ke_prop, quad_prop, u, (spare)
+    // tensor-core path operands (hi/lo TF32 splits), see mmc_dense_tc.cu
+    float *d_prec_split = nullptr;                  // [2, D, D]
+    float *d_delta_split[2] = {nullptr, nullptr};   // ping-pong of [2 (hi, lo), chains, D]
+    void *tc = nullptr;                             // tensor maps
+};
+
+enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };
 
 struct DenseRunArgs {
     float *positions;        // [chains, D] in/out

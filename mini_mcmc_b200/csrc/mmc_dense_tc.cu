@@ -1,12 +1,341 @@
-// K3 tensor-core path (tcgen05 + TMA): placeholder until the kernel lands.
+// K3 tensor-core path: Z = Delta . P on tcgen05 (5th-gen tensor cores), operands staged by TMA, fp32
+// accumulators in TMEM, leapfrog fused into the epilogue (see mmc_dense.cu for the step structure).
+//
+// Precision: the reference computes this contraction in fp32 (burn NdArray matmul).  Plain TF32 (10-bit mantissa)
+// misses the 1e-5 parity bar, so every operand is split x = hi + lo with hi = x truncated to TF32 and
+// lo = x - hi (exact), and three MMAs accumulate into the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped
+// lo.lo term is < 2^-20 relative).  The splits are produced by the previous epilogue, so they cost no extra pass.
+//
+// Tile: BLOCK_M 128 chains x BLOCK_N 256 columns x BLOCK_K 32 (one 128-byte swizzle row of fp32), UMMA
+// 128 x 256 x 8 (kind::tf32, cta_group::1).  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (each owns the 32 TMEM lanes of its quarter).
+// Pipeline: full/empty mbarriers per shared-memory stage (TMA -> MMA -> tcgen05.commit), one tmem_full barrier
+// (MMA -> epilogue).
+#include <cuda.h>
+
+#include <vector>
+
 #include "mmc_dense.cuh"
 
 namespace mmc {
-struct DenseState;
-int dense_tc_prepare(DenseState *) {
-    set_error("dense Gaussian: the tcgen05 path is not built yet");
-    return MMC_ERR_UNSUPPORTED;
+
+
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32, kStages = 2, UMMA_K = 8;
+constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB (one of hi / lo)
+constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // 96 KB
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 256;
+
+struct Maps {
+    CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int dense_gemm_tc(DenseState *, int, int64_t, int, float, int, cudaStream_t) { return MMC_ERR_UNSUPPORTED; }
-void dense_tc_destroy(DenseState *) {}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset = 8 rows x 128 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = 256
+__host__ __device__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const float *__restrict__ a_hi, const float *__restrict__ a_lo, float *__restrict__ n_hi,
+                     float *__restrict__ n_lo, float *__restrict__ mom, float *__restrict__ scal, int64_t M, int D, float eps,
+                     int mode) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int64_t m0 = (int64_t)blockIdx.y * BM;
+    const int nk = D / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t st = smem_base + s * kStageBytes;
+                mbar_expect_tx(full_bar(s), kStageBytes);
+                tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, (int)m0);
+                tma_load_2d(st + kABytes, &map_a_lo, full_bar(s), kb * BK, (int)m0);
+                tma_load_2d(st + 2 * kABytes, &map_b_hi, full_bar(s), kb * BK, n0);
+                tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, full_bar(s), kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc();
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t st = smem_base + s * kStageBytes;
+                const uint64_t da_hi = make_smem_desc(st), da_lo = make_smem_desc(st + kABytes);
+                const uint64_t db_hi = make_smem_desc(st + 2 * kABytes), db_lo = make_smem_desc(st + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the swizzle row
+                    tcgen05_mma_tf32(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_mma_tf32(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
+                    tcgen05_mma_tf32(tmem_base, da_lo + koff, db_hi + koff, idesc, 1u);
+                }
+                tcgen05_commit(empty_bar(s));   // frees the stage once the MMAs above have read it
+            }
+            tcgen05_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> fused leapfrog -> global =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int64_t m = m0 + row;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const float eps_half = eps * 0.5f;
+        float quad = 0.f, ke = 0.f;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
+            if (m < M) {
+                const int64_t off = m * D + n0 + chunk * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 h4 = *reinterpret_cast<const float4 *>(a_hi + off + j);
+                    const float4 l4 = *reinterpret_cast<const float4 *>(a_lo + off + j);
+                    float4 p4 = *reinterpret_cast<const float4 *>(mom + off + j);
+                    float dl[4] = {h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w};
+                    float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+                    float dn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float z = __uint_as_float(r[j + e]);
+                        const float gh = -z * eps_half;
+                        if (mode != kModeMid) quad = fmaf(z, dl[e], quad);
+                        if (mode == kModeFirst) {
+                            pp[e] = pp[e] + gh;
+                            dn[e] = fmaf(eps, pp[e], dl[e]);
+                        } else if (mode == kModeMid) {
+                            pp[e] = (pp[e] + gh) + gh;
+                            dn[e] = fmaf(eps, pp[e], dl[e]);
+                        } else {
+                            pp[e] = pp[e] + gh;
+                            ke = fmaf(pp[e], pp[e], ke);
+                            dn[e] = dl[e];
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(mom + off + j) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                    if (mode != kModeLast) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dn[e]); lo[e] = dn[e] - hi[e]; }
+                        *reinterpret_cast<float4 *>(n_hi + off + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4 *>(n_lo + off + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+        }
+        if (m < M && mode != kModeMid) {
+            atomicAdd(scal + (mode == kModeFirst ? 1 : 3) * M + m, quad);
+            if (mode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+__global__ void split_kernel(const float *__restrict__ src, float *__restrict__ hi, float *__restrict__ lo, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4 *>(src)[i];
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    reinterpret_cast<float4 *>(hi)[i] = h;
+    reinterpret_cast<float4 *>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_2d(EncodeTiledFn fn, CUtensorMap *map, float *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return MMC_ERR_CUDA;
+    }
+    return MMC_OK;
+}
+
+}  // namespace tc
+
+int dense_tc_prepare(DenseState *st) {
+    if (st->tc) return MMC_OK;
+    const int D = st->D;
+    const int64_t M = st->chains;
+    MMC_REQUIRE(D % tc::BN == 0, "tcgen05 path needs dim %% 256 == 0, got %d", D);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MMC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MMC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    const size_t md = (size_t)M * D * sizeof(float), dd = (size_t)D * D * sizeof(float);
+    MMC_CUDA(cudaMalloc((void **)&st->d_prec_split, 2 * dd));
+    MMC_CUDA(cudaMalloc((void **)&st->d_delta_split[0], 2 * md));
+    MMC_CUDA(cudaMalloc((void **)&st->d_delta_split[1], 2 * md));
+    const int64_t n4 = (int64_t)D * D / 4;
+    tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(st->d_prec, st->d_prec_split, st->d_prec_split + (size_t)D * D, n4);
+    MMC_CUDA(cudaGetLastError());
+    MMC_CUDA(cudaDeviceSynchronize());
+    tc::Maps *maps = new tc::Maps();
+    int rc = MMC_OK;
+    for (int b = 0; b < 2 && !rc; ++b) {
+        rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->a_hi[b], st->d_delta_split[b], (uint64_t)M, (uint64_t)D, tc::BM);
+        if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->a_lo[b], st->d_delta_split[b] + (size_t)M * D, (uint64_t)M, (uint64_t)D, tc::BM);
+    }
+    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_hi, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN);
+    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_lo, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN);
+    if (rc) { delete maps; return rc; }
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    st->tc = maps;
+    return MMC_OK;
+}
+
+// splits the full-precision Delta written by dense_begin_kernel into buffer 0 of the hi/lo ping-pong
+int dense_tc_split_delta(DenseState *st, cudaStream_t stream) {
+    const int64_t n4 = st->chains * st->D / 4;
+    float *hi = st->d_delta_split[0];
+    tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(st->d_delta[0], hi, hi + (size_t)st->chains * st->D, n4);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode, cudaStream_t stream) {
+    tc::Maps *maps = static_cast<tc::Maps *>(st->tc);
+    const size_t md = (size_t)M * D;
+    float *a_hi = st->d_delta_split[cur], *a_lo = a_hi + md;
+    float *n_hi = st->d_delta_split[cur ^ 1], *n_lo = n_hi + md;
+    const dim3 grid((unsigned)(D / tc::BN), (unsigned)((M + tc::BM - 1) / tc::BM));
+    tc::dense_gemm_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(maps->a_hi[cur], maps->a_lo[cur], maps->b_hi,
+                                                                             maps->b_lo, a_hi, a_lo, n_hi, n_lo, st->d_mom,
+                                                                             st->d_scal, M, D, eps, mode);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+void dense_tc_destroy(DenseState *st) {
+    if (st && st->tc) {
+        delete static_cast<tc::Maps *>(st->tc);
+        st->tc = nullptr;
+    }
+}
+
 }  // namespace mmc

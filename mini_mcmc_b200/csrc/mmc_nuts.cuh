@@ -35,12 +35,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// two independent sums in one butterfly (the shuffles of a step pipeline instead of serialising)
+template <class A>
+__device__ __forceinline__ void warp_sum2(float &a, float &b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ta = __shfl_xor_sync(kFull, a, o);
+        const float tb = __shfl_xor_sync(kFull, b, o);
+        a = A::add(a, ta);
+        b = A::add(b, tb);
+    }
+}
+
 // ---------------------------------------------------------------- warp-form targets
 // interface: float logp_grad(const float (&x)[E], float (&g)[E], int lane) const  -> logp (same in all lanes)
+//            kPartial = true: the returned value is this lane's partial sum of logp (the caller reduces it
+//            together with the kinetic energy in one butterfly); false: already the full logp in every lane.
 
 // RosenbrockND (src/distributions.rs:531-547) for any D <= 32 E.
 template <class A, int E>
 struct WRosenbrockND {
+    static constexpr bool kPartial = true;
     int D;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
         const float xn = __shfl_down_sync(kFull, x[0], 1);
@@ -64,13 +79,14 @@ struct WRosenbrockND {
             const float tp = e == 0 ? tprev : t[e == 0 ? 0 : e - 1];
             g[e] = A::add(A::mul(-200.0f, tp), g[e]);
         }
-        return -warp_sum<A>(acc);
+        return -acc;
     }
 };
 
 // StdNormal (src/nuts.rs:1024-1037) for any D <= 32 E (padding elements are zero).
 template <class A, int E>
 struct WStdNormal {
+    static constexpr bool kPartial = true;
     int D;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
         float acc = 0.0f;
@@ -79,13 +95,14 @@ struct WStdNormal {
             acc = A::mad(A::mul(x[e], x[e]), 0.5f, acc);
             g[e] = -x[e];
         }
-        return -warp_sum<A>(acc);
+        return -acc;
     }
 };
 
 // Any small thread-form target (kDim <= 4): every lane gathers the full vector and evaluates it.
 template <class T, int E>
 struct WSmall {
+    static constexpr bool kPartial = false;
     T t;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int lane) const {
         constexpr int K = T::kDim;
@@ -228,6 +245,16 @@ struct NutsWarp {
         for (int k = 0; k < E; ++k) s = A::mad(m[k], m[k], s);
         return warp_sum<A>(s);
     }
+    // completes a target evaluation: full logp (lp_io) and sum m^2, one fused butterfly when logp is partial
+    __device__ __forceinline__ float finish(float &lp_io, const float (&m)[E]) {
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < E; ++k) s = A::mad(m[k], m[k], s);
+        if (Target::kPartial) warp_sum2<A>(lp_io, s);
+        else s = warp_sum<A>(s);
+        return s;
+    }
+    __device__ __forceinline__ float full_logp(float lp) { return Target::kPartial ? warp_sum<A>(lp) : lp; }
     // stop_criterion, src/nuts.rs:963-977 (true = keep going)
     __device__ __forceinline__ bool keep_going(const float (&xm)[E], const float (&xp)[E], const float (&pm)[E],
                                                const float (&pp)[E]) {
@@ -238,8 +265,7 @@ struct NutsWarp {
             dm = A::mad(diff, pm[k], dm);
             dp = A::mad(diff, pp[k], dp);
         }
-        dm = warp_sum<A>(dm);
-        dp = warp_sum<A>(dp);
+        warp_sum2<A>(dm, dp);
         return dm >= 0.0f && dp >= 0.0f;
     }
     __device__ __forceinline__ bool all_finite(const float (&v)[E]) {
@@ -254,12 +280,12 @@ struct NutsWarp {
         float g0[E], x[E], m[E], g[E];
         const ST half = (ST)0.5;
         ST epsilon = (ST)1.0;
-        const float ulogp = tgt.logp_grad(x0, g0, lane);
+        const float ulogp = full_logp(tgt.logp_grad(x0, g0, lane));
         ++n_grad;
         auto leap = [&](ST e) {
 #pragma unroll
             for (int k = 0; k < E; ++k) { x[k] = x0[k]; m[k] = m0[k]; g[k] = g0[k]; }
-            return leapfrog(x, m, g, e);
+            return full_logp(leapfrog(x, m, g, e));
         };
         float ulogp_prime = leap(epsilon);
         ST k = (ST)1.0;
@@ -292,8 +318,9 @@ struct NutsWarp {
         ST ta = (ST)0.0;
         bool ts = true;
         for (uint32_t leaf = 0; leaf < n_leaves; ++leaf) {
-            const float lp = leapfrog(cx, cm, cg, veps);
-            const float joint_f = A::sub(lp, A::mul(sumsq(cm), 0.5f));
+            float lp = leapfrog(cx, cm, cg, veps);
+            const float ss = finish(lp, cm);
+            const float joint_f = A::sub(lp, A::mul(ss, 0.5f));
             const ST joint = (ST)(double)joint_f;
             tn = (logu < joint) ? 1 : 0;
             ts = (logu - (ST)1000.0) < joint;
@@ -413,9 +440,10 @@ __global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target 
             w.q = 0; w.q_batch = 0xffffffffu;
             float mom0[E], grad[E];
             w.draw_normals(mom0);
-            const float ulogp = tgt.logp_grad(pos, grad, lane);
+            float ulogp = tgt.logp_grad(pos, grad, lane);
             ++w.n_grad;
-            const float joint_f = A::sub(ulogp, A::mul(w.sumsq(mom0), 0.5f));
+            const float ss0 = w.finish(ulogp, mom0);
+            const float joint_f = A::sub(ulogp, A::mul(ss0, 0.5f));
             const ST joint = (ST)(double)joint_f;
             const ST logu = joint - w.draw_exp1();
             float xm[E], pm[E], gm[E], xp[E], pp[E], gp[E];

@@ -23,21 +23,15 @@ def make_problem(D, seed=42):
     return mean, cov
 
 
-def tc_available(mm):
-    try:
-        mean, cov = make_problem(128)
-        h = mm.HMC(mm.DenseGaussian(mean, cov), np.zeros((128, 128), dtype=np.float32), 0.05, 1).set_gemm_path(1)
-        h.run(1, 0)
-        return True
-    except Exception:
-        return False
+def tc_supported(D):
+    return D % 256 == 0   # tcgen05 tile is 128 x 256
 
 
 @pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
-    if path == 1 and not tc_available(mm):
-        pytest.skip("tcgen05 path not built")
+    if path == 1 and not tc_supported(D):
+        pytest.skip("tcgen05 path needs dim % 256 == 0")
     mean, cov = make_problem(D)
     tgt = mm.DenseGaussian(mean, cov)
     otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
@@ -62,12 +56,34 @@ def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
     np.testing.assert_allclose(h.positions[same], exp_pos[same], rtol=1e-5, atol=2e-5)
 
 
-def test_dense_hmc_native_tape_and_moments(mm):
-    D, chains, L = 128, 512, 8
+def test_tensor_core_path_matches_fp32_path(mm):
+    """Same replayed transition through both GEMM paths (3xTF32 on tcgen05 vs FP32 SIMT): ragged chain count."""
+    D, chains, L = 512, 333, 6
+    mean, cov = make_problem(D, seed=9)
+    tgt = mm.DenseGaussian(mean, cov)
+    rng = np.random.default_rng(1)
+    init = (rng.normal(size=(chains, D)) + mean).astype(np.float32)
+    mom = rng.normal(size=(3, chains, D)).astype(np.float32)
+    u = rng.random((3, chains)).astype(np.float32)
+    outs = []
+    for path in (0, 1):
+        h = mm.HMC(tgt, init, 0.05, L).set_gemm_path(path)
+        tr = np.zeros((3, chains, 4), dtype=np.float32)
+        outs.append((h.run(3, 0, replay=dict(momenta=mom, u=u), trace=tr), tr))
+    (a, ta), (b, tb) = outs
+    assert (ta[..., 3] == tb[..., 3]).mean() > 0.995
+    same = (ta[..., 3] == tb[..., 3]).all(axis=0)
+    np.testing.assert_allclose(a[same], b[same], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(ta[..., :2], tb[..., :2], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("path,D", [(0, 128), (1, 256)])
+def test_dense_hmc_native_tape_and_moments(mm, path, D):
+    chains, L = 512, 8
     mean, cov = make_problem(D, seed=3)
     tgt = mm.DenseGaussian(mean, cov)
     init = np.tile(mean.astype(np.float32), (chains, 1))
-    h = mm.HMC(tgt, init, 0.15, L).set_seed(5).set_chain_offset(1000)
+    h = mm.HMC(tgt, init, 0.15, L).set_seed(5).set_chain_offset(1000).set_gemm_path(path)
     mom, u = h.export_tape(0, 3)
     got = h.run(3, 0)
     otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
