@@ -161,15 +161,55 @@ struct NutsWarp {
     uint32_t q_batch = 0xffffffffu;
     uint4 ubatch;
     int64_t cur_n = 0, cur_e = 0, cur_u = 0;  // replay cursors
-    unsigned long long n_grad = 0, n_unif = 0;
+    uint32_t n_grad = 0, n_unif = 0;      // per chain, flushed into 64-bit totals by the caller
+    // per-level scalars of the pending halves live in shared memory (warp-uniform broadcast reads)
+    int *s_n, *s_na;
+    double *s_a;
 
-    __device__ NutsWarp(const Target &t, const NutsParams &pp, int ln, float *ss, float *gs)
-        : tgt(t), p(pp), lane(ln), s_stack(ss), g_stack(gs) {}
+    __device__ NutsWarp(const Target &t, const NutsParams &pp, int ln, float *ss, float *gs, void *scal)
+        : tgt(t), p(pp), lane(ln), s_stack(ss), g_stack(gs) {
+        s_a = reinterpret_cast<double *>(scal);
+        s_n = reinterpret_cast<int *>(s_a + 16);
+        s_na = s_n + 16;
+    }
 
-    __device__ __forceinline__ float *level_ptr(int lvl, int which) {
+    // pending-subtree vectors (which: 0 = first-leaf x, 1 = first-leaf p, 2 = proposal): explicit shared / global
+    // paths so the compiler emits LDS/STS and LDG/STG (vectorised when E == 4) instead of generic accesses
+    __device__ __forceinline__ void load_level(int lvl, int which, float (&v)[E]) {
         constexpr int V = 32 * E;
-        return lvl < kNutsSmemLevels ? s_stack + (lvl * 3 + which) * V + lane * E
-                                     : g_stack + ((lvl - kNutsSmemLevels) * 3 + which) * V + lane * E;
+        if (lvl < kNutsSmemLevels) {
+            const float *src = s_stack + (lvl * 3 + which) * V + lane * E;
+            if (E == 4) { const float4 t = *reinterpret_cast<const float4 *>(src); v[0] = t.x; v[1 % E] = t.y; v[2 % E] = t.z; v[3 % E] = t.w; }
+            else {
+#pragma unroll
+                for (int k = 0; k < E; ++k) v[k] = src[k];
+            }
+        } else {
+            const float *src = g_stack + ((lvl - kNutsSmemLevels) * 3 + which) * V + lane * E;
+            if (E == 4) { const float4 t = __ldcg(reinterpret_cast<const float4 *>(src)); v[0] = t.x; v[1 % E] = t.y; v[2 % E] = t.z; v[3 % E] = t.w; }
+            else {
+#pragma unroll
+                for (int k = 0; k < E; ++k) v[k] = __ldcg(src + k);
+            }
+        }
+    }
+    __device__ __forceinline__ void store_level(int lvl, int which, const float (&v)[E]) {
+        constexpr int V = 32 * E;
+        if (lvl < kNutsSmemLevels) {
+            float *dst = s_stack + (lvl * 3 + which) * V + lane * E;
+            if (E == 4) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1 % E], v[2 % E], v[3 % E]);
+            else {
+#pragma unroll
+                for (int k = 0; k < E; ++k) dst[k] = v[k];
+            }
+        } else {
+            float *dst = g_stack + ((lvl - kNutsSmemLevels) * 3 + which) * V + lane * E;
+            if (E == 4) __stcg(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1 % E], v[2 % E], v[3 % E]));
+            else {
+#pragma unroll
+                for (int k = 0; k < E; ++k) __stcg(dst + k, v[k]);
+            }
+        }
     }
 
     // ---- random draws (native Philox keying is documented in minimcmc.h)
@@ -310,11 +350,11 @@ struct NutsWarp {
     // One doubling = build_tree(edge, v, j), src/nuts.rs:764-946, iteratively.
     // cx/cm/cg: the edge to extend (in) and the new edge (out).  Outputs the subtree proposal, n', s', alpha, n_alpha.
     __device__ void doubling(float (&cx)[E], float (&cm)[E], float (&cg)[E], int v, int j, ST logu, ST eps, ST joint0,
-                             float (&prop)[E], long long &n_out, bool &s_out, ST &alpha_out, long long &nalpha_out) {
+                             float (&prop)[E], int &n_out, bool &s_out, ST &alpha_out, int &nalpha_out) {
         const ST veps = (ST)v * eps;
         const uint32_t n_leaves = 1u << j;
         float tfx[E], tfm[E];  // first leaf of the subtree currently being merged upward
-        long long tn = 0, tna = 0;
+        int tn = 0, tna = 0;
         ST ta = (ST)0.0;
         bool ts = true;
         for (uint32_t leaf = 0; leaf < n_leaves; ++leaf) {
@@ -334,19 +374,18 @@ struct NutsWarp {
             while (true) {
                 while (lvl < j && ((leaf >> lvl) & 1u)) {
                     // merge pending first half A = stack[lvl] with the later half T
-                    const float *afx = level_ptr(lvl, 0), *afm = level_ptr(lvl, 1), *apr = level_ptr(lvl, 2);
-                    const long long an = s_n[lvl], ana = s_na[lvl];
+                    const int an = s_n[lvl], ana = s_na[lvl];
                     const ST aa = (ST)s_a[lvl];
                     const double u = draw_uniform(true);
-                    long long denom = an + tn;
-                    if (denom < 1) denom = 1;
-                    const bool take_b = u < ((double)tn / (double)denom);
-#pragma unroll
-                    for (int k = 0; k < E; ++k) {
-                        tfx[k] = afx[k];
-                        tfm[k] = afm[k];
-                        if (!take_b) prop[k] = apr[k];
-                    }
+                    // u < n'' / max(n' + n'', 1) in f64 (src/nuts.rs:910-911); the quotient is exactly 0 or 1 in the
+                    // two common cases, which avoids the f64 division without changing the decision
+                    bool take_b;
+                    if (tn == 0) take_b = false;
+                    else if (an == 0) take_b = u < 1.0;
+                    else take_b = u < ((double)tn / (double)(an + tn));
+                    load_level(lvl, 0, tfx);
+                    load_level(lvl, 1, tfm);
+                    if (!take_b) load_level(lvl, 2, prop);
                     tn += an;
                     // s' = s'_1 && s'_2 && stop_criterion(minus, plus); pending halves always have s' = true
                     if (ts) ts = (v == 1) ? keep_going(tfx, cx, tfm, cm) : keep_going(cx, tfx, cm, tfm);
@@ -356,10 +395,11 @@ struct NutsWarp {
                 }
                 if (lvl == j) break;
                 if (ts) {  // park the finished first half at this level and build the next leaf
-                    float *afx = level_ptr(lvl, 0), *afm = level_ptr(lvl, 1), *apr = level_ptr(lvl, 2);
-#pragma unroll
-                    for (int k = 0; k < E; ++k) { afx[k] = tfx[k]; afm[k] = tfm[k]; apr[k] = prop[k]; }
-                    s_n[lvl] = tn; s_na[lvl] = tna; s_a[lvl] = (double)ta;
+                    store_level(lvl, 0, tfx);
+                    store_level(lvl, 1, tfm);
+                    store_level(lvl, 2, prop);
+                    if (lane == 0) { s_n[lvl] = tn; s_na[lvl] = tna; s_a[lvl] = (double)ta; }
+                    __syncwarp();
                     pushed = true;
                     break;
                 }
@@ -369,10 +409,6 @@ struct NutsWarp {
         }
         n_out = tn; s_out = ts; alpha_out = ta; nalpha_out = tna;
     }
-
-    // per-level scalars of the pending halves (warp-uniform, kept in registers of every lane)
-    long long s_n[16], s_na[16];
-    double s_a[16];
 };
 
 template <class Target, class A, class ST, int E, bool kReplay>
@@ -384,8 +420,10 @@ __global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target 
     const int64_t warp_slot = (int64_t)blockIdx.x * kNutsWarps + warp;
     const int n_glob = p.max_depth > kNutsSmemLevels ? p.max_depth - kNutsSmemLevels : 0;
     float *g_stack = p.scratch + warp_slot * (int64_t)n_glob * 3 * V;
-    NutsWarp<Target, A, ST, E, kReplay> w(tgt, p, lane, s_stack, g_stack);
-    unsigned long long my_depth_count = 0, n_trans = 0;
+    // per-warp scalar area after the vector stacks: 16 x (double alpha, int n, int n_alpha) = 256 B
+    void *s_scal = reinterpret_cast<unsigned char *>(nuts_smem + kNutsWarps * kNutsSmemLevels * 3 * V) + warp * 256;
+    NutsWarp<Target, A, ST, E, kReplay> w(tgt, p, lane, s_stack, g_stack, s_scal);
+    unsigned long long my_depth_count = 0, n_trans = 0, tot_grad = 0, tot_unif = 0;
 
     while (true) {
         long long c = 0;
@@ -454,15 +492,15 @@ __global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target 
                 gm[k] = gp[k] = grad[k];
             }
             int j = 0;
-            long long n = 1;
+            int n = 1;
             bool s = true;
             ST alpha = (ST)0.0;
-            long long n_alpha = 0;
+            int n_alpha = 0;
             while (s) {
                 const ST u1 = (ST)w.draw_uniform(false);
                 const int v = (u1 < (ST)0.5) ? 1 : -1;
                 float prop[E];
-                long long n_prime;
+                int n_prime;
                 bool s_prime;
                 if (v == -1) w.doubling(xm, pm, gm, v, j, logu, epsilon, joint, prop, n_prime, s_prime, alpha, n_alpha);
                 else w.doubling(xp, pp, gp, v, j, logu, epsilon, joint, prop, n_prime, s_prime, alpha, n_alpha);
@@ -503,11 +541,13 @@ __global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target 
             st[0] = (double)epsilon; st[1] = (double)epsilon_bar; st[2] = (double)h_bar; st[3] = (double)mu;
             st[4] = (double)m;
         }
+        tot_grad += w.n_grad; tot_unif += w.n_unif;
+        w.n_grad = 0; w.n_unif = 0;
     }
     if (lane == 0) {
-        atomicAdd(&p.counters[1], w.n_grad);
+        atomicAdd(&p.counters[1], tot_grad);
         atomicAdd(&p.counters[2], n_trans);
-        atomicAdd(&p.counters[3], w.n_unif);
+        atomicAdd(&p.counters[3], tot_unif);
     }
     if (my_depth_count) atomicAdd(&p.counters[8 + lane], my_depth_count);
 }

@@ -39,7 +39,7 @@ int nuts_launch_one(const Target &tgt, NutsParams p, int sm_count, int64_t *grid
                     bool query_only, cudaStream_t stream) {
     auto kernel = nuts_run_kernel<Target, A, ST, E, kReplay>;
     constexpr int V = 32 * E;
-    const size_t smem = (size_t)kNutsWarps * kNutsSmemLevels * 3 * V * sizeof(float);
+    const size_t smem = (size_t)kNutsWarps * kNutsSmemLevels * 3 * V * sizeof(float) + (size_t)kNutsWarps * 256;
     int per_sm = 0;
     MMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kNutsWarps * 32, smem));
     if (per_sm < 1) per_sm = 1;
