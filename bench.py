@@ -184,6 +184,7 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
