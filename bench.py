@@ -274,9 +274,13 @@ def main():
         if distributed:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        per_draw = handles[0].d2h_bytes_per_draw()
         e2e = {"value": chains * steps_per_run * e2e_steps * world / dt, "unit": UNIT,
-               "h2d_bytes_per_step": chains * 8, "d2h_bytes_per_step": full_bytes, "steps": e2e_steps,
-               "host_batches_per_step": n_batches, "ms_per_step": dt / e2e_steps * 1e3}
+               "h2d_bytes_per_step": chains * 8, "d2h_bytes_per_step": chains * N_COLLECT * per_draw,
+               "host_result_bytes_per_step": full_bytes, "steps": e2e_steps,
+               "host_batches_per_step": n_batches, "ms_per_step": dt / e2e_steps * 1e3,
+               "note": "draws cross PCIe as u8 and are widened to the caller's u64 [chains, n_collect] array by host "
+                       "threads inside mmc_mh_run, overlapped with sampling + copy of the next block of chains"}
         assert abs(float(out_np[::64, -1, 0].astype(np.float64).mean()) - LAMBDA) < 0.2
         del handles
 

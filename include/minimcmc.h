@@ -134,6 +134,9 @@ int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode);
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay);
 int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, const mmc_replay_mh *replay_dev,
                    void *stream);
+/* bytes that cross PCIe per collected draw in mmc_mh_run (8 for the plain u64 copy; 1 or 2 when the Poisson path
+ * ships compact draws and widens them to u64 on the host threads) */
+int mmc_mh_d2h_bytes_per_draw(mmc_mh *h);
 int mmc_mh_get_state(mmc_mh *h, void *state_host);
 int mmc_mh_set_state(mmc_mh *h, const void *state_host);
 void mmc_mh_destroy(mmc_mh *h);

@@ -1,5 +1,6 @@
 // Metropolis-Hastings C ABI (see include/minimcmc.h) — host side of K1.
 // Compiled with -fmad=false (see mmc_mh.cuh).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -34,7 +35,17 @@ struct mmc_mh {
     size_t d_replay_bytes[3] = {0, 0, 0};
     double *d_trace = nullptr;
     size_t d_trace_bytes = 0;
+    // compact device->host pipeline (Poisson): double-buffered device + pinned host staging
+    void *d_compact[2] = {nullptr, nullptr};
+    void *h_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_event[2] = {nullptr, nullptr};
 };
+
+namespace mmc {
+void widen_to_u64(const void *src, int elem_bytes, uint64_t *dst, size_t n);
+}
 
 namespace {
 
@@ -152,10 +163,12 @@ int run_cont(mmc_mh *h, int64_t n_collect, int64_t n_discard, double *out_dev, c
     }
 }
 
-int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_dev, const mmc_replay_mh *rp,
-                cudaStream_t stream) {
+// compact != 0: out_dev receives u8 (table_len <= 256) or u16 draws instead of u64 (host-API fast path)
+int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, const mmc_replay_mh *rp,
+                cudaStream_t stream, int64_t chain_begin = 0, int64_t chain_count = -1, bool compact = false) {
+    if (chain_count < 0) chain_count = h->chains;
     MhPoissonParams p{};
-    p.state = (uint64_t *)h->d_state;
+    p.state = (uint64_t *)h->d_state + chain_begin;
     p.out = out_dev;
     p.flip = rp ? rp->flip : nullptr;
     p.u = rp ? rp->u : nullptr;
@@ -165,8 +178,8 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     p.lambda = h->target.params[0];
     p.ln_lambda = h->ln_lambda;
     p.ln_half = h->ln_half;
-    p.chains = h->chains;
-    p.chain_offset = h->chain_offset;
+    p.chains = chain_count;
+    p.chain_offset = h->chain_offset + chain_begin;
     p.step_base = h->step;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
@@ -183,7 +196,7 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     const bool replay = rp && rp->flip && rp->u;
     MMC_REQUIRE(!rp || replay, "Poisson MH replay needs both flip and u tapes");
     const int block = kPoisWarps * 32;
-    const int64_t warps = (h->chains + 31) / 32;
+    const int64_t warps = (chain_count + 31) / 32;
     const unsigned grid = (unsigned)((warps + kPoisWarps - 1) / kPoisWarps);
     auto launch = [&](auto kernel, size_t tile_bytes) -> int {
         const size_t smem = (size_t)h->table_len * 16 + (size_t)kPoisWarps * tile_bytes;
@@ -200,6 +213,12 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_d
     int tile = h->table_len <= 256 ? h->tile_u8 : h->tile_u16;
     if (const char *e = getenv("MMC_POIS_TILE")) tile = atoi(e);
     const bool u8 = h->table_len <= 256 && !getenv("MMC_POIS_U16");
+    if (compact) {
+        MMC_REQUIRE(!getenv("MMC_POIS_U16"), "compact path and MMC_POIS_U16 are exclusive");
+        if (h->table_len <= 256)
+            return launch(mh_poisson_kernel<false, true, 128, uint8_t, uint8_t>, PoisTile<128, uint8_t>::kWarpBytes);
+        return launch(mh_poisson_kernel<false, true, 64, uint16_t, uint16_t>, PoisTile<64, uint16_t>::kWarpBytes);
+    }
     if (u8) {
         if (tile >= 256) return launch(mh_poisson_kernel<false, true, 256, uint8_t>, PoisTile<256, uint8_t>::kWarpBytes);
         if (tile >= 128) return launch(mh_poisson_kernel<false, true, 128, uint8_t>, PoisTile<128, uint8_t>::kWarpBytes);
@@ -298,8 +317,59 @@ int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_de
     return MMC_OK;
 }
 
+// Poisson host path: sample a block of chains into the compact (u8/u16) device buffer, copy it to pinned staging,
+// and widen into the caller's u64 array on the host threads while the next block is sampled and copied.
+static int mh_run_poisson_compact(mmc_mh *h, int64_t n_collect, int64_t n_discard, uint64_t *out_host) {
+    const int eb = h->table_len <= 256 ? 1 : 2;
+    const size_t row_bytes = (size_t)n_collect * eb;
+    int64_t group = (int64_t)((size_t)(384u << 20) / (row_bytes ? row_bytes : 1));
+    group = (group / 256) * 256;
+    if (group < 256) group = 256;
+    if (group > h->chains) group = h->chains;
+    const size_t need = (size_t)group * row_bytes;
+    if (h->stage_bytes < need) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->d_compact[k]) cudaFree(h->d_compact[k]);
+            if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+            h->d_compact[k] = h->h_stage[k] = nullptr;
+        }
+        h->stage_bytes = 0;
+        for (int k = 0; k < 2; ++k) {
+            MMC_CUDA(cudaMalloc(&h->d_compact[k], need));
+            MMC_CUDA(cudaHostAlloc(&h->h_stage[k], need, cudaHostAllocDefault));
+            if (!h->pipe_stream[k]) MMC_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[k], cudaStreamNonBlocking));
+            if (!h->pipe_event[k]) MMC_CUDA(cudaEventCreateWithFlags(&h->pipe_event[k], cudaEventDisableTiming));
+        }
+        h->stage_bytes = need;
+    }
+    const int64_t n_groups = (h->chains + group - 1) / group;
+    auto widen = [&](int64_t g) {
+        const int64_t begin = g * group, cnt = std::min(group, h->chains - begin);
+        widen_to_u64(h->h_stage[g & 1], eb, out_host + begin * n_collect, (size_t)cnt * n_collect);
+    };
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const int k = (int)(g & 1);
+        const int64_t begin = g * group, cnt = std::min(group, h->chains - begin);
+        int rc = run_poisson(h, n_collect, n_discard, h->d_compact[k], nullptr, h->pipe_stream[k], begin, cnt, true);
+        if (rc) return rc;
+        MMC_CUDA(cudaMemcpyAsync(h->h_stage[k], h->d_compact[k], (size_t)cnt * row_bytes, cudaMemcpyDeviceToHost,
+                                 h->pipe_stream[k]));
+        MMC_CUDA(cudaEventRecord(h->pipe_event[k], h->pipe_stream[k]));
+        if (g >= 1) {
+            MMC_CUDA(cudaEventSynchronize(h->pipe_event[k ^ 1]));
+            widen(g - 1);   // overlaps the sampling + copy of block g
+        }
+    }
+    MMC_CUDA(cudaEventSynchronize(h->pipe_event[(n_groups - 1) & 1]));
+    widen(n_groups - 1);
+    h->step += n_collect + n_discard;
+    return check_error_flag(h, h->pipe_stream[0]);
+}
+
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
+    if (h->target.kind == MMC_T_POISSON && !replay && h->accept_mode == 1 && n_collect > 0 && !getenv("MMC_NO_COMPACT"))
+        return mh_run_poisson_compact(h, n_collect, n_discard, (uint64_t *)out_host);
     const int64_t steps = n_collect + n_discard;
     const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * 8;
     int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 8);
@@ -340,6 +410,12 @@ int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, 
     return check_error_flag(h, h->stream);
 }
 
+int mmc_mh_d2h_bytes_per_draw(mmc_mh *h) {
+    if (!h) return MMC_ERR_INVALID;
+    if (h->target.kind == MMC_T_POISSON && h->accept_mode == 1 && !getenv("MMC_NO_COMPACT")) return h->table_len <= 256 ? 1 : 2;
+    return 8 * h->dim;
+}
+
 int mmc_mh_get_state(mmc_mh *h, void *state_host) {
     MMC_REQUIRE(h && state_host, "mmc_mh_get_state: bad arguments");
     MMC_CUDA(cudaMemcpy(state_host, h->d_state, (size_t)h->chains * h->dim * 8, cudaMemcpyDeviceToHost));
@@ -362,6 +438,12 @@ void mmc_mh_destroy(mmc_mh *h) {
     cudaFree(h->d_out);
     for (auto p : h->d_replay) cudaFree(p);
     cudaFree(h->d_trace);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->d_compact[k]);
+        if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+        if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
+        if (h->pipe_event[k]) cudaEventDestroy(h->pipe_event[k]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -170,7 +170,7 @@ __global__ void mh_cont_export_tape_kernel(uint2 key, int64_t chains, int64_t ch
 //   log mode: evaluates that predicate in f64 on the device (needs V every step).
 struct MhPoissonParams {
     uint64_t *state;        // [chains] in/out
-    uint64_t *out;          // [chains, n_collect]
+    void *out;              // [chains, n_collect] of OutT (u64 = reference layout, or the compact u8/u16 stream)
     const uint8_t *flip;    // replay [chains, steps]
     const double *u;        // replay [chains, steps]
     const double *lnfact;   // [table_len]  sum_{i<=k} ln i, built by the host libm in the reference's order
@@ -208,8 +208,9 @@ __device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t i) {
     return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
 }
 
-template <bool kReplay, bool kThreshold, int T = 64, class Elem = uint16_t>
+template <bool kReplay, bool kThreshold, int T = 64, class Elem = uint16_t, class OutT = uint64_t>
 __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __grid_constant__ MhPoissonParams p) {
+    constexpr bool kWide = sizeof(OutT) == 8;   // false: OutT == Elem, draws leave the GPU in their compact form
     constexpr int kPoisTile = T;
     constexpr int kPoisPitch = PoisTile<T, Elem>::kPitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,14 +291,33 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     int col_lo = (int)(g_first & 3);   // first valid column of the current tile (non-zero only for an unaligned start)
     int tpos = col_lo;                 // next column to fill
     int64_t t_base = -(int64_t)col_lo; // collected index of column 0
-    // 16-byte stores need (chain * n_collect + t_base) even for every chain of the warp
-    const bool vec_ok = (p.n_collect % 2 == 0) && col_lo == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    // vector stores need aligned row segments for every chain of the warp
+    const bool vec_ok = kWide ? ((p.n_collect % 2 == 0) && col_lo == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0))
+                              : (((p.n_collect * sizeof(OutT)) % 4 == 0) && col_lo == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0));
     auto flush = [&]() {
         __syncwarp();
         const int nrows = (int)((p.chains - chain0 < 32) ? (p.chains - chain0) : 32);
-        uint64_t *row = p.out + chain0 * p.n_collect + t_base;
+        OutT *row = reinterpret_cast<OutT *>(p.out) + chain0 * p.n_collect + t_base;
         const Elem *trow = tile;
-        if (vec_ok && (tpos % 2 == 0)) {
+        if (!kWide) {
+            constexpr int kPer = 4 / (int)sizeof(Elem);   // columns per 32-bit word
+            if (vec_ok && (tpos % kPer == 0)) {
+                for (int r = 0; r < nrows; ++r) {
+                    for (int col = kPer * lane; col < tpos; col += 32 * kPer)
+                        __stcs(reinterpret_cast<unsigned int *>(row + col), *reinterpret_cast<const unsigned int *>(trow + col));
+                    row += p.n_collect;
+                    trow += kPoisPitch;
+                }
+            } else {
+                for (int r = 0; r < nrows; ++r) {
+                    for (int col = lane; col < tpos; col += 32)
+                        if (col >= col_lo) row[col] = (OutT)trow[col];
+                    row += p.n_collect;
+                    trow += kPoisPitch;
+                }
+            }
+        } else if (vec_ok && (tpos % 2 == 0)) {
             // every warp-wide store instruction covers one contiguous 512 B run of a row (full 32 B sectors):
             // lane l widens columns (2l, 2l+1) of each 64-column group into one 16-byte streaming store
 #pragma unroll 4
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
         } else {
             for (int r = 0; r < nrows; ++r) {
                 for (int col = lane; col < tpos; col += 32)
-                    if (col >= col_lo) __stcs(reinterpret_cast<unsigned long long *>(row + col), (unsigned long long)trow[col]);
+                    if (col >= col_lo) row[col] = (OutT)trow[col];
                 row += p.n_collect;
                 trow += kPoisPitch;
             }

@@ -87,6 +87,9 @@ class MetropolisHastings:
         sample = self.run(n_collect, n_discard)
         return sample, RunStats.from_sample(sample)
 
+    def d2h_bytes_per_draw(self) -> int:
+        return int(L.lib.mmc_mh_d2h_bytes_per_draw(self._h))
+
     def set_state(self, state):
         st = np.ascontiguousarray(state, dtype=self._np_dtype)
         assert st.shape == (self.n_chains, self.dim)

@@ -151,3 +151,20 @@ def test_poisson_large_device_resident_properties(mm):
         e, _ = oracle.mh_poisson_run_philox(4.0, np.zeros(1, dtype=np.uint64), n_collect, n_discard, seed=99,
                                             chain_offset=r)
         np.testing.assert_array_equal(out[r].cpu().numpy().astype(np.uint64), e[0, :, 0])
+
+
+def test_poisson_host_paths_agree(mm, monkeypatch):
+    """mmc_mh_run's compact device->host pipeline (u8 draws over PCIe, widened to u64 on host threads) returns the
+    same array as the plain u64 copy, including ragged block sizes and odd n_collect (unaligned rows)."""
+    for chains, n_collect, n_discard in ((70001, 501, 7), (4096, 1000, 0)):
+        init = np.zeros((chains, 1), dtype=np.uint64)
+        a = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(3).run(n_collect, n_discard)
+        monkeypatch.setenv("MMC_NO_COMPACT", "1")
+        b = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(3).run(n_collect, n_discard)
+        monkeypatch.delenv("MMC_NO_COMPACT")
+        np.testing.assert_array_equal(a, b)
+    # wide state range (lambda large -> u16 compact elements)
+    init = np.full((3000, 1), 400, dtype=np.uint64)
+    a = mm.MetropolisHastings(mm.PoissonTarget(400.0), mm.NonnegativeProposal(), init).seed(3).run(300, 10)
+    exp, _ = oracle.mh_poisson_run_philox(400.0, init[:, 0], 300, 10, seed=3)
+    np.testing.assert_array_equal(a, exp)
