@@ -3,6 +3,7 @@
 
 #include "mmc_dense.cuh"
 #include "mmc_hmc.cuh"
+#include "mmc_hmc_warp.cuh"
 #include "mmc_targets.cuh"
 
 using namespace mmc;
@@ -93,7 +94,20 @@ int dispatch(const mmc_hmc *h, const HmcParams &p, bool replay, cudaStream_t s) 
         break;
     default: break;
     }
-    set_error("HMC: target kind %d with dim %d is not compiled into the register-resident kernel", t.kind, t.dim);
+    // other dimensions: one chain per warp (D <= 512)
+    const int D = t.dim;
+    if (t.kind == MMC_T_ROSENBROCK_ND) {
+        if (D <= 32) return launch_hmc_warp<WRosenbrockND<A, 1>, A, 1>({D}, p, D, replay, s);
+        if (D <= 128) return launch_hmc_warp<WRosenbrockND<A, 4>, A, 4>({D}, p, D, replay, s);
+        if (D <= 256) return launch_hmc_warp<WRosenbrockND<A, 8>, A, 8>({D}, p, D, replay, s);
+        if (D <= 512) return launch_hmc_warp<WRosenbrockND<A, 16>, A, 16>({D}, p, D, replay, s);
+    } else if (t.kind == MMC_T_STD_NORMAL) {
+        if (D <= 32) return launch_hmc_warp<WStdNormal<A, 1>, A, 1>({D}, p, D, replay, s);
+        if (D <= 128) return launch_hmc_warp<WStdNormal<A, 4>, A, 4>({D}, p, D, replay, s);
+        if (D <= 512) return launch_hmc_warp<WStdNormal<A, 16>, A, 16>({D}, p, D, replay, s);
+    }
+    set_error("HMC: target kind %d with dim %d is not compiled in (register kernel: listed dims; warp kernel: dim <= 512)",
+              t.kind, t.dim);
     return MMC_ERR_UNSUPPORTED;
 }
 
@@ -301,7 +315,14 @@ int mmc_hmc_export_tape_dev(mmc_hmc *h, int64_t step_base, int64_t steps, float 
     case 8: return export_tape<8>(h, step_base, steps, momenta_dev, u_dev, s);
     case 10: return export_tape<10>(h, step_base, steps, momenta_dev, u_dev, s);
     case 16: return export_tape<16>(h, step_base, steps, momenta_dev, u_dev, s);
-    default: set_error("tape export not compiled for dim %d", h->dim); return MMC_ERR_UNSUPPORTED;
+    default: {
+        const int64_t total = steps * h->chains * ((h->dim + 3) / 4);
+        hmc_export_tape_any_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(seed_key(h->seed), h->chains, h->dim,
+                                                                                   h->chain_offset, step_base, steps,
+                                                                                   momenta_dev, u_dev);
+        MMC_CUDA(cudaGetLastError());
+        return MMC_OK;
+    }
     }
 }
 

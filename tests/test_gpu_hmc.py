@@ -127,3 +127,32 @@ def test_hmc_shapes_like_reference(mm):
         assert h.run(n_collect, 0).shape == (chains, n_collect, 2)
     h.step()
     assert h.positions.shape == (1, 2)
+
+
+@pytest.mark.parametrize("D", [7, 33, 100, 300])
+def test_hmc_warp_kernel_general_dim(mm, D):
+    """Dimensions outside the register-kernel list run one chain per warp (E = 1/4/8/16 elements per lane);
+    reductions are butterflies, so values agree to f32 rounding rather than bit-for-bit."""
+    rng = np.random.default_rng(D)
+    chains, L, steps = 65, 5, 3
+    init = (rng.normal(size=(chains, D)) * 0.3 + 0.7).astype(np.float32)
+    mom = rng.normal(size=(steps, chains, D)).astype(np.float32)
+    u = rng.random((steps, chains)).astype(np.float32)
+    eps = 0.002
+    exp, exp_pos, exp_tr = oracle.hmc_run_replay(oracle.rosenbrock_nd(D), init, eps, L, steps, 0, mom, u, want_trace=True)
+    for exact in (True, False):
+        h = mm.HMC(mm.RosenbrockND(), init, eps, L).set_exact(exact)
+        tr = np.zeros((steps, chains, 4), dtype=np.float32)
+        got = h.run(steps, 0, replay=dict(momenta=mom, u=u), trace=tr)
+        scale = np.abs(exp_tr[..., :2]).max()
+        assert np.abs(tr[..., :2] - exp_tr[..., :2]).max() <= 2e-5 * scale
+        same = (tr[..., 3] == exp_tr[..., 3]).all(axis=0)
+        assert same.mean() > 0.9
+        np.testing.assert_allclose(got[same], exp[same], rtol=1e-5, atol=1e-5)
+    # native tape round trip for a non-listed dimension
+    h = mm.HMC(mm.RosenbrockND(), init, eps, L).set_seed(11).set_exact(True)
+    m2, u2 = h.export_tape(0, 2)
+    got = h.run(2, 0)
+    exp2, _, _ = oracle.hmc_run_replay(oracle.rosenbrock_nd(D), init, eps, L, 2, 0, m2.cpu().numpy(), u2.cpu().numpy())
+    ok = np.isclose(got, exp2, rtol=1e-5, atol=1e-5).all(axis=(1, 2))
+    assert ok.mean() > 0.9
