@@ -175,6 +175,13 @@ int mmc_hmc_export_tape_dev(mmc_hmc *h, int64_t step_base, int64_t steps, float 
                             void *stream);
 void mmc_hmc_destroy(mmc_hmc *h);
 
+/* Custom device targets (see include/minimcmc_target.cuh): a user-compiled shared library registers a launcher for
+ * its functor; the returned id (>= MMC_T_CUSTOM_BASE) is used as mmc_target_desc.kind in mmc_hmc_create.
+ * Replaces the role of the BatchedGradientTarget trait bound of HMC (src/distributions.rs:65-76, src/hmc.rs:36-57). */
+typedef int (*mmc_hmc_launch_fn)(const void *hmc_params, int replay, int exact, const double *target_params, void *stream);
+int mmc_register_hmc_target(const char *name, int32_t dim, mmc_hmc_launch_fn fn);
+int mmc_lookup_target(const char *name); /* kind id, or MMC_ERR_INVALID when unknown */
+
 /* ------------------------------------------------------------------ NUTS
  * Replaces NUTS::new / set_seed / run / run_progress and NUTSChain (src/nuts.rs:123-170,347-353,410-691).
  * scalar_dtype = type T of epsilon / joint / logu / alpha (MMC_F64 in the reference's golden tests,

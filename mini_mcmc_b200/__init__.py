@@ -6,7 +6,7 @@ kernels inside libminimcmc.so; there is no CPU fallback.
 """
 from . import _lib
 from .core import init, init_det, init_device, init_with_seed
-from .distributions import (DenseGaussian, DiffableGaussian2D, Gaussian2D, IsotropicGaussian, NonnegativeProposal,
+from .distributions import (CustomTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, IsotropicGaussian, NonnegativeProposal,
                             PoissonTarget, Rosenbrock2D, RosenbrockND, StandardNormalTarget)
 from .hmc import HMC
 from .metropolis_hastings import MetropolisHastings
@@ -15,5 +15,5 @@ from .stats import BasicStats, RunStats, basic_stats, split_rhat_mean_ess
 
 __all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "NUTS", "Gaussian2D",
            "IsotropicGaussian", "PoissonTarget", "NonnegativeProposal", "RosenbrockND", "Rosenbrock2D",
-           "DiffableGaussian2D", "DenseGaussian", "StandardNormalTarget", "RunStats", "BasicStats", "basic_stats",
+           "DiffableGaussian2D", "DenseGaussian", "CustomTarget", "StandardNormalTarget", "RunStats", "BasicStats", "basic_stats",
            "split_rhat_mean_ess"]

@@ -58,7 +58,7 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(or `make -C mini_mcmc_b200/csrc`). mini_mcmc_b200 has no CPU fallback.")
 
-lib = C.CDLL(LIB_PATH)
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)  # custom-target libraries link against its symbols
 lib.mmc_last_error.restype = C.c_char_p
 lib.mmc_stats_partial_len.restype = C.c_int64
 

@@ -1,5 +1,8 @@
 // HMC C ABI (see include/minimcmc.h) — host side of K2 and the built-in target dispatch.
 #include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "mmc_dense.cuh"
 #include "mmc_hmc.cuh"
@@ -31,6 +34,17 @@ struct mmc_hmc {
 };
 
 namespace {
+
+struct CustomTarget {
+    std::string name;
+    int dim;
+    mmc_hmc_launch_fn fn;
+};
+std::mutex g_registry_mutex;
+std::vector<CustomTarget> &registry() {
+    static std::vector<CustomTarget> r;
+    return r;
+}
 
 int grow(float **ptr, size_t *cap, size_t need) {
     if (*cap >= need) return MMC_OK;
@@ -132,6 +146,13 @@ int mmc_hmc_create(mmc_hmc **out, const mmc_target_desc *target, const float *in
     MMC_REQUIRE(out && target && init_host && chains > 0 && dim > 0 && n_leapfrog >= 0,
                 "mmc_hmc_create: bad arguments");
     MMC_REQUIRE(target->dim == dim, "target dim %d != dim %d", target->dim, dim);
+    if (target->kind >= MMC_T_CUSTOM_BASE) {
+        std::lock_guard<std::mutex> lock(g_registry_mutex);
+        const size_t idx = (size_t)(target->kind - MMC_T_CUSTOM_BASE);
+        MMC_REQUIRE(idx < registry().size(), "custom target kind %d is not registered", target->kind);
+        MMC_REQUIRE(registry()[idx].dim == dim, "custom target '%s' has dim %d, got %d", registry()[idx].name.c_str(),
+                    registry()[idx].dim, dim);
+    }
     mmc_hmc *h = new mmc_hmc();
     h->target = *target;
     h->chains = chains;
@@ -158,6 +179,29 @@ int mmc_hmc_create(mmc_hmc **out, const mmc_target_desc *target, const float *in
     }
     *out = h;
     return MMC_OK;
+}
+
+int mmc_register_hmc_target(const char *name, int32_t dim, mmc_hmc_launch_fn fn) {
+    MMC_REQUIRE(name && fn && dim > 0, "mmc_register_hmc_target: bad arguments");
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    auto &r = registry();
+    for (size_t i = 0; i < r.size(); ++i)
+        if (r[i].name == name) {
+            r[i].dim = dim;
+            r[i].fn = fn;
+            return MMC_T_CUSTOM_BASE + (int)i;
+        }
+    r.push_back({name, dim, fn});
+    return MMC_T_CUSTOM_BASE + (int)r.size() - 1;
+}
+
+int mmc_lookup_target(const char *name) {
+    if (!name) return MMC_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    auto &r = registry();
+    for (size_t i = 0; i < r.size(); ++i)
+        if (r[i].name == name) return MMC_T_CUSTOM_BASE + (int)i;
+    return MMC_ERR_INVALID;
 }
 
 int mmc_hmc_set_seed(mmc_hmc *h, uint64_t seed) {
@@ -228,8 +272,20 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
     p.eps = (float)h->step_size;
     p.n_leapfrog = h->n_leapfrog;
     p.key = seed_key(h->seed);
-    int rc = h->exact ? dispatch<Exact>(h, p, replay, (cudaStream_t)stream)
+    int rc;
+    if (h->target.kind >= MMC_T_CUSTOM_BASE) {
+        mmc_hmc_launch_fn fn = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_registry_mutex);
+            const size_t idx = (size_t)(h->target.kind - MMC_T_CUSTOM_BASE);
+            if (idx < registry().size()) fn = registry()[idx].fn;
+        }
+        MMC_REQUIRE(fn, "custom target kind %d is not registered", h->target.kind);
+        rc = fn(&p, replay ? 1 : 0, h->exact, h->target.params, stream);
+    } else {
+        rc = h->exact ? dispatch<Exact>(h, p, replay, (cudaStream_t)stream)
                       : dispatch<Fast>(h, p, replay, (cudaStream_t)stream);
+    }
     if (rc) return rc;
     h->step += n_collect + n_discard;
     h->total_transitions += (n_collect + n_discard) * h->chains;

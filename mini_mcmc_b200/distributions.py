@@ -170,3 +170,22 @@ class DenseGaussian(_Target):
 
     def _mat(self):
         return self.precision
+
+
+class CustomTarget(_Target):
+    """A user-compiled device target registered through include/minimcmc_target.cuh (HMC only).
+
+    `library` is the path of the shared object built from the user's .cu file, `name` the identifier given to
+    MMC_REGISTER_HMC_TARGET; `params` fill mmc_target_desc.params (up to 8 doubles)."""
+
+    def __init__(self, library: str, name: str, dim: int, params=()):
+        import ctypes
+
+        self._user_lib = ctypes.CDLL(library, mode=ctypes.RTLD_GLOBAL)
+        kind = getattr(self._user_lib, f"{name}_register")()
+        if kind < 1000:
+            raise RuntimeError(f"registering custom target {name!r} failed with code {kind}")
+        self.kind, self.dim, self._p = int(kind), int(dim), tuple(float(v) for v in params)
+
+    def _params(self):
+        return self._p
