@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libminimcmc.so")
+LIB_PATH = os.environ.get("MMC_LIB_PATH", os.path.join(_HERE, "libminimcmc.so"))  # override: tuning builds only
 
 MMC_F32, MMC_F64, MMC_U64 = 0, 1, 2
 (T_GAUSSIAN2D, T_ISO_GAUSSIAN, T_POISSON, T_ROSENBROCK_ND, T_ROSENBROCK_2D, T_DIFF_GAUSSIAN2D, T_DENSE_GAUSSIAN,

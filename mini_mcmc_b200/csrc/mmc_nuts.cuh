@@ -24,6 +24,9 @@
 
 namespace mmc {
 
+#ifndef MMC_NUTS_MIN_BLOCKS
+#define MMC_NUTS_MIN_BLOCKS 5   // 96 registers: 20 warps / SM (measured best on B200: 4 -> 544 ms, 5 -> 497 ms, 6 -> 514 ms at C5)
+#endif
 constexpr int kNutsSmemLevels = 3;
 constexpr int kNutsWarps = 4;
 constexpr unsigned kFull = 0xffffffffu;
@@ -412,7 +415,7 @@ struct NutsWarp {
 };
 
 template <class Target, class A, class ST, int E, bool kReplay>
-__global__ void __launch_bounds__(kNutsWarps * 32) nuts_run_kernel(const Target tgt, const NutsParams p) {
+__global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run_kernel(const Target tgt, const NutsParams p) {
     extern __shared__ __align__(16) float nuts_smem[];
     constexpr int V = 32 * E;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
