@@ -6,11 +6,13 @@
 // lo = x - hi (exact), and three MMAs accumulate into the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped
 // lo.lo term is < 2^-20 relative).  The splits are produced by the previous epilogue, so they cost no extra pass.
 //
-// Tile: BLOCK_M 128 chains x BLOCK_N 256 columns x BLOCK_K 32 (one 128-byte swizzle row of fp32), UMMA
-// 128 x 256 x 8 (kind::tf32, cta_group::1).  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
-// allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (each owns the 32 TMEM lanes of its quarter).
-// Pipeline: full/empty mbarriers per shared-memory stage (TMA -> MMA -> tcgen05.commit), one tmem_full barrier
-// (MMA -> epilogue).
+// Tile: BLOCK_M 128 chains x BLOCK_N 256 columns x BLOCK_K 16/32 (one swizzle row of fp32), UMMA 128 x 256 x 8
+// (kind::tf32, cta_group::1).  Persistent CTAs (one per SM) walk the tile list; warp roles (320 threads):
+// warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-9 = epilogue (two
+// warps per 32-lane TMEM quarter, one per 128-column half).  Pipelines: full/empty mbarriers per shared-memory
+// stage (TMA -> MMA -> tcgen05.commit) and tmem_full/tmem_empty per accumulator (MMA <-> epilogue); the
+// accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of one tile overlaps the main loop
+// of the next.
 #include <cuda.h>
 
 #include <vector>
@@ -22,13 +24,21 @@ namespace mmc {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, kStages = 2, UMMA_K = 8;
+#ifndef MMC_TC_BK
+#define MMC_TC_BK 16
+#endif
+// BLOCK_K 32 = one 128-byte swizzle row per operand row (2 stages fit), BLOCK_K 16 = 64-byte swizzle rows (4 stages):
+// the pipeline is bound by bytes in flight per SM, so more, smaller stages win (measured).
+constexpr int BM = 128, BN = 256, BK = MMC_TC_BK, kStages = (BK == 32 ? 2 : 4), UMMA_K = 8;
+constexpr uint32_t kRowBytes = BK * 4;                     // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+static_assert(BK == 32 || BK == 16, "BLOCK_K must be 32 or 16");
 constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB (one of hi / lo)
 constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // 96 KB
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;
-constexpr uint32_t kTmemCols = 256;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, one per 128-column half of the tile
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kTmemCols = 512;          // two 256-column fp32 accumulators
 
 struct Maps {
     CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
@@ -88,14 +98,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
+// shared-memory matrix descriptor: K-major tile, rows of kRowBytes with the matching swizzle, 8-row groups
+// 8 * kRowBytes apart
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset = 8 rows x 128 B, bits [32,46)
+    d |= (uint64_t)((8u * kRowBytes) >> 4) << 32;    // stride byte offset = 8 rows, bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell)
-    d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;         // layout type SWIZZLE_128B (2) / SWIZZLE_64B (4)
     return d;
 }
 // instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = 256
@@ -105,24 +116,25 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+// Persistent kernel: CTA b processes tiles b, b + grid, ...; the fp32 accumulator is double buffered in TMEM
+// (2 x 256 columns) so the epilogue of tile i overlaps the TMA/MMA main loop of tile i + 1.
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      const float *__restrict__ a_hi, const float *__restrict__ a_lo, float *__restrict__ n_hi,
                      float *__restrict__ n_lo, float *__restrict__ mom, float *__restrict__ scal, int64_t M, int D, float eps,
-                     int mode) {
+                     int mode, int n_tiles, int n_nblocks) {
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzled tiles need 1024 B alignment
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int64_t m0 = (int64_t)blockIdx.y * BM;
     const int nk = D / BK;
 
     if (warp == 0 && lane == 0) {
@@ -130,7 +142,10 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
@@ -150,95 +165,131 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t st = smem_base + s * kStageBytes;
-                mbar_expect_tx(full_bar(s), kStageBytes);
-                tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, (int)m0);
-                tma_load_2d(st + kABytes, &map_a_lo, full_bar(s), kb * BK, (int)m0);
-                tma_load_2d(st + 2 * kABytes, &map_b_hi, full_bar(s), kb * BK, n0);
-                tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, full_bar(s), kb * BK, n0);
+            uint32_t it = 0;  // running k-block counter across tiles (stage = it % kStages)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n0 = (tile % n_nblocks) * BN;
+                const int m0 = (tile / n_nblocks) * BM;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t st = smem_base + s * kStageBytes;
+                    mbar_expect_tx(full_bar(s), kStageBytes);
+                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + kABytes, &map_a_lo, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + 2 * kABytes, &map_b_hi, full_bar(s), kb * BK, n0);
+                    tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, full_bar(s), kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc();
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, lt = 0;  // lt = local tile counter (accumulator stage = lt & 1)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(as), aph ^ 1u);   // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t st = smem_base + s * kStageBytes;
-                const uint64_t da_hi = make_smem_desc(st), da_lo = make_smem_desc(st + kABytes);
-                const uint64_t db_hi = make_smem_desc(st + 2 * kABytes), db_lo = make_smem_desc(st + 2 * kABytes + kBBytes);
+                const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_base + s * kStageBytes;
+                    const uint64_t da_hi = make_smem_desc(st), da_lo = make_smem_desc(st + kABytes);
+                    const uint64_t db_hi = make_smem_desc(st + 2 * kABytes), db_lo = make_smem_desc(st + 2 * kABytes + kBBytes);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the swizzle row
-                    tcgen05_mma_tf32(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tcgen05_mma_tf32(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
-                    tcgen05_mma_tf32(tmem_base, da_lo + koff, db_hi + koff, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the swizzle row
+                        tcgen05_mma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tcgen05_mma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                        tcgen05_mma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                    }
+                    tcgen05_commit(empty_bar(s));   // frees the stage once the MMAs above have read it
                 }
-                tcgen05_commit(empty_bar(s));   // frees the stage once the MMAs above have read it
+                tcgen05_commit(tmem_full_bar(as));  // accumulator complete
             }
-            tcgen05_commit(tmem_full_bar);      // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> fused leapfrog -> global =====
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        // ===== epilogue (8 warps): TMEM -> registers -> fused leapfrog -> global =====
+        const int ew = warp - 2;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
+        const int half = ew >> 2;               // which 128-column half of the tile this warp handles
         const int row = q * 32 + lane;
-        const int64_t m = m0 + row;
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
         const float eps_half = eps * 0.5f;
-        float quad = 0.f, ke = 0.f;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int n0 = (tile % n_nblocks) * BN;
+            const int64_t m = (int64_t)(tile / n_nblocks) * BM + row;
+            const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+            const bool row_ok = m < M;
+            float quad = 0.f, ke = 0.f;
+            bool waited = false;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
-            if (m < M) {
-                const int64_t off = m * D + n0 + chunk * 32;
+            for (int chunk = 0; chunk < BN / 64; ++chunk) {
+                const int col = half * (BN / 2) + chunk * 32;
+                const int64_t off = (row_ok ? m : 0) * D + n0 + col;
+                // issue the global loads of this chunk before waiting on the accumulator
+                float4 h4[8], l4[8], p4[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 h4 = *reinterpret_cast<const float4 *>(a_hi + off + j);
-                    const float4 l4 = *reinterpret_cast<const float4 *>(a_lo + off + j);
-                    float4 p4 = *reinterpret_cast<const float4 *>(mom + off + j);
-                    float dl[4] = {h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w};
-                    float pp[4] = {p4.x, p4.y, p4.z, p4.w};
-                    float dn[4];
+                for (int j = 0; j < 8; ++j) {
+                    h4[j] = __ldcg(reinterpret_cast<const float4 *>(a_hi + off) + j);
+                    l4[j] = __ldcg(reinterpret_cast<const float4 *>(a_lo + off) + j);
+                    p4[j] = __ldcg(reinterpret_cast<const float4 *>(mom + off) + j);
+                }
+                if (!waited) {
+                    mbar_wait(tmem_full_bar(as), aph);
+                    tcgen05_fence_after();
+                    waited = true;
+                }
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)col, r);
+                if (chunk == BN / 64 - 1) {
+                    // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(as)) : "memory");
+                }
+                if (row_ok) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float z = __uint_as_float(r[j + e]);
-                        const float gh = -z * eps_half;
-                        if (mode != kModeMid) quad = fmaf(z, dl[e], quad);
-                        if (mode == kModeFirst) {
-                            pp[e] = pp[e] + gh;
-                            dn[e] = fmaf(eps, pp[e], dl[e]);
-                        } else if (mode == kModeMid) {
-                            pp[e] = (pp[e] + gh) + gh;
-                            dn[e] = fmaf(eps, pp[e], dl[e]);
-                        } else {
-                            pp[e] = pp[e] + gh;
-                            ke = fmaf(pp[e], pp[e], ke);
-                            dn[e] = dl[e];
+                    for (int j = 0; j < 8; ++j) {
+                        float dl[4] = {h4[j].x + l4[j].x, h4[j].y + l4[j].y, h4[j].z + l4[j].z, h4[j].w + l4[j].w};
+                        float pp[4] = {p4[j].x, p4[j].y, p4[j].z, p4[j].w};
+                        float dn[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float z = __uint_as_float(r[4 * j + e]);
+                            const float gh = -z * eps_half;
+                            if (mode != kModeMid) quad = fmaf(z, dl[e], quad);
+                            if (mode == kModeFirst) {
+                                pp[e] = pp[e] + gh;
+                                dn[e] = fmaf(eps, pp[e], dl[e]);
+                            } else if (mode == kModeMid) {
+                                pp[e] = (pp[e] + gh) + gh;
+                                dn[e] = fmaf(eps, pp[e], dl[e]);
+                            } else {
+                                pp[e] = pp[e] + gh;
+                                ke = fmaf(pp[e], pp[e], ke);
+                                dn[e] = dl[e];
+                            }
                         }
-                    }
-                    *reinterpret_cast<float4 *>(mom + off + j) = make_float4(pp[0], pp[1], pp[2], pp[3]);
-                    if (mode != kModeLast) {
-                        float hi[4], lo[4];
+                        __stcg(reinterpret_cast<float4 *>(mom + off) + j, make_float4(pp[0], pp[1], pp[2], pp[3]));
+                        if (mode != kModeLast) {
+                            float hi[4], lo[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dn[e]); lo[e] = dn[e] - hi[e]; }
-                        *reinterpret_cast<float4 *>(n_hi + off + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4 *>(n_lo + off + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dn[e]); lo[e] = dn[e] - hi[e]; }
+                            __stcg(reinterpret_cast<float4 *>(n_hi + off) + j, make_float4(hi[0], hi[1], hi[2], hi[3]));
+                            __stcg(reinterpret_cast<float4 *>(n_lo + off) + j, make_float4(lo[0], lo[1], lo[2], lo[3]));
+                        }
                     }
                 }
             }
-        }
-        if (m < M && mode != kModeMid) {
-            atomicAdd(scal + (mode == kModeFirst ? 1 : 3) * M + m, quad);
-            if (mode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
+            if (row_ok && mode != kModeMid) {
+                atomicAdd(scal + (mode == kModeFirst ? 1 : 3) * M + m, quad);
+                if (mode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
+            }
         }
     }
     tcgen05_fence_before();
@@ -268,7 +319,7 @@ int encode_2d(EncodeTiledFn fn, CUtensorMap *map, float *base, uint64_t rows, ui
     const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return MMC_ERR_CUDA;
@@ -323,10 +374,12 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
     const size_t md = (size_t)M * D;
     float *a_hi = st->d_delta_split[cur], *a_lo = a_hi + md;
     float *n_hi = st->d_delta_split[cur ^ 1], *n_lo = n_hi + md;
-    const dim3 grid((unsigned)(D / tc::BN), (unsigned)((M + tc::BM - 1) / tc::BM));
+    const int n_nblocks = D / tc::BN;
+    const int n_tiles = n_nblocks * (int)((M + tc::BM - 1) / tc::BM);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     tc::dense_gemm_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(maps->a_hi[cur], maps->a_lo[cur], maps->b_hi,
                                                                              maps->b_lo, a_hi, a_lo, n_hi, n_lo, st->d_mom,
-                                                                             st->d_scal, M, D, eps, mode);
+                                                                             st->d_scal, M, D, eps, mode, n_tiles, n_nblocks);
     MMC_CUDA(cudaGetLastError());
     return MMC_OK;
 }
