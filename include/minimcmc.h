@@ -24,10 +24,12 @@
  *   counter = (global_chain_lo, global_chain_hi, step_word, sub).  `global_chain` = local chain index +
  *   the handle's chain offset, `step` counts transitions since the handle was seeded, so results do not
  *   depend on how chains are sharded over GPUs.
- *     Poisson MH : step_word = step >> 2; W = call(sub 0), V = call(sub 1), i = step & 3:
- *                  flip = W[i] >> 31;  u = ((W[i] & 0x7fffffff) << 22 | V[i] >> 10) * 2^-53.
- *                  (V only matters when the top 31 bits tie with the accept threshold, so the kernel evaluates
- *                  it lazily: one Philox call per four transitions, still the exact 53-bit test.)
+ *     Poisson MH : step_word = step >> 3; W = call(sub 0); i = step & 7; h = 16-bit field i of W
+ *                  (h = (W[i >> 1] >> 16 (i & 1)) & 0xffff): flip = h >> 15, u15 = h & 0x7fff;
+ *                  V = call(sub 1 + (i >> 1)): low38 = ((i & 1) ? V[3]:V[2] : V[1]:V[0]) >> 26;
+ *                  u = (u15 << 38 | low38) * 2^-53.  (V only matters when the top 15 bits tie with the accept
+ *                  threshold, so the kernel evaluates it lazily: one Philox call per eight transitions, still the
+ *                  exact 53-bit test.)
  *     MH (f64)   : step_word = step; sub 0 words (0,1) -> accept uniform (53 bit); sub 1 + j ->
  *                  Box-Muller pair of proposal normals (2j, 2j+1), words (0,1) -> u1, (2,3) -> u2.
  *     HMC (f32)  : step_word = step; sub j -> momenta 4j..4j+3 (Box-Muller on words (0,1), (2,3));

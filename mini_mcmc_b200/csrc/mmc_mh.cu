@@ -24,7 +24,7 @@ struct mmc_mh {
     // Poisson tables
     int32_t table_len = 0;
     double *d_lnfact = nullptr;
-    uint2 *d_lim = nullptr;  // [table_len][2]: accept iff bits <= lim[k][up]
+    uint4 *d_lim = nullptr;  // [table_len][2]: (thr >> 38, thr_lo low 32, thr_lo high 6, 0)
     int32_t *d_error = nullptr;
     double ln_lambda = 0, ln_half = 0;
     // host-API staging
@@ -95,9 +95,12 @@ int build_poisson_tables(mmc_mh *h) {
         lnfact[k] = k < 2 ? 0.0 : acc;
         lp[k] = -lambda + (double)k * h->ln_lambda - lnfact[k];
     }
-    // table entry [k][dir] = (thr >> 22, thr & (2^22 - 1)):  u53 < thr  <=>  u31 < thr_hi || (u31 == thr_hi && u22 < thr_lo)
-    std::vector<uint2> lim(2 * len, make_uint2(0u, 0u));
-    auto encode = [](uint64_t thr) { return make_uint2((uint32_t)(thr >> 22), (uint32_t)(thr & 0x3fffffu)); };
+    // table entry [k][dir] = (thr >> 38, thr & (2^38 - 1)):  u53 < thr  <=>  u15 < thr_hi || (u15 == thr_hi && u38 < thr_lo)
+    std::vector<uint4> lim(2 * len, make_uint4(0u, 0u, 0u, 0u));
+    auto encode = [](uint64_t thr) {
+        const uint64_t lo = thr & ((1ULL << 38) - 1);
+        return make_uint4((uint32_t)(thr >> 38), (uint32_t)lo, (uint32_t)(lo >> 32), 0u);
+    };
     for (int64_t k = 0; k + 1 < len; ++k) {
         // x = k -> y = k + 1 : q_f = (k == 0 ? 0 : ln 1/2), q_b = ln 1/2
         const double qf = k == 0 ? 0.0 : h->ln_half, qb = h->ln_half;
@@ -109,10 +112,10 @@ int build_poisson_tables(mmc_mh *h) {
         }
     }
     MMC_CUDA(cudaMalloc(&h->d_lnfact, len * sizeof(double)));
-    MMC_CUDA(cudaMalloc(&h->d_lim, 2 * len * sizeof(uint2)));
+    MMC_CUDA(cudaMalloc(&h->d_lim, 2 * len * sizeof(uint4)));
     MMC_CUDA(cudaMalloc(&h->d_error, sizeof(int32_t)));
     MMC_CUDA(cudaMemcpy(h->d_lnfact, lnfact.data(), len * sizeof(double), cudaMemcpyHostToDevice));
-    MMC_CUDA(cudaMemcpy(h->d_lim, lim.data(), 2 * len * sizeof(uint2), cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaMemcpy(h->d_lim, lim.data(), 2 * len * sizeof(uint4), cudaMemcpyHostToDevice));
     MMC_CUDA(cudaMemset(h->d_error, 0, sizeof(int32_t)));
     return MMC_OK;
 }
@@ -199,7 +202,7 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, 
     const int64_t warps = (chain_count + 31) / 32;
     const unsigned grid = (unsigned)((warps + kPoisWarps - 1) / kPoisWarps);
     auto launch = [&](auto kernel, size_t tile_bytes) -> int {
-        const size_t smem = (size_t)h->table_len * 16 + (size_t)kPoisWarps * tile_bytes;
+        const size_t smem = (size_t)h->table_len * 8 + (size_t)kPoisWarps * tile_bytes;
         MMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, block, smem, stream>>>(p);
         MMC_CUDA(cudaGetLastError());

@@ -160,13 +160,15 @@ __global__ void mh_cont_export_tape_kernel(uint2 key, int64_t chains, int64_t ch
 // 32 chains in shared memory and emits them as contiguous row segments (full 32 B sectors) instead of 32
 // strided 8 B stores per step.
 //
-// RNG contract (minimcmc.h): global step s of a chain uses word i = s & 3 of two Philox calls,
-//   W = philox(key, (chain, s >> 2, sub 0)),  V = philox(key, (chain, s >> 2, sub 1)):
-//   flip = W[i] >> 31;  u53 = (W[i] & 0x7fffffff) << 22 | V[i] >> 10;  u = u53 * 2^-53.
-// The accept test u53 < thr is decided by the top 31 bits except on a tie (probability 2^-31), so V is
-// evaluated lazily: one Philox call feeds FOUR transitions and the result is still the exact 53-bit test.
+// RNG contract (minimcmc.h): global step s of a chain uses 16-bit field i = s & 7 of W = philox(key, (chain, s >> 3,
+// sub 0)), i.e. h = (W[i >> 1] >> 16 (i & 1)) & 0xffff:   flip = h >> 15,  u15 = h & 0x7fff  (top 15 bits of u).
+// The low 38 bits of the 53-bit uniform come from V = philox(key, (chain, s >> 3, sub 1 + (i >> 1))):
+//   low38 = ((i & 1) ? V.w:V.z : V.y:V.x) >> 26,   u53 = u15 << 38 | low38,   u = u53 * 2^-53.
+// The accept test u53 < thr is decided by the top 15 bits except on a tie (probability 2^-15 per step), so V is
+// evaluated lazily: ONE Philox call feeds EIGHT transitions and the result is still the exact 53-bit test
+// (an octet in which any lane-step tied is replayed through the exact path).
 //   threshold mode: thr[x][dir] is the host-built count of 53-bit uniforms satisfying
-//     (lp'+q_b)-(lp+q_f) > ln(u) (mmc_mh.cu), split as thr_hi = thr >> 22, thr_lo = thr & (2^22 - 1).
+//     (lp'+q_b)-(lp+q_f) > ln(u) (mmc_mh.cu), split as thr_hi = thr >> 38, thr_lo = thr & (2^38 - 1).
 //   log mode: evaluates that predicate in f64 on the device (needs V every step).
 struct MhPoissonParams {
     uint64_t *state;        // [chains] in/out
@@ -174,7 +176,7 @@ struct MhPoissonParams {
     const uint8_t *flip;    // replay [chains, steps]
     const double *u;        // replay [chains, steps]
     const double *lnfact;   // [table_len]  sum_{i<=k} ln i, built by the host libm in the reference's order
-    const uint2 *lim;       // [table_len][2] (thr_hi, thr_lo) of [k][0] = down, [k][1] = up
+    const uint4 *lim;       // [table_len][2] (thr >> 38, low 32 of thr_lo, high 6 of thr_lo, 0) of [k][0] = down, [k][1] = up
     int32_t table_len;
     double lambda, ln_lambda, ln_half;
     int64_t chains, chain_offset, step_base, n_collect, n_discard;
@@ -207,6 +209,13 @@ __device__ __forceinline__ uint4 philox_rk(const uint32_t (&rk)[20], uint32_t c0
 __device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t i) {
     return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
 }
+// 16-bit field i (0..7) of a Philox result
+__device__ __forceinline__ uint32_t pick16(const uint4 &w, uint32_t i) { return (pick(w, i >> 1) >> (16u * (i & 1u))) & 0xffffu; }
+// low 38 bits of the uniform of field i from the lazily evaluated call V (sub 1 + (i >> 1))
+__device__ __forceinline__ uint64_t low38_of(const uint4 &v, uint32_t i) {
+    const uint64_t bits = (i & 1u) ? (((uint64_t)v.w << 32) | v.z) : (((uint64_t)v.y << 32) | v.x);
+    return bits >> 26;
+}
 
 template <bool kReplay, bool kThreshold, int T = 64, class Elem = uint16_t, class OutT = uint64_t>
 __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __grid_constant__ MhPoissonParams p) {
@@ -215,16 +224,11 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     constexpr int kPoisPitch = PoisTile<T, Elem>::kPitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [table_len][2] uint2 (threshold) or [table_len] f64 (log mode), then the warp tiles
-    uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw);  // [2 table_len] thr >> 22   (one word per entry:
-    uint32_t *s_lo = s_hi + 2 * p.table_len;                  // [2 table_len] thr & 2^22-1  bank-conflict free)
-    double *s_lnf = reinterpret_cast<double *>(smem_raw);
-    Elem *tiles = reinterpret_cast<Elem *>(smem_raw + (size_t)p.table_len * 16);
+    uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw);  // [2 table_len] thr >> 38: one word per entry, conflict free
+    double *s_lnf = reinterpret_cast<double *>(smem_raw);     // (the low 38 bits stay in global memory: tie path only)
+    Elem *tiles = reinterpret_cast<Elem *>(smem_raw + (size_t)p.table_len * 8);
     if (kThreshold) {
-        for (int i = threadIdx.x; i < 2 * p.table_len; i += blockDim.x) {
-            const uint2 t = p.lim[i];
-            s_hi[i] = t.x;
-            s_lo[i] = t.y;
-        }
+        for (int i = threadIdx.x; i < 2 * p.table_len; i += blockDim.x) s_hi[i] = p.lim[i].x;
     } else {
         for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) s_lnf[i] = p.lnfact[i];
     }
@@ -248,19 +252,22 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
         x = x0 >= kmax ? kmax : (uint32_t)x0;
     }
 
-    // One transition from the first-level word w; `low22()` yields the lazily evaluated low bits of u53.
-    auto transition = [&](uint32_t w, auto low22) {
+    // One transition from the 16-bit field h; `low38()` yields the lazily evaluated low bits of u53.
+    auto transition = [&](uint32_t h, auto low38) {
         // NonnegativeProposal::sample, examples/poisson_mh.rs:34-47: 0 -> 1, else +-1 by the flip
-        const uint32_t up = (w >> 31) | (uint32_t)(x == 0);
+        const uint32_t up = (h >> 15) | (uint32_t)(x == 0);
         const uint32_t y = min(x + 2u * up - 1u, kmax);
-        const uint32_t u31 = w & 0x7fffffffu;
+        const uint32_t u15 = h & 0x7fffu;
         bool acc;
         if (kThreshold) {
             const uint32_t hi = s_hi[2u * x + up];
-            acc = u31 < hi;
-            if (u31 == hi) acc = low22() < s_lo[2u * x + up];  // tie in the top 31 bits: probability 2^-31
+            acc = u15 < hi;
+            if (u15 == hi) {  // tie in the top 15 bits: decide on the remaining 38
+                const uint4 t = __ldg(p.lim + 2u * x + up);
+                acc = low38() < (((uint64_t)t.z << 32) | t.y);
+            }
         } else {
-            const uint64_t u53 = ((uint64_t)u31 << 22) | low22();
+            const uint64_t u53 = ((uint64_t)u15 << 38) | low38();
             const double u = (double)u53 * (1.0 / 9007199254740992.0);
             // PoissonTarget::unnorm_logp, examples/poisson_mh.rs:19-25: -lambda + k ln(lambda) - ln k!
             const double cur_lp = (-p.lambda + (double)x * p.ln_lambda) - s_lnf[x];
@@ -274,21 +281,21 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
         x = acc ? y : x;
         xmax = max(xmax, x);
     };
-    // Branch-free fast transition (threshold mode): decides on the top 31 bits and records whether a tie
-    // occurred; the caller replays the whole quad through `transition` in that (2^-29 per quad) case.
-    auto fast = [&](uint32_t w, bool &tie) {
-        const uint32_t up = (w >> 31) | (uint32_t)(x == 0);
+    // Branch-free fast transition (threshold mode): decides on the top 15 bits and records whether a tie
+    // occurred; the caller replays the whole octet through `transition` in that case.
+    auto fast = [&](uint32_t h, bool &tie) {
+        const uint32_t up = (h >> 15) | (uint32_t)(x == 0);
         const uint32_t y = min(x + 2u * up - 1u, kmax);
-        const uint32_t u31 = w & 0x7fffffffu;
+        const uint32_t u15 = h & 0x7fffu;
         const uint32_t hi = s_hi[2u * x + up];
-        tie = tie || (u31 == hi);
-        x = (u31 < hi) ? y : x;
+        tie = tie || (u15 == hi);
+        x = (u15 < hi) ? y : x;
     };
 
-    // ---- staging tile: column j holds global step G + j with G a multiple of 4, so the four steps of one
-    // Philox call land in one aligned shared-memory store
+    // ---- staging tile: column j holds global step G + j with G a multiple of 8, so the eight steps of one
+    // Philox call land in aligned shared-memory stores
     const uint64_t g_first = (uint64_t)(p.step_base + p.n_discard);  // global index of the first collected step
-    int col_lo = (int)(g_first & 3);   // first valid column of the current tile (non-zero only for an unaligned start)
+    int col_lo = (int)(g_first & 7);   // first valid column of the current tile (non-zero only for an unaligned start)
     int tpos = col_lo;                 // next column to fill
     int64_t t_base = -(int64_t)col_lo; // collected index of column 0
     // vector stores need aligned row segments for every chain of the warp
@@ -367,8 +374,8 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
             for (; s < s1; ++s) {
                 const double u = p.u[cc * steps + s];
                 const uint64_t u53 = (uint64_t)(u * 9007199254740992.0);
-                const uint32_t w = ((uint32_t)(p.flip[cc * steps + s] & 1) << 31) | (uint32_t)(u53 >> 22);
-                transition(w, [&]() { return (uint32_t)(u53 & 0x3fffffu); });
+                const uint32_t h = ((uint32_t)(p.flip[cc * steps + s] & 1) << 15) | (uint32_t)(u53 >> 38);
+                transition(h, [&]() { return u53 & 0x3fffffffffULL; });
                 if (kEmit) emit1();
             }
             return;
@@ -376,49 +383,55 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
         const uint64_t g0 = (uint64_t)p.step_base;
         auto single = [&]() {  // unaligned head / tail steps
             const uint64_t gs = g0 + s;
-            const uint32_t quad = (uint32_t)(gs >> 2), i = (uint32_t)(gs & 3);
-            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, quad, 0u);
-            transition(pick(W, i), [&]() { return pick(philox_rk(p.rk, gc_lo, gc_hi, quad, 1u), i) >> 10; });
+            const uint32_t oct = (uint32_t)(gs >> 3), i = (uint32_t)(gs & 7);
+            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, oct, 0u);
+            transition(pick16(W, i), [&]() { return low38_of(philox_rk(p.rk, gc_lo, gc_hi, oct, 1u + (i >> 1)), i); });
             if (kEmit) emit1();
             ++s;
         };
-        while (s < s1 && ((g0 + s) & 3)) single();
-        uint32_t quad = (uint32_t)((g0 + s) >> 2);
-        for (; s + 3 < s1; s += 4, ++quad) {
-            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, quad, 0u);
-            uint32_t xa, xb, xc;
+        while (s < s1 && ((g0 + s) & 7)) single();
+        uint32_t oct = (uint32_t)((g0 + s) >> 3);
+        for (; s + 7 < s1; s += 8, ++oct) {
+            const uint4 W = philox_rk(p.rk, gc_lo, gc_hi, oct, 0u);
+            uint32_t xs[8];
+            auto exact_octet = [&]() {
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i) {
+                    transition(pick16(W, i), [&]() { return low38_of(philox_rk(p.rk, gc_lo, gc_hi, oct, 1u + (i >> 1)), i); });
+                    xs[i] = x;
+                }
+            };
             if (kThreshold) {
                 const uint32_t x_in = x;
                 bool tie = false;
-                fast(W.x, tie); xa = x;
-                fast(W.y, tie); xb = x;
-                fast(W.z, tie); xc = x;
-                fast(W.w, tie);
-                if (tie) {  // exact 53-bit replay of this quad
+                fast(W.x & 0xffffu, tie); xs[0] = x;
+                fast(W.x >> 16, tie); xs[1] = x;
+                fast(W.y & 0xffffu, tie); xs[2] = x;
+                fast(W.y >> 16, tie); xs[3] = x;
+                fast(W.z & 0xffffu, tie); xs[4] = x;
+                fast(W.z >> 16, tie); xs[5] = x;
+                fast(W.w & 0xffffu, tie); xs[6] = x;
+                fast(W.w >> 16, tie); xs[7] = x;
+                if (tie) {  // exact 53-bit replay of this octet (2^-12 per lane-octet)
                     x = x_in;
-                    const uint4 V = philox_rk(p.rk, gc_lo, gc_hi, quad, 1u);
-                    transition(W.x, [&]() { return V.x >> 10; }); xa = x;
-                    transition(W.y, [&]() { return V.y >> 10; }); xb = x;
-                    transition(W.z, [&]() { return V.z >> 10; }); xc = x;
-                    transition(W.w, [&]() { return V.w >> 10; });
+                    exact_octet();
                 }
-                xmax = max(xmax, x + 3);  // x moves by at most 1 per step: bounds the excursion inside the quad
+                xmax = max(xmax, x + 7);  // x moves by at most 1 per step: bounds the excursion inside the octet
             } else {
-                const uint4 V = philox_rk(p.rk, gc_lo, gc_hi, quad, 1u);
-                transition(W.x, [&]() { return V.x >> 10; }); xa = x;
-                transition(W.y, [&]() { return V.y >> 10; }); xb = x;
-                transition(W.z, [&]() { return V.z >> 10; }); xc = x;
-                transition(W.w, [&]() { return V.w >> 10; });
+                exact_octet();
             }
-            if (kEmit) {  // tpos is a multiple of 4 here: aligned packed store(s) for the four steps
+            if (kEmit) {  // tpos is a multiple of 8 here: aligned packed stores for the eight steps
+                uint32_t *dst = reinterpret_cast<uint32_t *>(my_row + tpos);  // 4-byte aligned (row pitch is a whole number of words)
                 if (sizeof(Elem) == 1) {
-                    *reinterpret_cast<uint32_t *>(my_row + tpos) = xa | (xb << 8) | (xc << 16) | (x << 24);
+                    dst[0] = xs[0] | (xs[1] << 8) | (xs[2] << 16) | (xs[3] << 24);
+                    dst[1] = xs[4] | (xs[5] << 8) | (xs[6] << 16) | (xs[7] << 24);
                 } else {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(my_row + tpos);  // 4-byte aligned (pitch is odd in words)
-                    dst[0] = xa | (xb << 16);
-                    dst[1] = xc | (x << 16);
+                    dst[0] = xs[0] | (xs[1] << 16);
+                    dst[1] = xs[2] | (xs[3] << 16);
+                    dst[2] = xs[4] | (xs[5] << 16);
+                    dst[3] = xs[6] | (xs[7] << 16);
                 }
-                tpos += 4;
+                tpos += 8;
                 if (tpos == kPoisTile) flush();
             }
         }
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     run_steps(p.n_discard, steps, std::true_type{});
     if (tpos > col_lo) flush();
     if (active) p.state[c] = x;
-    if (xmax >= kmax) *p.error_flag = 1;  // (conservative by 3 inside aligned quads)
+    if (xmax >= kmax) *p.error_flag = 1;  // (conservative by 7 inside aligned octets)
 }
 
 }  // namespace mmc

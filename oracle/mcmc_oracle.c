@@ -219,9 +219,10 @@ ORC_API int orc_mh_poisson_run_replay(double lambda, uint64_t *state, int64_t ch
 }
 
 /* Twin of the CUDA path's native Philox keying (include/minimcmc.h "RNG contract"):
- * key = seed; global step s uses word i = s & 3 of W = philox(ctr = (chain_lo, chain_hi, s >> 2, 0)) and
- * V = philox(ctr = (.., s >> 2, 1)):  flip = W[i] >> 31;  u53 = (W[i] & 0x7fffffff) << 22 | V[i] >> 10;
- * u = u53 * 2^-53. */
+ * key = seed; global step s uses 16-bit field i = s & 7 of W = philox(ctr = (chain_lo, chain_hi, s >> 3, 0)):
+ * h = (W[i >> 1] >> 16 (i & 1)) & 0xffff, flip = h >> 15, u15 = h & 0x7fff; the low 38 bits come from
+ * V = philox(ctr = (.., s >> 3, 1 + (i >> 1))): low38 = ((i & 1) ? V[3]:V[2] : V[1]:V[0]) >> 26;
+ * u = (u15 << 38 | low38) * 2^-53. */
 ORC_API int orc_mh_poisson_run_philox(double lambda, uint64_t *state, int64_t chains, int64_t chain_offset,
                                       int64_t step_base, int64_t n_collect, int64_t n_discard, uint64_t seed,
                                       uint64_t *out) {
@@ -231,19 +232,21 @@ ORC_API int orc_mh_poisson_run_philox(double lambda, uint64_t *state, int64_t ch
     for (int64_t c = 0; c < chains; ++c) {
         uint64_t x = state[c];
         const uint64_t gc = (uint64_t)(c + chain_offset);
-        for (int64_t i = 0; i < steps; ++i) {
-            const uint64_t gs = (uint64_t)(step_base + i);
-            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 2), 0u};
+        for (int64_t s = 0; s < steps; ++s) {
+            const uint64_t gs = (uint64_t)(step_base + s);
+            const uint32_t i = (uint32_t)(gs & 7);
+            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 3), 0u};
             uint32_t w[4], v[4];
             orc_philox4x32_10(key, ctr, w);
-            ctr[3] = 1u;
+            ctr[3] = 1u + (i >> 1);
             orc_philox4x32_10(key, ctr, v);
-            const int h = (int)(gs & 3);
-            int flip = (int)(w[h] >> 31);
-            uint64_t u53 = ((uint64_t)(w[h] & 0x7fffffffu) << 22) | (uint64_t)(v[h] >> 10);
-            double u = (double)u53 * (1.0 / 9007199254740992.0);
+            const uint32_t h = (w[i >> 1] >> (16u * (i & 1u))) & 0xffffu;
+            const int flip = (int)(h >> 15);
+            const uint64_t bits = (i & 1u) ? (((uint64_t)v[3] << 32) | v[2]) : (((uint64_t)v[1] << 32) | v[0]);
+            const uint64_t u53 = ((uint64_t)(h & 0x7fffu) << 38) | (bits >> 26);
+            const double u = (double)u53 * (1.0 / 9007199254740992.0);
             x = orc_mh_poisson_step(lambda, x, flip, u);
-            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
+            if (s >= n_discard) out[c * n_collect + (s - n_discard)] = x;
         }
         state[c] = x;
     }
