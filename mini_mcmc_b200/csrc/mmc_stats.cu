@@ -17,6 +17,7 @@
 // Host part (mmc_stats_finalize): the O(p * lags) Geyer loop and basic_stats (src/stats.rs:310-336).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mmc_common.cuh"
@@ -115,6 +116,184 @@ stats_pass_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, 
     }
 }
 
+// ---------------------------------------------------------------- shared-memory staged variant
+// When one split chain's [N, p] block fits in shared memory (C5: 200 x 100 x 4 B = 80 KB) it is fetched ONCE with a
+// single bulk async copy (cp.async.bulk + mbarrier, double buffered across chains) and every lag group is computed
+// from shared memory: thread (q, h) owns parameter q and the 16 lags lag0 + 16 h .. + 15, so one launch covers
+// 16 * H lags while the draws cross HBM once.
+__device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void st_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void st_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <bool kFirst>
+__global__ void __launch_bounds__(512, 1)
+stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int p, int64_t lag0, int H, int G, int nbuf,
+                   double *__restrict__ partial) {
+    extern __shared__ __align__(128) float st_smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int N = (int)(n / 2);
+    const int64_t C = 2 * c_local;
+    const int blk = N * p;                       // floats per split-chain block
+    float *bufs = st_smem;                       // [nbuf][blk]
+    float *mean_part = st_smem + (size_t)nbuf * blk;   // [H * G][p]
+    const int tid = threadIdx.x;
+    // thread (q, h, g): parameter q, lag group h (16 lags), time segment g (draws [t_lo, t_hi))
+    const int q = tid % p, r = tid / p, R = H * G;
+    const int h = r % H, g = r / H;
+    const bool active = r < R;
+    const int seg = (((N + G - 1) / G) + kLagBlock - 1) / kLagBlock * kLagBlock;
+    const int t_lo = g * seg, t_hi = (t_lo + seg < N) ? t_lo + seg : N;
+    const float inv_n = 1.0f / (float)N;
+    const uint32_t bytes = (uint32_t)blk * 4u;
+    if (tid == 0) {
+        st_mbar_init(st_smem_u32(&bars[0]), 1);
+        st_mbar_init(st_smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto block_src = [&](int64_t j) {
+        // splitcat, src/stats.rs:396-402
+        const int64_t chain = j < c_local ? j : j - c_local;
+        const int64_t row0 = j < c_local ? 0 : n - N;
+        return sample + (chain * n + row0) * p;
+    };
+    auto issue = [&](int64_t j, int b) {
+        st_mbar_expect_tx(st_smem_u32(&bars[b]), bytes);
+        st_bulk_load(st_smem_u32(bufs + (size_t)b * blk), block_src(j), bytes, st_smem_u32(&bars[b]));
+    };
+    float acc[kLagBlock];
+#pragma unroll
+    for (int i = 0; i < kLagBlock; ++i) acc[i] = 0.f;
+    double acc_m = 0.0, acc_m2 = 0.0;
+    const int lag_base = (int)lag0 + h * kLagBlock;
+
+    int64_t j = blockIdx.x;
+    if (tid == 0 && j < C) issue(j, 0);
+    uint32_t it = 0;
+    for (; j < C; j += gridDim.x, ++it) {
+        const int b = nbuf == 2 ? (int)(it & 1u) : 0;
+        const uint32_t ph = nbuf == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        if (nbuf == 2 && tid == 0 && j + gridDim.x < C) issue(j + gridDim.x, b ^ 1);   // prefetch the next chain
+        st_mbar_wait(st_smem_u32(&bars[b]), ph);
+        const float *x = bufs + (size_t)b * blk + q;
+        // ---- mean: thread (q, h) sums t = h, h + H, ...; the H partials are combined through shared memory
+        if (active) {
+            float s0 = 0.f;
+            for (int t = r; t < N; t += R) s0 += x[(size_t)t * p];
+            mean_part[r * p + q] = s0;
+        }
+        __syncthreads();
+        float m = 0.f;
+        if (active && t_lo < N) {
+            for (int rr = 0; rr < R; ++rr) m += mean_part[rr * p + q];
+            m *= inv_n;
+            // ---- centred lagged products for lags lag_base .. lag_base + 15 over this thread's time segment
+            float P[kLagBlock], ring[kLagBlock];
+#pragma unroll
+            for (int i = 0; i < kLagBlock; ++i) P[i] = 0.f;
+#pragma unroll
+            for (int u = 0; u < kLagBlock; ++u) {   // warm the ring with the 16 partner values preceding the segment
+                const int tb = t_lo - kLagBlock + u - lag_base;
+                const float vb = x[(size_t)(tb > 0 ? tb : 0) * p];
+                ring[u] = (t_lo > 0 && tb >= 0) ? vb - m : 0.f;
+            }
+            // full 16-blocks need no masks when the partner index cannot be negative; the rest takes the masked path
+            int t0 = t_lo;
+            const bool lag_zero = kFirst && h == 0;
+            for (; t0 + kLagBlock <= t_hi && (lag_zero || t0 >= lag_base); t0 += kLagBlock) {
+                const float *xa = x + (size_t)t0 * p;
+                const float *xb = x + (size_t)(t0 - lag_base) * p;
+#pragma unroll
+                for (int u = 0; u < kLagBlock; ++u) {
+                    const float a = xa[(size_t)u * p] - m;
+                    ring[u] = lag_zero ? a : xb[(size_t)u * p] - m;
+#pragma unroll
+                    for (int i = 0; i < kLagBlock; ++i) P[i] = fmaf(a, ring[(u - i) & (kLagBlock - 1)], P[i]);
+                }
+            }
+            for (; t0 < t_hi; t0 += kLagBlock) {
+#pragma unroll
+                for (int u = 0; u < kLagBlock; ++u) {
+                    const int t = t0 + u;
+                    const int tc = t < N ? t : N - 1;
+                    const int tb = tc - lag_base;
+                    const float va = x[(size_t)tc * p];
+                    const float vb = x[(size_t)(tb > 0 ? tb : 0) * p];
+                    const float a = t < N ? va - m : 0.f;
+                    ring[u] = (t < N && tb >= 0) ? vb - m : 0.f;
+#pragma unroll
+                    for (int i = 0; i < kLagBlock; ++i) P[i] = fmaf(a, ring[(u - i) & (kLagBlock - 1)], P[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kLagBlock; ++i) acc[i] += P[i] * inv_n;
+            if (kFirst && r == 0) {
+                acc_m += (double)m;
+                acc_m2 += (double)m * (double)m;
+            }
+        }
+        __syncthreads();   // everyone is done with buffer b (and mean_part) before it is refilled
+        if (nbuf == 1 && tid == 0 && j + gridDim.x < C) issue(j + gridDim.x, 0);
+    }
+    if (active) {
+        if (kFirst && r == 0) {
+            atomicAdd(partial + q, acc_m);
+            atomicAdd(partial + p + q, acc_m2);
+        }
+#pragma unroll
+        for (int i = 0; i < kLagBlock; ++i)
+            if (lag_base + i < N) atomicAdd(partial + (int64_t)(2 + lag_base + i) * p + q, (double)acc[i]);
+    }
+}
+
+// returns the number of lags covered by one launch (0 when the staged variant does not apply)
+int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p, int64_t lag0, int64_t n_lags,
+                      double *partial, cudaStream_t stream, int64_t *covered) {
+    *covered = 0;
+    const int64_t N = n / 2;
+    const size_t blk_bytes = (size_t)N * p * 4;
+    if (p % 4 != 0 || p > 512 || blk_bytes > 200 * 1024 || blk_bytes % 16 != 0 || getenv("MMC_STATS_NO_SMEM")) return MMC_OK;
+    if ((reinterpret_cast<uintptr_t>(sample) & 15) != 0) return MMC_OK;
+    int H = (int)std::min<int64_t>((n_lags + kLagBlock - 1) / kLagBlock, 512 / p);
+    if (H < 1) H = 1;
+    int G = (int)(512 / ((int64_t)p * H));     // time segments: fill the CTA when few lag groups are requested
+    if (G < 1) G = 1;
+    if (G > (int)((N + kLagBlock - 1) / kLagBlock)) G = (int)((N + kLagBlock - 1) / kLagBlock);
+    const size_t extra = (size_t)H * G * p * 4 + 256;
+    const int nbuf = (2 * blk_bytes + extra <= 220 * 1024) ? 2 : 1;
+    const size_t smem = nbuf * blk_bytes + extra;
+    int threads = (int)(((int64_t)H * G * p + 31) / 32 * 32);
+    int64_t grid = sm_count();
+    if (grid > 2 * c_local) grid = 2 * c_local;
+    auto kern = lag0 == 0 ? stats_block_kernel<true> : stats_block_kernel<false>;
+    MMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, threads, smem, stream>>>(sample, c_local, n, (int)p, lag0, H, G, nbuf, partial);
+    MMC_CUDA(cudaGetLastError());
+    *covered = std::min<int64_t>((int64_t)H * kLagBlock, N - lag0);
+    return MMC_OK;
+}
+
 int launch_pass(const float *sample, int64_t c_local, int64_t n, int64_t p, int64_t lag0, int nlag, double *partial,
                 cudaStream_t stream) {
     const int64_t nb = (p + 31) / 32;
@@ -150,11 +329,22 @@ int mmc_stats_partial_dev(const float *sample_dev, int64_t c_local, int64_t n, i
     cudaStream_t s = (cudaStream_t)stream;
     // zero the rows this call produces
     if (lag0 == 0) MMC_CUDA(cudaMemsetAsync(partial_dev, 0, sizeof(double) * 2 * p, s));
-    MMC_CUDA(cudaMemsetAsync(partial_dev + (2 + lag0) * p, 0, sizeof(double) * n_lags * p, s));
-    for (int64_t l = 0; l < n_lags; l += kLagBlock) {
+    {   // zero the rows this call produces (the staged kernel rounds its last group up to 16 lags)
+        const int64_t hi = std::min<int64_t>(N, lag0 + (n_lags + kLagBlock - 1) / kLagBlock * kLagBlock);
+        MMC_CUDA(cudaMemsetAsync(partial_dev + (2 + lag0) * p, 0, sizeof(double) * (hi - lag0) * p, s));
+    }
+    for (int64_t l = 0; l < n_lags;) {
+        int64_t covered = 0;
+        rc = launch_block_pass(sample_dev, c_local, n, p, lag0 + l, n_lags - l, partial_dev, s, &covered);
+        if (rc) return rc;
+        if (covered > 0) {   // shared-memory staged variant handled `covered` lags (it may compute a few beyond
+            l += covered;    // n_lags inside its last group of 16; those rows were zeroed below)
+            continue;
+        }
         const int nl = (int)std::min<int64_t>(kLagBlock, n_lags - l);
         rc = launch_pass(sample_dev, c_local, n, p, lag0 + l, nl, partial_dev, s);
         if (rc) return rc;
+        l += kLagBlock;
     }
     return MMC_OK;
 }
