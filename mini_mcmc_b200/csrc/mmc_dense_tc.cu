@@ -114,6 +114,22 @@ __host__ __device__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// 256-bit global accesses (LDG/STG.E.256): a lane moves one full 32-byte sector of its row per instruction, which
+// halves the L1->XBAR request count of the row-per-lane epilogue
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ldg256(const float *p) {
+    f8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(float *p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // Persistent kernel: CTA b processes tiles b, b + grid, ...; the fp32 accumulator is double buffered in TMEM
@@ -232,12 +248,12 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 const int col = half * (BN / 2) + chunk * 32;
                 const int64_t off = (row_ok ? m : 0) * D + n0 + col;
                 // issue the global loads of this chunk before waiting on the accumulator
-                float4 h4[8], l4[8], p4[8];
+                f8 h8[4], l8[4], p8[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    h4[j] = __ldcg(reinterpret_cast<const float4 *>(a_hi + off) + j);
-                    l4[j] = __ldcg(reinterpret_cast<const float4 *>(a_lo + off) + j);
-                    p4[j] = __ldcg(reinterpret_cast<const float4 *>(mom + off) + j);
+                for (int j = 0; j < 4; ++j) {
+                    h8[j] = ldg256(a_hi + off + 8 * j);
+                    l8[j] = ldg256(a_lo + off + 8 * j);
+                    p8[j] = ldg256(mom + off + 8 * j);
                 }
                 if (!waited) {
                     mbar_wait(tmem_full_bar(as), aph);
@@ -254,34 +270,33 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 }
                 if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float dl[4] = {h4[j].x + l4[j].x, h4[j].y + l4[j].y, h4[j].z + l4[j].z, h4[j].w + l4[j].w};
-                        float pp[4] = {p4[j].x, p4[j].y, p4[j].z, p4[j].w};
-                        float dn[4];
+                    for (int j = 0; j < 4; ++j) {
+                        float pp[8], hi[8], lo[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float z = __uint_as_float(r[4 * j + e]);
+                        for (int e = 0; e < 8; ++e) {
+                            const float z = __uint_as_float(r[8 * j + e]);
+                            const float dl = h8[j].v[e] + l8[j].v[e];
                             const float gh = -z * eps_half;
-                            if (mode != kModeMid) quad = fmaf(z, dl[e], quad);
+                            float dn;
+                            if (mode != kModeMid) quad = fmaf(z, dl, quad);
                             if (mode == kModeFirst) {
-                                pp[e] = pp[e] + gh;
-                                dn[e] = fmaf(eps, pp[e], dl[e]);
+                                pp[e] = p8[j].v[e] + gh;
+                                dn = fmaf(eps, pp[e], dl);
                             } else if (mode == kModeMid) {
-                                pp[e] = (pp[e] + gh) + gh;
-                                dn[e] = fmaf(eps, pp[e], dl[e]);
+                                pp[e] = (p8[j].v[e] + gh) + gh;
+                                dn = fmaf(eps, pp[e], dl);
                             } else {
-                                pp[e] = pp[e] + gh;
+                                pp[e] = p8[j].v[e] + gh;
                                 ke = fmaf(pp[e], pp[e], ke);
-                                dn[e] = dl[e];
+                                dn = dl;
                             }
+                            hi[e] = tf32_hi(dn);
+                            lo[e] = dn - hi[e];
                         }
-                        __stcg(reinterpret_cast<float4 *>(mom + off) + j, make_float4(pp[0], pp[1], pp[2], pp[3]));
+                        stg256(mom + off + 8 * j, pp);
                         if (mode != kModeLast) {
-                            float hi[4], lo[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dn[e]); lo[e] = dn[e] - hi[e]; }
-                            __stcg(reinterpret_cast<float4 *>(n_hi + off) + j, make_float4(hi[0], hi[1], hi[2], hi[3]));
-                            __stcg(reinterpret_cast<float4 *>(n_lo + off) + j, make_float4(lo[0], lo[1], lo[2], lo[3]));
+                            stg256(n_hi + off + 8 * j, hi);
+                            stg256(n_lo + off + 8 * j, lo);
                         }
                     }
                 }
