@@ -19,7 +19,7 @@ struct mmc_mh {
     int64_t step = 0;  // transitions since the last seed()
     uint64_t seed = 0;
     int32_t accept_mode = 1;
-    int32_t tile_u8 = 128, tile_u16 = 64;  // staging-tile steps (tuned on B200)
+    int32_t tile_u8 = 256, tile_u16 = 128;  // staging-tile steps (tuned on B200)
     void *d_state = nullptr;
     // Poisson tables
     int32_t table_len = 0;

@@ -324,6 +324,31 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
                     trow += kPoisPitch;
                 }
             }
+        } else if (vec_ok && (tpos % 4 == 0) && (p.n_collect % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0)) {
+            // every warp-wide store instruction covers one contiguous 1 KB run of a row (full 32 B sectors): lane l
+            // widens columns 4l .. 4l+3 of each 128-column group into one 256-bit streaming store
+#pragma unroll 4
+            for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+                for (int g = 0; g < (kPoisTile + 127) / 128; ++g) {
+                    const int col = 128 * g + 4 * lane;
+                    if (col < tpos) {
+                        unsigned long long a, b, c2, d;
+                        if (sizeof(Elem) == 1) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t *>(trow + col);
+                            a = v & 0xffu; b = (v >> 8) & 0xffu; c2 = (v >> 16) & 0xffu; d = v >> 24;
+                        } else {
+                            const uint32_t v0 = *reinterpret_cast<const uint32_t *>(trow + col);
+                            const uint32_t v1 = *reinterpret_cast<const uint32_t *>(trow + col + 2);
+                            a = v0 & 0xffffu; b = v0 >> 16; c2 = v1 & 0xffffu; d = v1 >> 16;
+                        }
+                        asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(row + col), "l"(a), "l"(b), "l"(c2), "l"(d)
+                                     : "memory");
+                    }
+                }
+                row += p.n_collect;
+                trow += kPoisPitch;
+            }
         } else if (vec_ok && (tpos % 2 == 0)) {
             // every warp-wide store instruction covers one contiguous 512 B run of a row (full 32 B sectors):
             // lane l widens columns (2l, 2l+1) of each 64-column group into one 16-byte streaming store
