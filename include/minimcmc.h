@@ -133,6 +133,10 @@ int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset);     /* first global chai
  * 1 (default) = compare the 53-bit uniform against host-built integer thresholds that encode the same
  * predicate with the host libm's ln (bit-exact with the reference's CPU decisions). */
 int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode);
+/* *_run_dev only: the caller's tensor has `pitch_steps` draws per chain row (0 = n_collect of the call), so a run can
+ * fill the window [t0, t0 + n_collect) of a [chains, pitch_steps, dim] tensor when it is handed out_dev + t0 * dim.
+ * This is how run_progress samples in blocks (progress statistics between blocks) without an extra copy. */
+int mmc_mh_set_out_pitch(mmc_mh *h, int64_t pitch_steps);
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay);
 int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, const mmc_replay_mh *replay_dev,
                    void *stream);
@@ -163,6 +167,7 @@ int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact);
 /* dense Gaussian target only: gradient GEMM on 0 = FP32 SIMT tiles, 1 = tcgen05 tensor cores (3xTF32 split, fp32
  * accumulation in TMEM).  exact = 1 always selects the FP32 path. */
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path);
+int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps); /* see mmc_mh_set_out_pitch */
 int mmc_hmc_step(mmc_hmc *h);
 int mmc_hmc_run(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, const mmc_replay_hmc *replay);
 int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_dev,
@@ -203,6 +208,12 @@ int mmc_nuts_create(mmc_nuts **h, const mmc_target_desc *target, const float *in
 int mmc_nuts_set_seed(mmc_nuts *h, uint64_t seed);
 int mmc_nuts_set_chain_offset(mmc_nuts *h, int64_t offset);
 int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact);
+int mmc_nuts_set_out_pitch(mmc_nuts *h, int64_t pitch_steps); /* see mmc_mh_set_out_pitch */
+/* Splitting one run over several launches (run_progress in blocks): adapt_until = absolute step count m up to which
+ * dual averaging adapts (-1 = the reference's rule `m <= n_discard` of each call, src/nuts.rs:681); resume = 1 makes
+ * the following runs continue the chains without init_chain (src/nuts.rs:528-545), so that the blocks reproduce the
+ * single-launch run exactly. */
+int mmc_nuts_set_continuation(mmc_nuts *h, int64_t adapt_until, int32_t resume);
 /* progress_semantics 0: NUTS::run (n_collect+n_discard-1 steps, slot 0 = starting position);
  *                    1: NUTS::run_progress (n_collect+n_discard steps). */
 int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress_semantics, float *out_host,
@@ -238,6 +249,33 @@ int mmc_stats_finalize(const double *partial_host, int64_t c_total, int64_t n, i
 typedef struct { float min, median, max, mean, std; } mmc_basic_stats;
 typedef struct { mmc_basic_stats ess, rhat; } mmc_run_stats;
 int mmc_basic_stats_of(const float *data_host, int64_t len, mmc_basic_stats *out);
+
+/* ------------------------------------------------------------------ progress trackers (run_progress)
+ * Replaces MultiChainTracker (src/stats.rs:189-307; HMC::run_progress src/hmc.rs:242-281) and ChainTracker +
+ * collect_rhat (src/stats.rs:26-178; ChainRunner::run_progress src/core.rs:90-136,229-324).  The reference copies
+ * every step's state to the host; here the tracker folds blocks of draws that are already in HBM:
+ * mmc_tracker_steps_dev(sample [chains, n_total, dim], steps [t0, t0 + n_steps)) applies `step` once per draw, in
+ * order, with the reference's f32 recurrences.  Rhat comes from f64 partial sums over the local chains
+ * ([sum mean | sum mean^2 | sum sm2] per parameter, then sum of p_accept weights, then chains) that can be summed over
+ * ranks before mmc_tracker_finalize.  mmc_tracker_summary = partial + finalize for one process; p_accept is
+ * MultiChainTracker::p_accept (MULTI) or the mean over all chains of ChainStats::p_accept (PER_CHAIN; the
+ * reference's progress bar averages the <= 5 chains it displays). */
+typedef struct mmc_tracker mmc_tracker;
+#define MMC_TRACK_MULTI 0
+#define MMC_TRACK_PER_CHAIN 1
+int mmc_tracker_create(mmc_tracker **out, int64_t chains, int32_t dim, int32_t flavor);
+/* ChainTracker::new(initial_state): [chains, dim] of dtype (mmc_dtype); MULTI starts from zeros like the reference */
+int mmc_tracker_set_initial_dev(mmc_tracker *t, const void *state_dev, int32_t dtype, void *stream);
+int mmc_tracker_steps_dev(mmc_tracker *t, const void *sample_dev, int32_t dtype, int64_t n_total, int64_t t0,
+                          int64_t n_steps, void *stream);
+int64_t mmc_tracker_partial_len(int32_t dim);
+int mmc_tracker_partial_dev(mmc_tracker *t, double *partial_dev, void *stream);
+int mmc_tracker_finalize(const double *partial_host, int64_t chains_total, int32_t dim, uint64_t n_steps, int32_t flavor,
+                         float *rhat_host, float *max_rhat);
+int mmc_tracker_summary(mmc_tracker *t, float *rhat_host, float *max_rhat, float *p_accept, uint64_t *n_steps);
+/* raw state for parity tests: mean / mean_sq [chains, dim]; p_accept [chains] (PER_CHAIN) or [1] (MULTI) */
+int mmc_tracker_get(mmc_tracker *t, float *mean_host, float *mean_sq_host, float *p_accept_host);
+void mmc_tracker_destroy(mmc_tracker *t);
 
 #ifdef __cplusplus
 }

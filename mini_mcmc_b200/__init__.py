@@ -11,6 +11,7 @@ from .distributions import (CustomTarget, DenseGaussian, DiffableGaussian2D, Gau
 from .hmc import HMC
 from .metropolis_hastings import MetropolisHastings
 from .nuts import NUTS
+from .progress import ChainTrackers, MultiChainTracker
 from .stats import BasicStats, RunStats, basic_stats, split_rhat_mean_ess
 
 __all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "NUTS", "Gaussian2D",

@@ -60,7 +60,7 @@ __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *_
 __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__restrict__ mean, const float *__restrict__ delta,
                                     const float *__restrict__ delta_lo, const float *__restrict__ scal, float norm_const, float *__restrict__ out,
                                     float *__restrict__ trace, unsigned long long *accept_count, int64_t chains, int D,
-                                    int64_t n_collect, int64_t slot, int64_t local_step) {
+                                    int64_t out_pitch, int64_t slot, int64_t local_step) {
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= chains) return;
@@ -83,7 +83,7 @@ __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__rest
             x = make_float4(d.x + m.x, d.y + m.y, d.z + m.z, d.w + m.w);
             *reinterpret_cast<float4 *>(pos + c * D + i) = x;
         }
-        if (out) *reinterpret_cast<float4 *>(out + (c * n_collect + slot) * D + i) = x;
+        if (out) *reinterpret_cast<float4 *>(out + (c * out_pitch + slot) * D + i) = x;
     }
     if (lane == 0) {
         if (acc) atomicAdd(accept_count, 1ULL);
@@ -287,7 +287,7 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
         const float *fin = a.gemm_path == 1 ? st->d_delta_split[cur] : st->d_delta[cur];
         const float *fin_lo = a.gemm_path == 1 ? st->d_delta_split[cur] + (size_t)M * D : nullptr;
         dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, fin, fin_lo, st->d_scal, st->norm_const,
-                                                       collect ? a.out : nullptr, a.trace, a.accept_count, M, D, a.n_collect,
+                                                       collect ? a.out : nullptr, a.trace, a.accept_count, M, D, a.out_pitch,
                                                        collect ? s - a.n_discard : 0, s);
     }
     MMC_CUDA(cudaGetLastError());

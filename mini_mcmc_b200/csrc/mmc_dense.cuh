@@ -34,6 +34,7 @@ struct DenseRunArgs {
     float *trace;            // optional [steps, chains, 4]
     unsigned long long *accept_count;
     int64_t chains, chain_offset, step_base, n_collect, n_discard;
+    int64_t out_pitch;       // draws per chain row of `out` (>= n_collect)
     float eps;
     int n_leapfrog;
     uint64_t seed;

@@ -21,6 +21,7 @@ struct mmc_hmc {
     int64_t step = 0;
     uint64_t seed = 0;
     int32_t exact = 0;
+    int64_t out_pitch = 0;       // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
     int32_t gemm_path = 0;       // dense Gaussian: 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32
     DenseState *dense = nullptr;  // only for MMC_T_DENSE_GAUSSIAN
     float *d_pos = nullptr;
@@ -223,6 +224,12 @@ int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact) {
     return MMC_OK;
 }
 
+int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps) {
+    MMC_REQUIRE(h && pitch_steps >= 0, "mmc_hmc_set_out_pitch: bad arguments");
+    h->out_pitch = pitch_steps;
+    return MMC_OK;
+}
+
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
     MMC_REQUIRE(h && (path == 0 || path == 1), "gemm path must be 0 (FP32 SIMT) or 1 (tcgen05 3xTF32)");
     h->gemm_path = path;
@@ -232,6 +239,7 @@ int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
 int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_dev, const mmc_replay_hmc *rp,
                     void *stream) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_hmc_run_dev: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0 || h->out_pitch >= n_collect, "mmc_hmc_run_dev: out pitch %lld < n_collect", (long long)h->out_pitch);
     const bool replay = rp && rp->momenta && rp->u;
     MMC_REQUIRE(!rp || replay, "HMC replay needs both momenta and u tapes");
     if (h->dense) {
@@ -247,6 +255,7 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
         a.step_base = h->step;
         a.n_collect = n_collect;
         a.n_discard = n_discard;
+        a.out_pitch = h->out_pitch > 0 ? h->out_pitch : n_collect;
         a.eps = (float)h->step_size;
         a.n_leapfrog = h->n_leapfrog;
         a.seed = h->seed;
@@ -269,6 +278,7 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
     p.step_base = h->step;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
+    p.out_pitch = h->out_pitch > 0 ? h->out_pitch : n_collect;
     p.eps = (float)h->step_size;
     p.n_leapfrog = h->n_leapfrog;
     p.key = seed_key(h->seed);
@@ -302,6 +312,7 @@ int mmc_hmc_step(mmc_hmc *h) {
 
 int mmc_hmc_run(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, const mmc_replay_hmc *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_hmc_run: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_hmc_run: an output pitch only applies to mmc_hmc_run_dev");
     const int64_t steps = n_collect + n_discard;
     const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * sizeof(float);
     int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 16);

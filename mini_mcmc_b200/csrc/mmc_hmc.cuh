@@ -24,6 +24,7 @@ struct HmcParams {
     int64_t chain_offset;
     int64_t step_base;
     int64_t n_collect, n_discard;
+    int64_t out_pitch;       // draws per chain row of `out` (>= n_collect)
     float eps;
     int n_leapfrog;
     uint2 key;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(128) hmc_run_kernel(const Target tgt, const Hm
                 reinterpret_cast<float4 *>(p.trace)[s * p.chains + c] = t;
             }
             if (s >= p.n_discard && p.out) {
-                float *o = p.out + (c * p.n_collect + (s - p.n_discard)) * D;
+                float *o = p.out + (c * p.out_pitch + (s - p.n_discard)) * D;
 #pragma unroll
                 for (int i = 0; i < D; ++i) o[i] = x[i];
             }

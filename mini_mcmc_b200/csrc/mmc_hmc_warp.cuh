@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) hmc_warp_kernel(const Target tgt, const H
         if (p.trace && lane == 0)
             reinterpret_cast<float4 *>(p.trace)[s * p.chains + c] = make_float4(logp_cur, logp_prop, accept_logp, acc ? 1.0f : 0.0f);
         if (s >= p.n_discard && p.out) {
-            float *o = p.out + (c * p.n_collect + (s - p.n_discard)) * D;
+            float *o = p.out + (c * p.out_pitch + (s - p.n_discard)) * D;
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const int i = lane * E + k;

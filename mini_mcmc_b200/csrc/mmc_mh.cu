@@ -19,6 +19,7 @@ struct mmc_mh {
     int64_t step = 0;  // transitions since the last seed()
     uint64_t seed = 0;
     int32_t accept_mode = 1;
+    int64_t out_pitch = 0;  // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
     int32_t tile_u8 = 256, tile_u16 = 128;  // staging-tile steps (tuned on B200)
     void *d_state = nullptr;
     // Poisson tables
@@ -145,6 +146,7 @@ int run_cont(mmc_mh *h, int64_t n_collect, int64_t n_discard, double *out_dev, c
     p.step_base = h->step;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
+    p.out_pitch = h->out_pitch > 0 ? h->out_pitch : n_collect;
     p.key = seed_key(h->seed);
     p.target_kind = h->target.kind;
     for (int i = 0; i < 6; ++i) p.tp[i] = h->target.params[i];
@@ -186,6 +188,7 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, 
     p.step_base = h->step;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
+    p.out_pitch = (!compact && h->out_pitch > 0) ? h->out_pitch : n_collect;
     {
         uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
         for (int r = 0; r < 10; ++r) {
@@ -300,6 +303,12 @@ int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset) {
     return MMC_OK;
 }
 
+int mmc_mh_set_out_pitch(mmc_mh *h, int64_t pitch_steps) {
+    MMC_REQUIRE(h && pitch_steps >= 0, "mmc_mh_set_out_pitch: bad arguments");
+    h->out_pitch = pitch_steps;
+    return MMC_OK;
+}
+
 int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode) {
     MMC_REQUIRE(h && (mode == 0 || mode == 1), "accept mode must be 0 or 1");
     h->accept_mode = mode;
@@ -310,6 +319,7 @@ int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_de
                    void *stream) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_mh_run_dev: bad arguments");
     MMC_REQUIRE(out_dev || n_collect == 0, "mmc_mh_run_dev: out is null");
+    MMC_REQUIRE(h->out_pitch == 0 || h->out_pitch >= n_collect, "mmc_mh_run_dev: out pitch %lld < n_collect", (long long)h->out_pitch);
     int rc;
     if (h->target.kind == MMC_T_POISSON)
         rc = run_poisson(h, n_collect, n_discard, (uint64_t *)out_dev, replay_dev, (cudaStream_t)stream);
@@ -371,6 +381,7 @@ static int mh_run_poisson_compact(mmc_mh *h, int64_t n_collect, int64_t n_discar
 
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run: an output pitch only applies to mmc_mh_run_dev");
     if (h->target.kind == MMC_T_POISSON && !replay && h->accept_mode == 1 && n_collect > 0 && !getenv("MMC_NO_COMPACT"))
         return mh_run_poisson_compact(h, n_collect, n_discard, (uint64_t *)out_host);
     const int64_t steps = n_collect + n_discard;

@@ -20,6 +20,7 @@ struct MhContParams {
     const double *u;       // replay [chains, steps]
     double *trace;         // optional [chains, steps, 4]
     int64_t chains, chain_offset, step_base, n_collect, n_discard;
+    int64_t out_pitch;     // draws per chain row of `out` (>= n_collect; the caller may fill a window of a longer tensor)
     uint2 key;
     int32_t target_kind;   // MMC_T_GAUSSIAN2D | MMC_T_ISO_GAUSSIAN
     double tp[6];          // Gaussian2D: mean0, mean1, a, b, c, d ; Iso: std
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) mh_cont_kernel(const MhContParams p) {
             t[0] = cur_lp; t[1] = prop_lp; t[2] = r; t[3] = acc ? 1.0 : 0.0;
         }
         if (s >= p.n_discard && p.out) {
-            double *o = p.out + (c * p.n_collect + (s - p.n_discard)) * D;
+            double *o = p.out + (c * p.out_pitch + (s - p.n_discard)) * D;
 #pragma unroll
             for (int i = 0; i < D; ++i) o[i] = x[i];
         }
@@ -180,6 +181,7 @@ struct MhPoissonParams {
     int32_t table_len;
     double lambda, ln_lambda, ln_half;
     int64_t chains, chain_offset, step_base, n_collect, n_discard;
+    int64_t out_pitch;     // draws per chain row of `out` (>= n_collect; the caller may fill a window of a longer tensor)
     uint32_t rk[20];        // Philox round keys (key + r * Weyl), host-expanded: they depend on the seed only
     int32_t *error_flag;    // set to 1 when a chain reaches the end of the table
 };
@@ -299,13 +301,13 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     int tpos = col_lo;                 // next column to fill
     int64_t t_base = -(int64_t)col_lo; // collected index of column 0
     // vector stores need aligned row segments for every chain of the warp
-    const bool vec_ok = kWide ? ((p.n_collect % 2 == 0) && col_lo == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0))
-                              : (((p.n_collect * sizeof(OutT)) % 4 == 0) && col_lo == 0 &&
+    const bool vec_ok = kWide ? ((p.out_pitch % 2 == 0) && col_lo == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0))
+                              : (((p.out_pitch * sizeof(OutT)) % 4 == 0) && col_lo == 0 &&
                                  ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0));
     auto flush = [&]() {
         __syncwarp();
         const int nrows = (int)((p.chains - chain0 < 32) ? (p.chains - chain0) : 32);
-        OutT *row = reinterpret_cast<OutT *>(p.out) + chain0 * p.n_collect + t_base;
+        OutT *row = reinterpret_cast<OutT *>(p.out) + chain0 * p.out_pitch + t_base;
         const Elem *trow = tile;
         if (!kWide) {
             constexpr int kPer = 4 / (int)sizeof(Elem);   // columns per 32-bit word
@@ -313,18 +315,18 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
                 for (int r = 0; r < nrows; ++r) {
                     for (int col = kPer * lane; col < tpos; col += 32 * kPer)
                         __stcs(reinterpret_cast<unsigned int *>(row + col), *reinterpret_cast<const unsigned int *>(trow + col));
-                    row += p.n_collect;
+                    row += p.out_pitch;
                     trow += kPoisPitch;
                 }
             } else {
                 for (int r = 0; r < nrows; ++r) {
                     for (int col = lane; col < tpos; col += 32)
                         if (col >= col_lo) row[col] = (OutT)trow[col];
-                    row += p.n_collect;
+                    row += p.out_pitch;
                     trow += kPoisPitch;
                 }
             }
-        } else if (vec_ok && (tpos % 4 == 0) && (p.n_collect % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0)) {
+        } else if (vec_ok && (tpos % 4 == 0) && (p.out_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0)) {
             // every warp-wide store instruction covers one contiguous 1 KB run of a row (full 32 B sectors): lane l
             // widens columns 4l .. 4l+3 of each 128-column group into one 256-bit streaming store
 #pragma unroll 4
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
                                      : "memory");
                     }
                 }
-                row += p.n_collect;
+                row += p.out_pitch;
                 trow += kPoisPitch;
             }
         } else if (vec_ok && (tpos % 2 == 0)) {
@@ -370,14 +372,14 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
                                make_ulonglong2((unsigned long long)a, (unsigned long long)b));
                     }
                 }
-                row += p.n_collect;
+                row += p.out_pitch;
                 trow += kPoisPitch;
             }
         } else {
             for (int r = 0; r < nrows; ++r) {
                 for (int col = lane; col < tpos; col += 32)
                     if (col >= col_lo) row[col] = (OutT)trow[col];
-                row += p.n_collect;
+                row += p.out_pitch;
                 trow += kPoisPitch;
             }
         }

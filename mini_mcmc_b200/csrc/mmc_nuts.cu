@@ -15,6 +15,9 @@ struct mmc_nuts {
     int64_t chain_offset = 0;
     uint64_t seed = 0;
     int32_t exact = 0;
+    int64_t out_pitch = 0;     // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
+    int64_t adapt_until = -1;  // -1: the reference's rule (m <= n_discard of the call)
+    int32_t resume = 0;        // 1: the next run continues the chains without init_chain
     float *d_pos = nullptr;
     double *d_state = nullptr;            // [chains, 5]
     unsigned long long *d_counters = nullptr;  // [8 + 32]
@@ -103,10 +106,24 @@ int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact) {
     return MMC_OK;
 }
 
+int mmc_nuts_set_out_pitch(mmc_nuts *h, int64_t pitch_steps) {
+    MMC_REQUIRE(h && pitch_steps >= 0, "mmc_nuts_set_out_pitch: bad arguments");
+    h->out_pitch = pitch_steps;
+    return MMC_OK;
+}
+
+int mmc_nuts_set_continuation(mmc_nuts *h, int64_t adapt_until, int32_t resume) {
+    MMC_REQUIRE(h && adapt_until >= -1, "mmc_nuts_set_continuation: bad arguments");
+    h->adapt_until = adapt_until;
+    h->resume = resume ? 1 : 0;
+    return MMC_OK;
+}
+
 int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress, float *out_dev,
                      const mmc_replay_nuts *rp, void *stream) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0, "mmc_nuts_run_dev: bad arguments");
     MMC_REQUIRE(out_dev || n_collect == 0, "mmc_nuts_run_dev: out is null");
+    MMC_REQUIRE(h->out_pitch == 0 || h->out_pitch >= n_collect, "mmc_nuts_run_dev: out pitch %lld < n_collect", (long long)h->out_pitch);
     const bool replay = rp && rp->normals && rp->exps && rp->unifs;
     MMC_REQUIRE(!rp || replay, "NUTS replay needs normals, exps and unifs tapes");
     cudaStream_t s = (cudaStream_t)stream;
@@ -123,6 +140,9 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     p.chain_offset = h->chain_offset;
     p.n_collect = n_collect;
     p.n_discard = n_discard;
+    p.out_pitch = h->out_pitch > 0 ? h->out_pitch : n_collect;
+    p.adapt_until = h->adapt_until >= 0 ? h->adapt_until : n_discard;
+    p.resume = h->resume;
     p.progress = progress ? 1 : 0;
     p.max_depth = h->max_depth;
     p.D = h->dim;
@@ -143,6 +163,7 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
 int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress, float *out_host,
                  const mmc_replay_nuts *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_nuts_run: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_nuts_run: an output pitch only applies to mmc_nuts_run_dev");
     const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * sizeof(float);
     int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 16);
     if (rc) return rc;

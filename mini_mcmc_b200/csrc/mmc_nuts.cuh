@@ -144,7 +144,10 @@ struct NutsParams {
     unsigned long long *counters;  // [0] next chain, [1] n_grad, [2] n_transitions, [3] uniforms consumed, [8..] depth histogram
     int64_t chains, chain_offset;
     int64_t n_collect, n_discard;
+    int64_t out_pitch;      // draws per chain row of `out` (>= n_collect)
+    int64_t adapt_until;    // dual averaging adapts while m <= adapt_until (= n_discard in the reference, src/nuts.rs:681)
     int32_t progress, max_depth, D;
+    int32_t resume;         // 1: continue a run split over several launches (skip init_chain, keep mu)
     double target_accept;
     uint2 key;
 };
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
         const long long t_0 = 10;
 
         auto store_draw = [&](int64_t slot) {
-            float *o = p.out + (c * p.n_collect + slot) * p.D;
+            float *o = p.out + (c * p.out_pitch + slot) * p.D;
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const int i = lane * E + k;
@@ -459,8 +462,10 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
         };
 
         // ---- init_chain, src/nuts.rs:528-545
-        if (p.n_collect > 0) store_draw(0);
-        {
+        if (p.resume) {
+            mu = (ST)st[3];
+        } else {
+            if (p.n_collect > 0) store_draw(0);
             float m0[E];
             w.step_word = 0;
             w.q = 0; w.q_batch = 0xffffffffu;
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
         }
 
         const int64_t total = p.n_collect + p.n_discard;
-        const int64_t first = p.progress ? 0 : 1;
+        const int64_t first = (p.progress || p.resume) ? 0 : 1;
         for (int64_t it = first; it < total; ++it) {
             // ---- NUTSChain::step, src/nuts.rs:550-691
             m += 1;
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
             // dual averaging, src/nuts.rs:676-690
             ST eta = (ST)1.0 / (ST)(m + t_0);
             h_bar = ((ST)1.0 - eta) * h_bar + eta * (delta - alpha / (ST)n_alpha);
-            if (m <= p.n_discard) {
+            if (m <= p.adapt_until) {
                 const ST _m = (ST)m;
                 epsilon = s_exp(mu - s_sqrt(_m) / gamma * h_bar);
                 eta = s_pow(_m, -kappa);

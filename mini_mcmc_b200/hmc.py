@@ -85,12 +85,36 @@ class HMC:
                                       C.byref(rp) if rp is not None else None, L.current_stream_ptr()))
         return out
 
-    def run_progress(self, n_collect: int, n_discard: int):
-        """HMC::run_progress, src/hmc.rs:222-294: (sample, RunStats)."""
+    def run_progress(self, n_collect: int, n_discard: int, progress=True, block=None, group=None):
+        """HMC::run_progress, src/hmc.rs:222-294: (sample [chains, n_collect, D] in HBM, RunStats).
+
+        Burn-in runs untracked; a MultiChainTracker then folds the post-burn-in positions and every collected draw
+        (src/hmc.rs:242-281).  Sampling proceeds in blocks of `block` steps written straight into the final tensor;
+        after each block `progress(done, dict(p_accept, max_rhat, rhat, n))` is called (True = status line on
+        stderr, False = silent).  The draws are identical to run_device(n_collect, n_discard)."""
+        import torch
+
+        from .progress import MultiChainTracker, block_plan, resolve_reporter
         from .stats import RunStats
 
-        sample = self.run_device(n_collect, n_discard)
-        return sample, RunStats.from_sample(sample)
+        report = resolve_reporter(progress, "HMC", n_collect)
+        if n_discard:
+            self.run_device(0, n_discard)
+        tracker = MultiChainTracker(self.n_chains, self.dim)
+        tracker.step(self.positions)
+        sample = torch.empty((self.n_chains, n_collect, self.dim), dtype=torch.float32, device="cuda")
+        L.check(L.lib.mmc_hmc_set_out_pitch(self._h, C.c_int64(n_collect)))
+        try:
+            for t0, k in block_plan(n_collect, block):
+                L.check(L.lib.mmc_hmc_run_dev(self._h, C.c_int64(k), C.c_int64(0), C.c_void_p(sample.data_ptr() + 4 * t0 * self.dim),
+                                              None, L.current_stream_ptr()))
+                tracker.steps(sample, t0, k)
+                if report is not None:
+                    report(t0 + k, tracker.summary(group=group))
+        finally:
+            L.check(L.lib.mmc_hmc_set_out_pitch(self._h, C.c_int64(0)))
+        self.tracker = tracker
+        return sample, RunStats.from_sample(sample, group=group)
 
     def export_tape(self, step_base: int, steps: int):
         """The native Philox draws (momenta [steps, chains, D], u [steps, chains]) for a step range."""

@@ -80,12 +80,53 @@ class MetropolisHastings:
                                      C.byref(rp) if rp is not None else None, L.current_stream_ptr()))
         return out
 
-    def run_progress(self, n_collect: int, n_discard: int):
-        """ChainRunner::run_progress, src/core.rs:208-360: (sample, RunStats)."""
+    def run_progress(self, n_collect: int, n_discard: int, progress=True, block=None, group=None, device=False):
+        """ChainRunner::run_progress, src/core.rs:208-360: (sample [chains, n_collect, dim], RunStats).
+
+        One ChainTracker per chain folds every step, burn-in included (run_chain_progress, src/core.rs:90-136); the
+        progress message is the mean p(accept) and max over collect_rhat (src/core.rs:262-289).  Steps run in blocks:
+        burn-in blocks go to a scratch tensor, collected blocks straight into the final one.  `progress(done, info)`
+        is called after each block (True = status line on stderr).  device=True keeps the sample in HBM."""
+        import torch
+
+        from .progress import ChainTrackers, block_plan, resolve_reporter
         from .stats import RunStats
 
-        sample = self.run(n_collect, n_discard)
-        return sample, RunStats.from_sample(sample)
+        total = n_collect + n_discard
+        report = resolve_reporter(progress, "MH", total)
+        esize = 8
+        tdt = torch.int64 if self._np_dtype == np.uint64 else torch.float64
+        tracker = ChainTrackers(self.dim, self.current_state())
+        sample = torch.empty((self.n_chains, n_collect, self.dim), dtype=tdt, device="cuda")
+
+        def run_block(dst_ptr, k):
+            L.check(L.lib.mmc_mh_run_dev(self._h, C.c_int64(k), C.c_int64(0), C.c_void_p(dst_ptr), None, L.current_stream_ptr()))
+
+        plan_d = block_plan(n_discard, block)
+        if plan_d:
+            scratch = torch.empty((self.n_chains, plan_d[0][1], self.dim), dtype=tdt, device="cuda")
+            for t0, k in plan_d:
+                L.check(L.lib.mmc_mh_set_out_pitch(self._h, C.c_int64(scratch.shape[1])))
+                run_block(scratch.data_ptr(), k)
+                tracker.steps(scratch, 0, k)
+                if report is not None:
+                    report(t0 + k, tracker.summary(group=group))
+            del scratch
+        L.check(L.lib.mmc_mh_set_out_pitch(self._h, C.c_int64(n_collect)))
+        try:
+            for t0, k in block_plan(n_collect, block):
+                run_block(sample.data_ptr() + esize * t0 * self.dim, k)
+                tracker.steps(sample, t0, k)
+                if report is not None:
+                    report(n_discard + t0 + k, tracker.summary(group=group))
+        finally:
+            L.check(L.lib.mmc_mh_set_out_pitch(self._h, C.c_int64(0)))
+        self.tracker = tracker
+        stats = RunStats.from_sample(sample, group=group)
+        if device:
+            return sample, stats
+        host = sample.cpu().numpy()
+        return (host.view(np.uint64) if self._np_dtype == np.uint64 else host), stats
 
     def d2h_bytes_per_draw(self) -> int:
         return int(L.lib.mmc_mh_d2h_bytes_per_draw(self._h))

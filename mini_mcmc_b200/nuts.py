@@ -87,15 +87,59 @@ class NUTS:
                                        L.vp(out), C.byref(rp) if rp is not None else None, L.current_stream_ptr()))
         return out
 
-    def run_progress(self, n_collect: int, n_discard: int, replay=None, group=None):
+    def run_progress(self, n_collect: int, n_discard: int, replay=None, group=None, progress=False, block=None):
         """NUTS::run_progress, src/nuts.rs:194-338: n_collect + n_discard steps, returns (sample, RunStats);
-        the statistics are computed on the device (and all-reduced across ranks when sharded)."""
+        the statistics are computed on the device (and all-reduced across ranks when sharded).
+
+        With `progress` (True = status line on stderr, or a callable(done, info)) the run is split into blocks of
+        `block` steps (mmc_nuts_set_continuation keeps the adaptation window and skips init_chain on the later
+        blocks, so the draws equal the single-launch run); one ChainTracker per chain folds every step, burn-in
+        included (NUTSChain::run_progress, src/nuts.rs:472-527) and the message is mean p(accept) / max collect_rhat."""
         from .stats import RunStats
 
         if replay is not None:
             sample = self._run(n_collect, n_discard, 1, replay, None)
-        else:
+            return sample, RunStats.from_sample(sample, group=group)
+        if progress in (False, None):
             sample = self.run_device(n_collect, n_discard, progress=True)
+            return sample, RunStats.from_sample(sample, group=group)
+        import torch
+
+        from .progress import ChainTrackers, block_plan, resolve_reporter
+
+        total = n_collect + n_discard
+        report = resolve_reporter(progress, "NUTS", total)
+        tracker = ChainTrackers(self.dim, self.positions)
+        sample = torch.empty((self.n_chains, n_collect, self.dim), dtype=torch.float32, device="cuda")
+
+        def run_block(dst_ptr, k, first):
+            # the reference compares the chain's absolute step count m with this call's n_discard (src/nuts.rs:681)
+            L.check(L.lib.mmc_nuts_set_continuation(self._h, C.c_int64(n_discard), C.c_int32(0 if first else 1)))
+            L.check(L.lib.mmc_nuts_run_dev(self._h, C.c_int64(k), C.c_int64(0), C.c_int32(1), C.c_void_p(dst_ptr), None,
+                                           L.current_stream_ptr()))
+
+        first = True
+        try:
+            plan_d = block_plan(n_discard, block)
+            if plan_d:
+                scratch = torch.empty((self.n_chains, plan_d[0][1], self.dim), dtype=torch.float32, device="cuda")
+                L.check(L.lib.mmc_nuts_set_out_pitch(self._h, C.c_int64(scratch.shape[1])))
+                for t0, k in plan_d:
+                    run_block(scratch.data_ptr(), k, first)
+                    first = False
+                    tracker.steps(scratch, 0, k)
+                    report(t0 + k, tracker.summary(group=group))
+                del scratch
+            L.check(L.lib.mmc_nuts_set_out_pitch(self._h, C.c_int64(n_collect)))
+            for t0, k in block_plan(n_collect, block):
+                run_block(sample.data_ptr() + 4 * t0 * self.dim, k, first)
+                first = False
+                tracker.steps(sample, t0, k)
+                report(n_discard + t0 + k, tracker.summary(group=group))
+        finally:
+            L.check(L.lib.mmc_nuts_set_out_pitch(self._h, C.c_int64(0)))
+            L.check(L.lib.mmc_nuts_set_continuation(self._h, C.c_int64(-1), C.c_int32(0)))
+        self.tracker = tracker
         return sample, RunStats.from_sample(sample, group=group)
 
     def state(self) -> np.ndarray:

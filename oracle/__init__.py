@@ -435,3 +435,46 @@ class MultiChainTracker:
         within = sm2.mean(axis=0, dtype=np.float32)
         var = within * ((n - np.float32(1.0)) / n) + between * (np.float32(1.0) / n)
         return np.sqrt(var / within)
+
+
+class ChainTracker:
+    """ChainTracker, src/stats.rs:26-141: one chain's f32 running mean / mean-of-squares and accept EMA.
+    p_accept starts at -1; the first step seeds it with (x[0] != initial[0]) before folding the whole-row
+    comparison once (src/stats.rs:103-122)."""
+
+    ALPHA = np.float32(0.01)
+
+    def __init__(self, n_params, initial_state):
+        self.n = 0
+        self.p_accept = np.float32(-1.0)
+        self.last_state = np.asarray(initial_state, dtype=np.float64).astype(np.float32).reshape(n_params)
+        self.mean = np.zeros(n_params, dtype=np.float32)
+        self.mean_sq = np.zeros(n_params, dtype=np.float32)
+
+    def step(self, x):
+        self.n += 1
+        n = np.float32(self.n)
+        x = np.asarray(x).astype(np.float32).reshape(self.mean.shape)
+        self.mean = (self.mean * (n - np.float32(1.0)) + x) / n
+        self.mean_sq = x * x if self.n == 1 else (self.mean_sq * (n - np.float32(1.0)) + x * x) / n
+        p = self.p_accept if self.p_accept >= 0 else np.float32(1.0 if x[0] != self.last_state[0] else 0.0)
+        accepted = np.float32(1.0 if np.any(x != self.last_state) else 0.0)
+        self.p_accept = (np.float32(1.0) - self.ALPHA) * p + self.ALPHA * accepted
+        self.last_state = x.copy()
+
+    def stats(self):
+        n = np.float32(self.n)
+        return dict(n=self.n, p_accept=self.p_accept, mean=self.mean.copy(),
+                    sm2=(self.mean_sq - self.mean * self.mean) * n / (n - np.float32(1.0)))
+
+
+def collect_rhat(chain_stats):
+    """collect_rhat / withinvar_from_cs, src/stats.rs:150-178 (between divides by chains*params - 1, :173)."""
+    means = np.stack([s["mean"] for s in chain_stats]).astype(np.float32)
+    sm2s = np.stack([s["sm2"] for s in chain_stats]).astype(np.float32)
+    within = sm2s.mean(axis=0, dtype=np.float32)
+    diffs = means - means.mean(axis=0, dtype=np.float32)[None, :]
+    between = (diffs * diffs).sum(axis=0, dtype=np.float32) / np.float32(diffs.size - 1)
+    n = np.float32(sum(np.float32(s["n"]) for s in chain_stats)) / np.float32(len(chain_stats))
+    var = between + within * ((n - np.float32(1.0)) / n)
+    return np.sqrt(var / within)
