@@ -10,7 +10,7 @@ use std::ffi::{c_char, c_void, CStr};
 #[repr(C)] pub struct mmc_replay_hmc { pub momenta: *const f32, pub u: *const f32, pub trace: *mut f32 }
 #[repr(C)] pub struct mmc_replay_nuts { pub normals: *const f64, pub cap_normals: i64, pub exps: *const f64, pub cap_exps: i64, pub unifs: *const f64, pub cap_unifs: i64 }
 #[repr(C)] pub struct mmc_basic_stats { pub min: f32, pub median: f32, pub max: f32, pub mean: f32, pub std: f32 }
-pub enum mmc_mh {} pub enum mmc_hmc {} pub enum mmc_nuts {}
+pub enum mmc_mh {} pub enum mmc_hmc {} pub enum mmc_nuts {} pub enum mmc_tracker {}
 
 extern "C" {
     pub fn mmc_last_error() -> *const c_char;
@@ -31,6 +31,15 @@ extern "C" {
     pub fn mmc_nuts_destroy(h: *mut mmc_nuts);
     pub fn mmc_split_rhat_ess(sample: *const f32, c: i64, n: i64, p: i64, rhat: *mut f32, ess: *mut f32) -> i32;
     pub fn mmc_basic_stats_of(data: *const f32, len: i64, out: *mut mmc_basic_stats) -> i32;
+    // run_progress: block-wise device runs + device-side trackers (src/stats.rs:26-307)
+    pub fn mmc_hmc_run_dev(h: *mut mmc_hmc, n_collect: i64, n_discard: i64, out_dev: *mut f32, replay: *const mmc_replay_hmc, stream: *mut c_void) -> i32;
+    pub fn mmc_hmc_set_out_pitch(h: *mut mmc_hmc, pitch_steps: i64) -> i32;
+    pub fn mmc_hmc_positions_dev(h: *mut mmc_hmc, positions_dev: *mut *mut f32) -> i32;
+    pub fn mmc_tracker_create(t: *mut *mut mmc_tracker, chains: i64, dim: i32, flavor: i32) -> i32;
+    pub fn mmc_tracker_set_initial_dev(t: *mut mmc_tracker, state_dev: *const c_void, dtype: i32, stream: *mut c_void) -> i32;
+    pub fn mmc_tracker_steps_dev(t: *mut mmc_tracker, sample_dev: *const c_void, dtype: i32, n_total: i64, t0: i64, n_steps: i64, stream: *mut c_void) -> i32;
+    pub fn mmc_tracker_summary(t: *mut mmc_tracker, rhat: *mut f32, max_rhat: *mut f32, p_accept: *mut f32, n_steps: *mut u64) -> i32;
+    pub fn mmc_tracker_destroy(t: *mut mmc_tracker);
 }
 
 fn check(rc: i32) -> Result<(), String> {
