@@ -16,8 +16,10 @@
 //
 // Host part (mmc_stats_finalize): the O(p * lags) Geyer loop and basic_stats (src/stats.rs:310-336).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "mmc_common.cuh"
@@ -148,18 +150,20 @@ __device__ __forceinline__ void st_bulk_load(uint32_t dst, const void *src, uint
 
 template <bool kFirst>
 __global__ void __launch_bounds__(512, 1)
-stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int p, int64_t lag0, int H, int G, int nbuf,
+stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int p, int64_t lag0, int H, int G, int K, int nbuf,
                    double *__restrict__ partial) {
     extern __shared__ __align__(128) float st_smem[];
     __shared__ __align__(8) uint64_t bars[2];
     const int N = (int)(n / 2);
     const int64_t C = 2 * c_local;
     const int blk = N * p;                       // floats per split-chain block
-    float *bufs = st_smem;                       // [nbuf][blk]
-    float *mean_part = st_smem + (size_t)nbuf * blk;   // [H * G][p]
+    float *bufs = st_smem;                       // [nbuf][K][blk]: K split chains are staged per round (small p)
+    float *mean_part = st_smem + (size_t)nbuf * K * blk;   // [H * G][K * p]
     const int tid = threadIdx.x;
-    // thread (q, h, g): parameter q, lag group h (16 lags), time segment g (draws [t_lo, t_hi))
-    const int q = tid % p, r = tid / p, R = H * G;
+    // thread (k, q, h, g): staged chain k, parameter q, lag group h (16 lags), time segment g (draws [t_lo, t_hi))
+    const int PK = p * K;
+    const int v = tid % PK, r = tid / PK, R = H * G;
+    const int q = v % p, k = v / p;
     const int h = r % H, g = r / H;
     const bool active = r < R;
     const int seg = (((N + G - 1) / G) + kLagBlock - 1) / kLagBlock * kLagBlock;
@@ -179,8 +183,10 @@ stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n,
         return sample + (chain * n + row0) * p;
     };
     auto issue = [&](int64_t j, int b) {
-        st_mbar_expect_tx(st_smem_u32(&bars[b]), bytes);
-        st_bulk_load(st_smem_u32(bufs + (size_t)b * blk), block_src(j), bytes, st_smem_u32(&bars[b]));
+        const int nk = (int)((C - j < K) ? (C - j) : K);
+        st_mbar_expect_tx(st_smem_u32(&bars[b]), bytes * (uint32_t)nk);
+        for (int kk = 0; kk < nk; ++kk)
+            st_bulk_load(st_smem_u32(bufs + ((size_t)b * K + kk) * blk), block_src(j + kk), bytes, st_smem_u32(&bars[b]));
     };
     float acc[kLagBlock];
 #pragma unroll
@@ -188,25 +194,27 @@ stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n,
     double acc_m = 0.0, acc_m2 = 0.0;
     const int lag_base = (int)lag0 + h * kLagBlock;
 
-    int64_t j = blockIdx.x;
+    int64_t j = (int64_t)blockIdx.x * K;
+    const int64_t stride = (int64_t)gridDim.x * K;
     if (tid == 0 && j < C) issue(j, 0);
     uint32_t it = 0;
-    for (; j < C; j += gridDim.x, ++it) {
+    for (; j < C; j += stride, ++it) {
         const int b = nbuf == 2 ? (int)(it & 1u) : 0;
         const uint32_t ph = nbuf == 2 ? ((it >> 1) & 1u) : (it & 1u);
-        if (nbuf == 2 && tid == 0 && j + gridDim.x < C) issue(j + gridDim.x, b ^ 1);   // prefetch the next chain
+        if (nbuf == 2 && tid == 0 && j + stride < C) issue(j + stride, b ^ 1);   // prefetch the next round
         st_mbar_wait(st_smem_u32(&bars[b]), ph);
-        const float *x = bufs + (size_t)b * blk + q;
-        // ---- mean: thread (q, h) sums t = h, h + H, ...; the H partials are combined through shared memory
-        if (active) {
+        const bool have = active && (j + k < C);
+        const float *x = bufs + ((size_t)b * K + k) * blk + q;
+        // ---- mean: thread (k, q, r) sums t = r, r + R, ...; the R partials are combined through shared memory
+        if (have) {
             float s0 = 0.f;
             for (int t = r; t < N; t += R) s0 += x[(size_t)t * p];
-            mean_part[r * p + q] = s0;
+            mean_part[r * PK + v] = s0;
         }
         __syncthreads();
         float m = 0.f;
-        if (active && t_lo < N) {
-            for (int rr = 0; rr < R; ++rr) m += mean_part[rr * p + q];
+        if (have && t_lo < N) {
+            for (int rr = 0; rr < R; ++rr) m += mean_part[rr * PK + v];
             m *= inv_n;
             // ---- centred lagged products for lags lag_base .. lag_base + 15 over this thread's time segment
             float P[kLagBlock], ring[kLagBlock];
@@ -254,7 +262,7 @@ stats_block_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n,
             }
         }
         __syncthreads();   // everyone is done with buffer b (and mean_part) before it is refilled
-        if (nbuf == 1 && tid == 0 && j + gridDim.x < C) issue(j + gridDim.x, 0);
+        if (nbuf == 1 && tid == 0 && j + stride < C) issue(j + stride, 0);
     }
     if (active) {
         if (kFirst && r == 0) {
@@ -273,22 +281,30 @@ int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p
     *covered = 0;
     const int64_t N = n / 2;
     const size_t blk_bytes = (size_t)N * p * 4;
-    if (p % 4 != 0 || p > 512 || blk_bytes > 200 * 1024 || blk_bytes % 16 != 0 || getenv("MMC_STATS_NO_SMEM")) return MMC_OK;
+    // bulk copies need 16-byte aligned, 16-byte granular split-chain blocks (both halves of every chain)
+    if (p > 512 || blk_bytes > 200 * 1024 || blk_bytes % 16 != 0 || ((size_t)n * p * 4) % 16 != 0 || ((size_t)(n - N) * p * 4) % 16 != 0 ||
+        getenv("MMC_STATS_NO_SMEM"))
+        return MMC_OK;
     if ((reinterpret_cast<uintptr_t>(sample) & 15) != 0) return MMC_OK;
     int H = (int)std::min<int64_t>((n_lags + kLagBlock - 1) / kLagBlock, 512 / p);
     if (H < 1) H = 1;
     int G = (int)(512 / ((int64_t)p * H));     // time segments: fill the CTA when few lag groups are requested
     if (G < 1) G = 1;
     if (G > (int)((N + kLagBlock - 1) / kLagBlock)) G = (int)((N + kLagBlock - 1) / kLagBlock);
-    const size_t extra = (size_t)H * G * p * 4 + 256;
-    const int nbuf = (2 * blk_bytes + extra <= 220 * 1024) ? 2 : 1;
-    const size_t smem = nbuf * blk_bytes + extra;
-    int threads = (int)(((int64_t)H * G * p + 31) / 32 * 32);
+    // small p: stage K split chains per round so that the CTA still has ~512 threads of work
+    int K = (int)std::min<int64_t>(16, 512 / ((int64_t)p * H * G));
+    if (K < 1) K = 1;
+    while (K > 1 && 2 * (size_t)K * blk_bytes + (size_t)H * G * K * p * 4 + 256 > 200 * 1024) --K;
+    if ((int64_t)K > 2 * c_local) K = (int)(2 * c_local);
+    const size_t extra = (size_t)H * G * K * p * 4 + 256;
+    const int nbuf = (2 * K * blk_bytes + extra <= 220 * 1024) ? 2 : 1;
+    const size_t smem = nbuf * K * blk_bytes + extra;
+    int threads = (int)(((int64_t)H * G * K * p + 31) / 32 * 32);
     int64_t grid = sm_count();
-    if (grid > 2 * c_local) grid = 2 * c_local;
+    if (grid > (2 * c_local + K - 1) / K) grid = (2 * c_local + K - 1) / K;
     auto kern = lag0 == 0 ? stats_block_kernel<true> : stats_block_kernel<false>;
     MMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, threads, smem, stream>>>(sample, c_local, n, (int)p, lag0, H, G, nbuf, partial);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(sample, c_local, n, (int)p, lag0, H, G, K, nbuf, partial);
     MMC_CUDA(cudaGetLastError());
     *covered = std::min<int64_t>((int64_t)H * kLagBlock, N - lag0);
     return MMC_OK;
@@ -399,28 +415,48 @@ int mmc_split_rhat_ess_dev(const float *sample_dev, int64_t c, int64_t n, int64_
     const int64_t N = n / 2;
     const int64_t len = mmc_stats_partial_len(n, p);
     cudaStream_t s = (cudaStream_t)stream;
-    double *d_partial = nullptr;
-    MMC_CUDA(cudaMalloc((void **)&d_partial, sizeof(double) * len));
+    // grow-only device workspace shared by the calls of this process (cudaMalloc / cudaFree cost 2-16 ms each on a
+    // busy context, more than the kernel itself); the lock mirrors "a handle is not thread-safe"
+    static std::mutex ws_mutex;
+    static double *ws = nullptr;
+    static size_t ws_len = 0;
+    static int ws_device = -1;
+    std::lock_guard<std::mutex> guard(ws_mutex);
+    int dev = 0;
+    MMC_CUDA(cudaGetDevice(&dev));
+    if (dev != ws_device || (size_t)len > ws_len) {
+        if (ws) cudaFree(ws);
+        ws = nullptr; ws_len = 0; ws_device = dev;
+        MMC_CUDA(cudaMalloc((void **)&ws, sizeof(double) * len));
+        ws_len = (size_t)len;
+    }
+    double *d_partial = ws;
+    const bool dbg = getenv("MMC_STATS_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tA = now();
     std::vector<double> h_partial((size_t)len, 0.0);
     int64_t have = 0, block = kLagBlock;
     int result = MMC_OK;
     while (have < N) {
         const int64_t want = std::min<int64_t>(block, N - have);
+        tA = now();
         rc = mmc_stats_partial_dev(sample_dev, c, n, p, have, want, d_partial, stream);
         if (rc) { result = rc; break; }
+        if (dbg) fprintf(stderr, "[stats] launch lags %lld+%lld %.3f ms\n", (long long)have, (long long)want, now() - tA);
+        tA = now();
         const size_t off = have == 0 ? 0 : (size_t)(2 + have) * p;
         const size_t cnt = (have == 0 ? 2 * p : 0) + (size_t)want * p;
         cudaError_t e = cudaMemcpyAsync(h_partial.data() + off, d_partial + off, cnt * sizeof(double),
                                         cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { result = cuda_fail(e, "stats D2H", __FILE__, __LINE__); break; }
+        if (dbg) fprintf(stderr, "[stats] sync+d2h %.3f ms\n", now() - tA);
         have += want;
         const int more = mmc_stats_finalize(h_partial.data(), c, n, p, have, rhat_host, ess_host);
         if (more < 0) { result = more; break; }
         if (more == 0) break;
         block *= 2;  // geometric growth keeps the number of host round trips logarithmic
     }
-    cudaFree(d_partial);
     return result;
 }
 

@@ -60,6 +60,43 @@ def stats(c=65536, n=400, p=100):
     print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
 
 
+def tracker():
+    """one streaming pass of the progress tracker over a block of draws (HBM read bound)"""
+    for name, shape, dt, flavor in (("c2_poisson", (1 << 20, 512, 1), torch.int64, 1), ("c3_hmc", (262144, 400, 3), torch.float32, 0),
+                                    ("c5_nuts", (65536, 400, 100), torch.float32, 1), ("c4_dense", (32768, 16, 1024), torch.float32, 0)):
+        c, n, p = shape
+        x = (torch.randn(shape, device="cuda") * 3).to(dt)
+        t = mm.progress.DeviceTracker(c, p, flavor)
+        ms, ts = ev_time(lambda: t.steps(x), warm=1, reps=3)
+        t0 = time.perf_counter()
+        s = t.summary()
+        sum_ms = (time.perf_counter() - t0) * 1e3
+        print(json.dumps(dict(k="tracker", cfg=name, shape=shape, ms=ms, read_GBs=x.numel() * x.element_size() / ms / 1e6,
+                              summary_ms=sum_ms, max_rhat=s["max_rhat"], p_accept=s["p_accept"])))
+        del x, t
+
+
+def run_progress_overhead():
+    """block-wise run_progress (tracker + summaries + RunStats) vs the plain single launch, C3 shape"""
+    chains, L, nc, nd = 262144, 50, 400, 50
+    init = mm.init_device(chains, 3, 42).cpu().numpy()
+    h = mm.HMC(mm.RosenbrockND(), init, 0.01, L).set_seed(1)
+    out = torch.empty((chains, nc, 3), dtype=torch.float32, device="cuda")
+    ms_plain, _ = ev_time(lambda: h.run_device(nc, nd, out=out), warm=1, reps=2)
+    del out
+    seen = []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sample, stats = h.run_progress(nc, nd, progress=lambda d, i: seen.append((d, i["max_rhat"], i["p_accept"])))
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    mm.RunStats.from_sample(sample)
+    stats_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps(dict(k="run_progress_c3", plain_kernel_ms=ms_plain, run_progress_wall_ms=wall, of_which_final_stats_ms=stats_ms,
+                          blocks=len(seen), last=seen[-1], ess_min=stats.ess.min)))
+
+
 def dense(chains=4096, D=1024, L=50, steps=4, path=0):
     rng = np.random.default_rng(42)
     A = rng.normal(size=(D, D))
@@ -128,6 +165,9 @@ if __name__ == "__main__":
             dense(chains=32768, steps=2, path=1)
         except Exception as e:
             print("tc path:", e)
+    if "tracker" in which:
+        tracker()
+        run_progress_overhead()
     if "nuts" in which:
         nuts(chains=8192)
         nuts()

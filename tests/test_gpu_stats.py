@@ -29,6 +29,9 @@ def _ar1(rng, c, n, p, phi, offset=0.0):
     (8, 400, 100, 0.3, -50.0),   # C5 row shape, large mean (shift robustness)
     (3, 51, 33, 0.9, 0.0),       # odd n (middle draw dropped), p not a multiple of 32, slow mixing
     (16, 600, 7, 0.97, 10.0),    # needs many lags
+    (37, 64, 3, 0.5, 1.0),       # small p: several split chains staged per round, ragged last round
+    (40, 400, 2, 0.95, 0.0),     # small p and many lag blocks
+    (300, 40, 1, 0.2, 0.0),      # p = 1, more rounds than CTAs would need at K = 16
 ])
 def test_split_rhat_ess_matches_oracle(mm, c, n, p, phi, offset):
     rng = np.random.default_rng(c * 1000 + n)
