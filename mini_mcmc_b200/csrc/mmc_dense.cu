@@ -259,22 +259,23 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
     const uint2 key = seed_key(a.seed);
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
     const dim3 ggrid((unsigned)(D / kBN), (unsigned)((M + kBM - 1) / kBM));
-    MMC_REQUIRE(D % kBN == 0 || a.gemm_path == 1, "FP32 GEMM path needs dim %% 128 == 0, got %d", D);
-    if (a.gemm_path == 1) {
+    MMC_REQUIRE(D % kBN == 0 || a.gemm_path >= 1, "FP32 GEMM path needs dim %% 128 == 0, got %d", D);
+    if (a.gemm_path >= 1) {
         int rc = dense_tc_prepare(st);
         if (rc) return rc;
+        st->tc_pair = a.gemm_path == 2;
     }
     for (int64_t s = 0; s < steps; ++s) {
         dense_begin_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, st->d_delta[0], st->d_mom, st->d_scal,
                                                       a.momenta, a.u, M, D, a.chain_offset, (uint32_t)(a.step_base + s), s, key);
-        if (a.gemm_path == 1) {
+        if (a.gemm_path >= 1) {
             int rc = dense_tc_split_delta(st, stream);
             if (rc) return rc;
         }
         int cur = 0;
         for (int l = 0; l <= a.n_leapfrog; ++l) {
             const int mode = l == 0 ? kModeFirst : (l == a.n_leapfrog ? kModeLast : kModeMid);
-            if (a.gemm_path == 1) {
+            if (a.gemm_path >= 1) {
                 int rc = dense_gemm_tc(st, cur, M, D, a.eps, mode, stream);
                 if (rc) return rc;
             } else {
@@ -284,8 +285,8 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
             if (mode != kModeLast) cur ^= 1;
         }
         const bool collect = s >= a.n_discard && a.out;
-        const float *fin = a.gemm_path == 1 ? st->d_delta_split[cur] : st->d_delta[cur];
-        const float *fin_lo = a.gemm_path == 1 ? st->d_delta_split[cur] + (size_t)M * D : nullptr;
+        const float *fin = a.gemm_path >= 1 ? st->d_delta_split[cur] : st->d_delta[cur];
+        const float *fin_lo = a.gemm_path >= 1 ? st->d_delta_split[cur] + (size_t)M * D : nullptr;
         dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, fin, fin_lo, st->d_scal, st->norm_const,
                                                        collect ? a.out : nullptr, a.trace, a.accept_count, M, D, a.out_pitch,
                                                        collect ? s - a.n_discard : 0, s);

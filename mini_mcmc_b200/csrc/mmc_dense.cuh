@@ -22,6 +22,7 @@ struct DenseState {
     float *d_prec_split = nullptr;                  // [2, D, D]
     float *d_delta_split[2] = {nullptr, nullptr};   // ping-pong of [2 (hi, lo), chains, D]
     void *tc = nullptr;                             // tensor maps
+    bool tc_pair = false;                           // CTA-pair (cta_group::2) kernel instead of the 1-CTA one
 };
 
 enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };

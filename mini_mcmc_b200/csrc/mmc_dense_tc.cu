@@ -25,10 +25,11 @@ namespace mmc {
 namespace tc {
 
 #ifndef MMC_TC_BK
-#define MMC_TC_BK 16
+#define MMC_TC_BK 32
 #endif
-// BLOCK_K 32 = one 128-byte swizzle row per operand row (2 stages fit), BLOCK_K 16 = 64-byte swizzle rows (4 stages):
-// the pipeline is bound by bytes in flight per SM, so more, smaller stages win (measured).
+// BLOCK_K 32 = one 128-byte swizzle row per operand row (2 stages of 96 KB; 3 of 64 KB in the CTA-pair kernel),
+// BLOCK_K 16 = 64-byte swizzle rows (4 / 6 stages).  With the 256-bit epilogue both run within 3 % of each other;
+// 32 is slightly ahead (measured).
 constexpr int BM = 128, BN = 256, BK = MMC_TC_BK, kStages = (BK == 32 ? 2 : 4), UMMA_K = 8;
 constexpr uint32_t kRowBytes = BK * 4;                     // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
 static_assert(BK == 32 || BK == 16, "BLOCK_K must be 32 or 16");
@@ -42,6 +43,7 @@ constexpr uint32_t kTmemCols = 512;          // two 256-column fp32 accumulators
 
 struct Maps {
     CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
+    CUtensorMap b_hi_half, b_lo_half;   // 128-row boxes for the CTA-pair kernel
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -315,6 +317,244 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 }
 
+// ================================================================== CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) share one 256 x 256 tile: CTA r stages its own 128 rows of A and
+// rows [128 r, 128 r + 128) of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256), each tensor core reads
+// both halves of B, and every CTA keeps its 128 x 256 accumulator in its own TMEM.  Per SM this cuts the bytes staged
+// per k-block from 48 KB to 32 KB (L2 -> SM traffic and shared-memory fill bandwidth, the limiters of the 1-CTA
+// kernel), which also leaves room for 6 instead of 4 stages.
+constexpr uint32_t kBHalfBytes = kBBytes / 2;
+constexpr uint32_t kStageBytes2 = 2 * kABytes + 2 * kBHalfBytes;
+constexpr int kStages2 = (BK == 32 ? 3 : 6);
+constexpr uint32_t kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_pair() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                          const float *__restrict__ a_hi, const float *__restrict__ a_lo, float *__restrict__ n_hi,
+                          float *__restrict__ n_lo, float *__restrict__ mom, float *__restrict__ scal, int64_t M, int D, float eps,
+                          int mode, int n_tiles, int n_nblocks) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages2 * kStageBytes2;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages2 + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages2 + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages2 + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages2 + 4);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = D / BK;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(full_bar(s), 1);    // the leader's producer arrives with the bytes of BOTH CTAs
+            mbar_init(empty_bar(s), 1);   // multicast tcgen05.commit of the leader
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 2 * kEpiWarps);   // epilogue warps of both CTAs (used in the leader only)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer (one per CTA; both signal the leader's full barrier) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int n0 = (tile % n_nblocks) * BN + (int)rank * (BN / 2);
+                const int m0 = (tile / n_nblocks) * (2 * BM) + (int)rank * BM;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kStages2;
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t st = smem_base + s * kStageBytes2;
+                    const uint32_t lbar = mapa_shared(full_bar(s), 0);
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes2);
+                    tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, m0);
+                    tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kb * BK, m0);
+                    tma_load_2d_pair(st + 2 * kABytes, &map_b_hi, lbar, kb * BK, n0);
+                    tma_load_2d_pair(st + 2 * kABytes + kBHalfBytes, &map_b_lo, lbar, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_pair();
+            uint32_t it = 0, lt = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+                const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(as), aph ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kStages2;
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_base + s * kStageBytes2;
+                    const uint64_t da_hi = make_smem_desc(st), da_lo = make_smem_desc(st + kABytes);
+                    const uint64_t db_hi = make_smem_desc(st + 2 * kABytes), db_lo = make_smem_desc(st + 2 * kABytes + kBHalfBytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                        tcgen05_mma_tf32_pair(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tcgen05_mma_tf32_pair(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                        tcgen05_mma_tf32_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                    }
+                    tcgen05_commit_pair(empty_bar(s));      // frees the stage in both CTAs
+                }
+                tcgen05_commit_pair(tmem_full_bar(as));     // accumulators of both CTAs complete
+            }
+        }
+    } else {
+        // ===== epilogue (8 warps per CTA): own 128 rows x 256 columns =====
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int row = q * 32 + lane;
+        const float eps_half = eps * 0.5f;
+        uint32_t lt = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+            const int n0 = (tile % n_nblocks) * BN;
+            const int64_t m = (int64_t)(tile / n_nblocks) * (2 * BM) + (int64_t)rank * BM + row;
+            const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+            const bool row_ok = m < M;
+            float quad = 0.f, ke = 0.f;
+            bool waited = false;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 64; ++chunk) {
+                const int col = half * (BN / 2) + chunk * 32;
+                const int64_t off = (row_ok ? m : 0) * D + n0 + col;
+                f8 h8[4], l8[4], p8[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    h8[j] = ldg256(a_hi + off + 8 * j);
+                    l8[j] = ldg256(a_lo + off + 8 * j);
+                    p8[j] = ldg256(mom + off + 8 * j);
+                }
+                if (!waited) {
+                    mbar_wait(tmem_full_bar(as), aph);
+                    tcgen05_fence_after();
+                    waited = true;
+                }
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)col, r);
+                if (chunk == BN / 64 - 1) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t lbar = mapa_shared(tmem_empty_bar(as), 0);
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
+                    }
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float pp[8], hi[8], lo[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float z = __uint_as_float(r[8 * j + e]);
+                            const float dl = h8[j].v[e] + l8[j].v[e];
+                            const float gh = -z * eps_half;
+                            float dn;
+                            if (mode != kModeMid) quad = fmaf(z, dl, quad);
+                            if (mode == kModeFirst) {
+                                pp[e] = p8[j].v[e] + gh;
+                                dn = fmaf(eps, pp[e], dl);
+                            } else if (mode == kModeMid) {
+                                pp[e] = (p8[j].v[e] + gh) + gh;
+                                dn = fmaf(eps, pp[e], dl);
+                            } else {
+                                pp[e] = p8[j].v[e] + gh;
+                                ke = fmaf(pp[e], pp[e], ke);
+                                dn = dl;
+                            }
+                            hi[e] = tf32_hi(dn);
+                            lo[e] = dn - hi[e];
+                        }
+                        stg256(mom + off + 8 * j, pp);
+                        if (mode != kModeLast) {
+                            stg256(n_hi + off + 8 * j, hi);
+                            stg256(n_lo + off + 8 * j, lo);
+                        }
+                    }
+                }
+            }
+            if (row_ok && mode != kModeMid) {
+                atomicAdd(scal + (mode == kModeFirst ? 1 : 3) * M + m, quad);
+                if (mode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer can still read its shared memory / signal it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 __global__ void split_kernel(const float *__restrict__ src, float *__restrict__ hi, float *__restrict__ lo, int64_t n4) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -369,8 +609,11 @@ int dense_tc_prepare(DenseState *st) {
     }
     if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_hi, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN);
     if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_lo, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN);
+    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_hi_half, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN / 2);
+    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_lo_half, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN / 2);
     if (rc) { delete maps; return rc; }
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     st->tc = maps;
     return MMC_OK;
 }
@@ -390,6 +633,27 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
     float *a_hi = st->d_delta_split[cur], *a_lo = a_hi + md;
     float *n_hi = st->d_delta_split[cur ^ 1], *n_lo = n_hi + md;
     const int n_nblocks = D / tc::BN;
+    if (st->tc_pair) {
+        // CTA-pair kernel: 256 x 256 tiles, clusters of two CTAs, persistent over min(tiles, SMs / 2) pairs
+        const int n_tiles2 = n_nblocks * (int)((M + 2 * tc::BM - 1) / (2 * tc::BM));
+        const int pairs = n_tiles2 < sm_count() / 2 ? n_tiles2 : sm_count() / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = tc::kSmemBytes2;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
+                                    maps->b_lo_half, (const float *)a_hi, (const float *)a_lo, n_hi, n_lo, st->d_mom, st->d_scal, M, D,
+                                    eps, mode, n_tiles2, n_nblocks));
+        return MMC_OK;
+    }
     const int n_tiles = n_nblocks * (int)((M + tc::BM - 1) / tc::BM);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     tc::dense_gemm_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(maps->a_hi[cur], maps->a_lo[cur], maps->b_hi,

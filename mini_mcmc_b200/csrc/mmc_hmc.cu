@@ -231,7 +231,7 @@ int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps) {
 }
 
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
-    MMC_REQUIRE(h && (path == 0 || path == 1), "gemm path must be 0 (FP32 SIMT) or 1 (tcgen05 3xTF32)");
+    MMC_REQUIRE(h && path >= 0 && path <= 2, "gemm path must be 0 (FP32 SIMT), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xTF32, CTA pairs)");
     h->gemm_path = path;
     return MMC_OK;
 }

@@ -131,7 +131,7 @@ def c4(args):
     tgt = mm.DenseGaussian(mean, cov)
     init = mm.init_device(chains, D, 42, chain_offset=RANK * chains).cpu().numpy()
     res = {}
-    for path, name in ((1, "tcgen05_3xTF32"), (0, "fp32_simt")):
+    for path, name in ((2, "tcgen05_3xTF32_cta_pair"), (1, "tcgen05_3xTF32_1cta"), (0, "fp32_simt")):
         h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_chain_offset(RANK * chains).set_gemm_path(path)
         out = torch.empty((chains, steps, D), dtype=torch.float32, device="cuda")
         ms = timed(lambda: h.run_device(steps, 0, out=out), warm=1, reps=2)

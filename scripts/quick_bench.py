@@ -106,7 +106,7 @@ def dense(chains=4096, D=1024, L=50, steps=4, path=0):
     init = (rng.normal(size=(chains, D))).astype(np.float32)
     h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_gemm_path(path)
     out = torch.empty((chains, steps, D), dtype=torch.float32, device="cuda")
-    ms, ts = ev_time(lambda: h.run_device(steps, 0, out=out), warm=1, reps=2)
+    ms, ts = ev_time(lambda: h.run_device(steps, 0, out=out), warm=1, reps=5)
     ge = chains * steps * (L + 1)
     acc, tot = h.accept_counts()
     print(json.dumps(dict(k="dense_hmc", path=path, chains=chains, D=D, L=L, ms=ms, all=ts, grad_evals_per_s=ge / ms * 1e3,

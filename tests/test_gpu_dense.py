@@ -27,10 +27,10 @@ def tc_supported(D):
     return D % 256 == 0   # tcgen05 tile is 128 x 256
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [0, 1, 2])
 @pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
-    if path == 1 and not tc_supported(D):
+    if path >= 1 and not tc_supported(D):
         pytest.skip("tcgen05 path needs dim % 256 == 0")
     mean, cov = make_problem(D)
     tgt = mm.DenseGaussian(mean, cov)
@@ -57,7 +57,7 @@ def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
 
 
 def test_tensor_core_path_matches_fp32_path(mm):
-    """Same replayed transition through both GEMM paths (3xTF32 on tcgen05 vs FP32 SIMT): ragged chain count."""
+    """Same replayed transition through all GEMM paths (3xTF32 on tcgen05, 1-CTA and CTA-pair, vs FP32 SIMT): ragged chain count."""
     D, chains, L = 512, 333, 6
     mean, cov = make_problem(D, seed=9)
     tgt = mm.DenseGaussian(mean, cov)
@@ -66,18 +66,21 @@ def test_tensor_core_path_matches_fp32_path(mm):
     mom = rng.normal(size=(3, chains, D)).astype(np.float32)
     u = rng.random((3, chains)).astype(np.float32)
     outs = []
-    for path in (0, 1):
+    for path in (0, 1, 2):
         h = mm.HMC(tgt, init, 0.05, L).set_gemm_path(path)
         tr = np.zeros((3, chains, 4), dtype=np.float32)
         outs.append((h.run(3, 0, replay=dict(momenta=mom, u=u), trace=tr), tr))
-    (a, ta), (b, tb) = outs
-    assert (ta[..., 3] == tb[..., 3]).mean() > 0.995
-    same = (ta[..., 3] == tb[..., 3]).all(axis=0)
-    np.testing.assert_allclose(a[same], b[same], rtol=1e-5, atol=2e-5)
-    np.testing.assert_allclose(ta[..., :2], tb[..., :2], rtol=1e-5, atol=1e-3)
+    a, ta = outs[0]
+    for b, tb in outs[1:]:
+        assert (ta[..., 3] == tb[..., 3]).mean() > 0.995
+        same = (ta[..., 3] == tb[..., 3]).all(axis=0)
+        np.testing.assert_allclose(a[same], b[same], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(ta[..., :2], tb[..., :2], rtol=1e-5, atol=1e-3)
+    # the 1-CTA and the CTA-pair kernels issue the same MMAs in the same order: identical results
+    np.testing.assert_array_equal(outs[1][0], outs[2][0])
 
 
-@pytest.mark.parametrize("path,D", [(0, 128), (1, 256)])
+@pytest.mark.parametrize("path,D", [(0, 128), (1, 256), (2, 256)])
 def test_dense_hmc_native_tape_and_moments(mm, path, D):
     chains, L = 512, 8
     mean, cov = make_problem(D, seed=3)
