@@ -278,6 +278,18 @@ int mmc_tracker_summary(mmc_tracker *t, float *rhat_host, float *max_rhat, float
 int mmc_tracker_get(mmc_tracker *t, float *mean_host, float *mean_sq_host, float *p_accept_host);
 void mmc_tracker_destroy(mmc_tracker *t);
 
+/* ------------------------------------------------------------------ sample sinks
+ * Replaces the data movement of save_arrow / save_parquet / save_parquet_tensor (src/io/arrow.rs:53-117,
+ * src/io/parquet.rs:49-221) and all of save_csv / save_csv_tensor (src/io/csv.rs:47-147).
+ * mmc_sink_columns_dev turns chains [c0, c0 + c_count) of a device sample [chains, n, dim] (mmc_dtype) into the f64
+ * columns the Arrow schema holds: dim_cols_dev[d * rows + r] = (double) sample[c0 + r / n][r % n][d], rows = c_count * n.
+ * The host wraps the copied columns as Arrow buffers (the file encoders stay library code, like the arrow / parquet
+ * crates in the reference).  mmc_save_csv writes the whole file natively: header `chain,observation,dim_0..`, records
+ * in chain-major order, numbers printed like Rust's Display (shortest round-trip digits, no exponent). */
+int mmc_sink_columns_dev(const void *sample_dev, int32_t dtype, int64_t chains, int64_t n, int32_t dim, int64_t c0,
+                         int64_t c_count, double *dim_cols_dev, void *stream);
+int mmc_save_csv(const void *sample_host, int32_t dtype, int64_t chains, int64_t n, int32_t dim, const char *filename);
+
 #ifdef __cplusplus
 }
 #endif

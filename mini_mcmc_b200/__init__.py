@@ -5,6 +5,7 @@ split_rhat_mean_ess) over the C ABI in include/minimcmc.h.  All arithmetic runs 
 kernels inside libminimcmc.so; there is no CPU fallback.
 """
 from . import _lib
+from . import io
 from .core import init, init_det, init_device, init_with_seed
 from .distributions import (CustomTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, IsotropicGaussian, NonnegativeProposal,
                             PoissonTarget, Rosenbrock2D, RosenbrockND, StandardNormalTarget)

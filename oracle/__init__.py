@@ -478,3 +478,49 @@ def collect_rhat(chain_stats):
     n = np.float32(sum(np.float32(s["n"]) for s in chain_stats)) / np.float32(len(chain_stats))
     var = between + within * ((n - np.float32(1.0)) / n)
     return np.sqrt(var / within)
+
+
+# ------------------------------------------------------------------ sample sinks (src/io/*.rs), restated with plain loops
+def _rust_display(v, as_f32=False):
+    """What Rust's `Display` prints for a number: integers as digits; floats as the shortest decimal string that
+    round-trips in the value's own type, never in exponent notation; NaN / inf / -inf."""
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    x = np.float32(v) if as_f32 else np.float64(v)
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "-inf" if x < 0 else "inf"
+    return np.format_float_positional(x, unique=True, trim="-")
+
+
+def csv_text(data, as_f32=False):
+    """save_csv / save_csv_tensor, src/io/csv.rs:47-77,110-147."""
+    a = np.asarray(data)
+    n_dims = a.shape[2]
+    lines = [",".join(["chain", "observation"] + [f"dim_{i}" for i in range(n_dims)])]
+    for c in range(a.shape[0]):
+        for t in range(a.shape[1]):
+            vals = [(_rust_display(v, as_f32) if a.dtype.kind == "f" else str(int(v))) for v in a[c, t]]
+            lines.append(",".join([str(c), str(t)] + vals))
+    return "\n".join(lines) + "\n"
+
+
+def long_table(data, tensor_layout=False):
+    """Columns of save_arrow / save_parquet (src/io/arrow.rs:53-117) or, with tensor_layout, save_parquet_tensor
+    (src/io/parquet.rs:154-221: data is [observations, chains, dims], columns observation, chain, dim_*)."""
+    a = np.asarray(data)
+    names = ("observation", "chain") if tensor_layout else ("chain", "observation")
+    cols = {names[0]: [], names[1]: []}
+    for i in range(a.shape[2]):
+        cols[f"dim_{i}"] = []
+    for o in range(a.shape[0]):
+        for i in range(a.shape[1]):
+            cols[names[0]].append(o)
+            cols[names[1]].append(i)
+            for d in range(a.shape[2]):
+                cols[f"dim_{d}"].append(float(a[o, i, d]))
+    out = {names[0]: np.array(cols[names[0]], dtype=np.uint32), names[1]: np.array(cols[names[1]], dtype=np.uint32)}
+    for d in range(a.shape[2]):
+        out[f"dim_{d}"] = np.array(cols[f"dim_{d}"], dtype=np.float64)
+    return out

@@ -76,6 +76,37 @@ def tracker():
         del x, t
 
 
+def sinks():
+    """device widening transpose (kernel alone) and the streamed Arrow IPC sink end to end, C3-shaped sample"""
+    import ctypes as C
+    import tempfile
+    from mini_mcmc_b200 import _lib as L
+    c, n, d = 262144, 100, 3
+    x = torch.randn((c, n, d), device="cuda")
+    cols = torch.empty(d * c * n, dtype=torch.float64, device="cuda")
+    ms, _ = ev_time(lambda: L.check(L.lib.mmc_sink_columns_dev(L.vp(x), C.c_int32(0), C.c_int64(c), C.c_int64(n), C.c_int32(d), C.c_int64(0),
+                                                               C.c_int64(c), L.vp(cols), L.current_stream_ptr())))
+    print(json.dumps(dict(k="sink_columns_kernel", shape=(c, n, d), ms=ms, GBs=x.numel() * 12 / ms / 1e6)))
+    y = torch.randn((8192, 400, 100), device="cuda")
+    cols = torch.empty(y.numel(), dtype=torch.float64, device="cuda")
+    ms, _ = ev_time(lambda: L.check(L.lib.mmc_sink_columns_dev(L.vp(y), C.c_int32(0), C.c_int64(8192), C.c_int64(400), C.c_int32(100), C.c_int64(0),
+                                                               C.c_int64(8192), L.vp(cols), L.current_stream_ptr())))
+    print(json.dumps(dict(k="sink_columns_kernel", shape=(8192, 400, 100), ms=ms, GBs=y.numel() * 12 / ms / 1e6)))
+    del cols, y
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, fn in (("arrow", mm.io.save_arrow), ("parquet", mm.io.save_parquet)):
+            t0 = time.perf_counter()
+            fn(x, os.path.join(tmp, "s." + name))
+            dt = time.perf_counter() - t0
+            size = os.path.getsize(os.path.join(tmp, "s." + name))
+            print(json.dumps(dict(k="sink_" + name, rows=c * n, s=dt, rows_per_s=c * n / dt, file_GB=size / 1e9)))
+        host = x[:16384].cpu().numpy()
+        t0 = time.perf_counter()
+        mm.io.save_csv_tensor(host, os.path.join(tmp, "s.csv"))
+        dt = time.perf_counter() - t0
+        print(json.dumps(dict(k="sink_csv", rows=16384 * n, s=dt, rows_per_s=16384 * n / dt, file_GB=os.path.getsize(os.path.join(tmp, "s.csv")) / 1e9)))
+
+
 def run_progress_overhead():
     """block-wise run_progress (tracker + summaries + RunStats) vs the plain single launch, C3 shape"""
     chains, L, nc, nd = 262144, 50, 400, 50
@@ -165,6 +196,8 @@ if __name__ == "__main__":
             dense(chains=32768, steps=2, path=1)
         except Exception as e:
             print("tc path:", e)
+    if "sinks" in which:
+        sinks()
     if "tracker" in which:
         tracker()
         run_progress_overhead()
