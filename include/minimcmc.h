@@ -278,6 +278,30 @@ int mmc_tracker_summary(mmc_tracker *t, float *rhat_host, float *max_rhat, float
 int mmc_tracker_get(mmc_tracker *t, float *mean_host, float *mean_sq_host, float *p_accept_host);
 void mmc_tracker_destroy(mmc_tracker *t);
 
+/* ------------------------------------------------------------------ Gibbs
+ * Replaces GibbsSampler::new / set_seed / run(_progress) and GibbsMarkovChain::step (src/gibbs.rs:89-205): each step
+ * sweeps the coordinates in order, state[i] = conditional.sample(i, state).  `Conditional` is user code in the
+ * reference (src/distributions.rs:485-487); the built-ins are the ones its tests and examples define:
+ * MMC_G_CONSTANT (src/gibbs.rs:218-226, params = c) and MMC_G_MIXTURE2, the two-component Gaussian mixture with state
+ * [x, z] (src/gibbs.rs:228-275, examples/mixture_gibbs.rs:24-72; params = mu0, sigma0, mu1, sigma1, pi0).
+ * Native RNG: Philox counter (global chain, step, sub = coordinate): sub 0 -> Box-Muller z-score for x, sub 1 words
+ * (0,1) -> 53-bit uniform for z.  Replay tapes feed the reference's own draws: normals / unifs [chains, steps];
+ * trace [chains, steps, 2] receives the (z-score, uniform) every sweep consumed. */
+typedef struct mmc_gibbs mmc_gibbs;
+#define MMC_G_CONSTANT 1
+#define MMC_G_MIXTURE2 2
+typedef struct { int32_t kind; int32_t reserved; double params[8]; } mmc_conditional_desc;
+typedef struct { const double *normals; const double *unifs; double *trace; } mmc_replay_gibbs;
+int mmc_gibbs_create(mmc_gibbs **out, const mmc_conditional_desc *cond, const double *init_host, int64_t chains, int32_t dim);
+int mmc_gibbs_set_seed(mmc_gibbs *h, uint64_t seed);
+int mmc_gibbs_set_chain_offset(mmc_gibbs *h, int64_t offset);
+int mmc_gibbs_set_out_pitch(mmc_gibbs *h, int64_t pitch_steps); /* see mmc_mh_set_out_pitch */
+int mmc_gibbs_run(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_host, const mmc_replay_gibbs *replay);
+int mmc_gibbs_run_dev(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_dev, const mmc_replay_gibbs *replay_dev,
+                      void *stream);
+int mmc_gibbs_get_state(mmc_gibbs *h, double *state_host);
+void mmc_gibbs_destroy(mmc_gibbs *h);
+
 /* ------------------------------------------------------------------ sample sinks
  * Replaces the data movement of save_arrow / save_parquet / save_parquet_tensor (src/io/arrow.rs:53-117,
  * src/io/parquet.rs:49-221) and all of save_csv / save_csv_tensor (src/io/csv.rs:47-147).

@@ -15,6 +15,7 @@ MMC_F32, MMC_F64, MMC_U64 = 0, 1, 2
 (T_GAUSSIAN2D, T_ISO_GAUSSIAN, T_POISSON, T_ROSENBROCK_ND, T_ROSENBROCK_2D, T_DIFF_GAUSSIAN2D, T_DENSE_GAUSSIAN,
  T_STD_NORMAL) = range(1, 9)
 Q_ISO_GAUSSIAN, Q_NONNEG_RW = 1, 2
+G_CONSTANT, G_MIXTURE2 = 1, 2
 
 ERR_NAMES = {0: "MMC_OK", -1: "MMC_ERR_INVALID", -2: "MMC_ERR_NO_DEVICE", -3: "MMC_ERR_CUDA",
              -4: "MMC_ERR_UNSUPPORTED", -5: "MMC_ERR_OVERFLOW", -6: "MMC_ERR_NOMEM"}
@@ -46,6 +47,14 @@ class ReplayHMC(C.Structure):
 class ReplayNUTS(C.Structure):
     _fields_ = [("normals", C.c_void_p), ("cap_normals", C.c_int64), ("exps", C.c_void_p), ("cap_exps", C.c_int64),
                 ("unifs", C.c_void_p), ("cap_unifs", C.c_int64)]
+
+
+class ConditionalDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 8)]
+
+
+class ReplayGibbs(C.Structure):
+    _fields_ = [("normals", C.c_void_p), ("unifs", C.c_void_p), ("trace", C.c_void_p)]
 
 
 class BasicStats(C.Structure):

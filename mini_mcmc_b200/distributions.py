@@ -189,3 +189,31 @@ class CustomTarget(_Target):
 
     def _params(self):
         return self._p
+
+
+class ConstantConditional:
+    """ConstantConditional { c }, src/gibbs.rs:218-226: every coordinate is set to c."""
+
+    def __init__(self, c: float):
+        self.c = float(c)
+
+    def cond_desc(self):
+        d = L.ConditionalDesc()
+        d.kind = L.G_CONSTANT
+        d.params[0] = self.c
+        return d
+
+
+class MixtureConditional:
+    """Two-component Gaussian mixture over the state [x, z] (src/gibbs.rs:228-275, examples/mixture_gibbs.rs:13-72):
+    x | z ~ N(mu_z, sigma_z^2), P(z = 1 | x) = (1 - pi0) pdf1(x) / (pi0 pdf0(x) + (1 - pi0) pdf1(x))."""
+
+    def __init__(self, mu0: float, sigma0: float, mu1: float, sigma1: float, pi0: float):
+        self.mu0, self.sigma0, self.mu1, self.sigma1, self.pi0 = map(float, (mu0, sigma0, mu1, sigma1, pi0))
+
+    def cond_desc(self):
+        d = L.ConditionalDesc()
+        d.kind = L.G_MIXTURE2
+        for i, v in enumerate((self.mu0, self.sigma0, self.mu1, self.sigma1, self.pi0)):
+            d.params[i] = v
+        return d

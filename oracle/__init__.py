@@ -524,3 +524,30 @@ def long_table(data, tensor_layout=False):
     for d in range(a.shape[2]):
         out[f"dim_{d}"] = np.array(cols[f"dim_{d}"], dtype=np.float64)
     return out
+
+
+# ------------------------------------------------------------------ Gibbs (src/gibbs.rs)
+G_CONSTANT, G_MIXTURE2 = 1, 2
+
+
+def gibbs_run(kind, params, init, n_collect, n_discard, cond_seed=None, tapes=None, record=False):
+    """GibbsSampler::run (src/gibbs.rs:89-205 through ChainRunner::run).  cond_seed: the conditional's own SmallRng
+    seed (cloned into every chain, as the reference does); tapes = (normals, unifs) [chains, steps] replays draws.
+    Returns dict(out [chains, n_collect, D], state, tapes)."""
+    state = _f64(init).copy()
+    chains, D = state.shape
+    steps = n_collect + n_discard
+    params = _f64(list(params) + [0.0] * (8 - len(params)))
+    out = np.empty((chains, n_collect, D), dtype=np.float64)
+    reference = tapes is None
+    if reference:
+        normals = np.zeros((chains, steps), dtype=np.float64) if record else None
+        unifs = np.zeros((chains, steps), dtype=np.float64) if record else None
+    else:
+        normals, unifs = _f64(tapes[0]), _f64(tapes[1])
+        assert normals.shape == (chains, steps) and unifs.shape == (chains, steps)
+    rc = lib().orc_gibbs_run(kind, _p(params, C.c_double), _p(state, C.c_double), C.c_int64(chains), D, C.c_int64(n_collect),
+                             C.c_int64(n_discard), int(reference), C.c_uint64(cond_seed or 0), _p(normals, C.c_double),
+                             _p(unifs, C.c_double), _p(out, C.c_double))
+    assert rc == 0
+    return dict(out=out, state=state, tapes=(normals, unifs))

@@ -682,3 +682,63 @@ ORC_API void orc_basic_stats(const float *data, int64_t n, float *out5) {
     out5[4] = sqrtf(s2 / ((float)n - 1.0f));
     free(d);
 }
+
+/* ------------------------------------------------------------------ Gibbs sampler (src/gibbs.rs:89-205)
+ * GibbsMarkovChain::step sweeps the coordinates in order, state[i] = target.sample(i, &state) (:122-126).  The
+ * conditional is the two-component Gaussian mixture of the reference's tests / examples/mixture_gibbs.rs:24-72
+ * (state = [x, z]) or ConstantConditional (src/gibbs.rs:218-226).  In the reference every chain holds a CLONE of the
+ * conditional including its SmallRng (GibbsSampler::new :165-176), so all chains consume the same noise stream;
+ * `reference` mode reproduces that (one SmallRng(cond_seed) per chain) and can record the draws as tapes
+ * normals[chains, steps] (z-scores) / unifs[chains, steps]; replay mode consumes such tapes. */
+static inline double orc_mix_pdf(double x, double mu, double sigma) {
+    const double var = sigma * sigma;
+    const double coeff = 1.0 / sqrt(2.0 * 3.14159265358979323846 * var);
+    const double d = x - mu;
+    const double exp_val = exp(-(d * d) / (2.0 * var));
+    return coeff * exp_val;
+}
+
+/* kind 1 = constant (p[0] = c), kind 2 = mixture (p = mu0, sigma0, mu1, sigma1, pi0) */
+ORC_API int orc_gibbs_run(int kind, const double *p, double *state, int64_t chains, int D, int64_t n_collect, int64_t n_discard,
+                          int reference, uint64_t cond_seed, double *normals, double *unifs, double *out) {
+    const int64_t steps = n_collect + n_discard;
+    if (kind == 2 && D != 2) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_smallrng rng;
+        orc_smallrng_seed(&rng, cond_seed);
+        double *x = state + c * D;
+        for (int64_t s = 0; s < steps; ++s) {
+            if (kind == 1) {
+                for (int i = 0; i < D; ++i) x[i] = p[0];
+            } else {
+                double z01, u;
+                if (reference) {
+                    z01 = orc_next_normal(&rng);
+                    if (normals) normals[c * steps + s] = z01;
+                } else {
+                    z01 = normals[c * steps + s];
+                }
+                /* i = 0: x | z ~ Normal(mu_z, sigma_z) = mean + std * zscore (rand_distr 0.5 Normal::sample) */
+                x[0] = (x[1] < 0.5) ? p[0] + p[1] * z01 : p[2] + p[3] * z01;
+                if (reference) {
+                    u = orc_next_f64(&rng);
+                    if (unifs) unifs[c * steps + s] = u;
+                } else {
+                    u = unifs[c * steps + s];
+                }
+                /* i = 1: z | x */
+                const double p0 = p[4] * orc_mix_pdf(x[0], p[0], p[1]);
+                const double p1 = (1.0 - p[4]) * orc_mix_pdf(x[0], p[2], p[3]);
+                const double total = p0 + p1;
+                const double prob_z1 = total > 0.0 ? p1 / total : 0.5;
+                x[1] = (u < prob_z1) ? 1.0 : 0.0;
+            }
+            if (s >= n_discard && out) {
+                double *o = out + (c * n_collect + (s - n_discard)) * D;
+                for (int i = 0; i < D; ++i) o[i] = x[i];
+            }
+        }
+    }
+    return 0;
+}

@@ -76,6 +76,15 @@ def tracker():
         del x, t
 
 
+def gibbs(chains=1 << 20, n_collect=1000, n_discard=100):
+    s = mm.GibbsSampler(mm.MixtureConditional(-2.0, 1.0, 3.0, 1.5, 0.25), np.zeros((chains, 2))).set_seed(1)
+    out = torch.empty((chains, n_collect, 2), dtype=torch.float64, device="cuda")
+    ms, ts = ev_time(lambda: s.run_device(n_collect, n_discard, out=out), warm=1, reps=3)
+    sweeps = chains * (n_collect + n_discard)
+    print(json.dumps(dict(k="gibbs_mixture", chains=chains, n_collect=n_collect, ms=ms, sweeps_per_s=sweeps / ms * 1e3,
+                          write_GBs=chains * n_collect * 16 / ms / 1e6)))
+
+
 def sinks():
     """device widening transpose (kernel alone) and the streamed Arrow IPC sink end to end, C3-shaped sample"""
     import ctypes as C
@@ -196,6 +205,8 @@ if __name__ == "__main__":
             dense(chains=32768, steps=2, path=1)
         except Exception as e:
             print("tc path:", e)
+    if "gibbs" in which:
+        gibbs()
     if "sinks" in which:
         sinks()
     if "tracker" in which:

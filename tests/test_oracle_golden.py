@@ -232,3 +232,26 @@ def test_poisson_kernels_agree():
         if r > (math.log(u[0, i]) if u[0, i] > 0 else -math.inf):
             x = y
         assert out[0, i, 0] == x
+
+
+# ---------------------------------------------------------------- Gibbs (src/gibbs.rs tests)
+@pytest.mark.parametrize("params", [(-2.0, 1.0, 3.0, 1.5, 0.5), (-42.0, 69.0, 1.0, 2.0, 0.123)])
+def test_gibbs_mixture_statistical_pins(params):
+    # assert_mixture_simulation(…, 4 chains, 100_000 + 10_000, seed 42), src/gibbs.rs:327-410
+    mu0, s0, mu1, s1, pi0 = params
+    init = oracle.init_det(4, 2) if hasattr(oracle, "init_det") else np.zeros((4, 2))
+    r = oracle.gibbs_run(oracle.G_MIXTURE2, params, init, 100_000, 10_000, cond_seed=42)
+    x = r["out"][:, :, 0].ravel()
+    theo_mean = pi0 * mu0 + (1 - pi0) * mu1
+    theo_var = pi0 * (s0 ** 2 + (mu0 - theo_mean) ** 2) + (1 - pi0) * (s1 ** 2 + (mu1 - theo_mean) ** 2)
+    assert abs(x.mean() - theo_mean) < abs(theo_mean) / 10.0
+    assert abs(x.var(ddof=1) - theo_var) < abs(theo_var) / 10.0
+
+
+def test_gibbs_constant_and_replay_roundtrip():
+    r = oracle.gibbs_run(oracle.G_CONSTANT, [42.0], np.zeros((4, 2)), 10, 5)   # src/gibbs.rs:291-305
+    np.testing.assert_array_equal(r["out"], np.full((4, 10, 2), 42.0))
+    init = np.array([[0.3, 0.0], [-1.0, 1.0]])
+    rec = oracle.gibbs_run(oracle.G_MIXTURE2, (-2.0, 1.0, 3.0, 1.5, 0.25), init, 50, 10, cond_seed=7, record=True)
+    rep = oracle.gibbs_run(oracle.G_MIXTURE2, (-2.0, 1.0, 3.0, 1.5, 0.25), init, 50, 10, tapes=rec["tapes"])
+    np.testing.assert_array_equal(rec["out"], rep["out"])
