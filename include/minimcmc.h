@@ -73,6 +73,7 @@ typedef enum {
     MMC_T_DIFF_GAUSSIAN2D = 6, /* DiffableGaussian2D   src/distributions.rs:213-316  params = mean0,mean1,c00,c01,c10,c11 */
     MMC_T_DENSE_GAUSSIAN = 7,  /* D-dim dense Gaussian (config C4)  params = norm_const; vec = mean[D]; mat = precision[D,D] */
     MMC_T_STD_NORMAL = 8,      /* test target          src/nuts.rs:1024-1037                                               */
+    MMC_T_CATEGORICAL = 9,     /* Categorical          src/distributions.rs:422-477  (mmc_mh_create_categorical)            */
     MMC_T_CUSTOM_BASE = 1000
 } mmc_target_kind;
 
@@ -127,6 +128,10 @@ typedef struct {
 
 int mmc_mh_create(mmc_mh **h, const mmc_target_desc *target, const mmc_proposal_desc *proposal,
                   const void *init_host, int64_t chains, int32_t dim, int32_t state_dtype);
+/* MetropolisHastings over Categorical<f64> (src/distributions.rs:422-477, Target<usize, T>: logp(k) = ln(probs[k] / sum)
+ * for k < n, -inf beyond) with the +-1 NonnegativeProposal of examples/poisson_mh.rs:28-77; u64 state [chains], dim 1.
+ * Runs through the same table-driven integer kernel as the Poisson target (threshold accept mode). */
+int mmc_mh_create_categorical(mmc_mh **out, const double *probs, int32_t n_categories, const void *init_host, int64_t chains);
 int mmc_mh_seed(mmc_mh *h, uint64_t seed);                  /* .seed(s): also resets the step counter */
 int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset);     /* first global chain id held by this handle */
 /* Poisson accept test: 0 = evaluate (lp'+qb)-(lp+qf) > ln(u) in f64 on the device,

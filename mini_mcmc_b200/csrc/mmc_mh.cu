@@ -52,6 +52,9 @@ namespace {
 
 size_t elem_size(int32_t dtype) { return 8; }
 
+// integer-state targets driven by the threshold tables: Poisson and Categorical
+bool is_int_target(const mmc_mh *h) { return h->target.kind == MMC_T_POISSON || h->target.kind == MMC_T_CATEGORICAL; }
+
 int grow(void **ptr, size_t *cap, size_t need) {
     if (*cap >= need) return MMC_OK;
     if (*ptr) MMC_CUDA(cudaFree(*ptr));
@@ -78,6 +81,8 @@ uint64_t accept_threshold(double r) {
     return hi;
 }
 
+int upload_int_tables(mmc_mh *h, const std::vector<double> &lp, const std::vector<double> &lnfact);
+
 int build_poisson_tables(mmc_mh *h) {
     const double lambda = h->target.params[0];
     MMC_REQUIRE(lambda > 0.0, "Poisson target needs lambda > 0");
@@ -87,7 +92,6 @@ int build_poisson_tables(mmc_mh *h) {
     if (len > 4096) len = 4096;
     h->table_len = (int32_t)len;
     h->ln_lambda = std::log(lambda);
-    h->ln_half = std::log(0.5);
     std::vector<double> lnfact(len), lp(len);
     // ln_factorial, examples/poisson_mh.rs:79-89: 0 for k < 2, else sum_{i=1..k} ln(i) in that order.
     double acc = 0.0;
@@ -96,6 +100,27 @@ int build_poisson_tables(mmc_mh *h) {
         lnfact[k] = k < 2 ? 0.0 : acc;
         lp[k] = -lambda + (double)k * h->ln_lambda - lnfact[k];
     }
+    return upload_int_tables(h, lp, lnfact);
+}
+
+// Categorical::new / logp, src/distributions.rs:431-468: probs normalised by their left-fold sum, logp = ln(p_k) for
+// k < K and -inf beyond.  The table carries 16 unreachable states past K (the kernel's overflow check is conservative
+// by 7 inside an octet).
+int build_categorical_tables(mmc_mh *h, const double *probs, int32_t n) {
+    double sum = 0.0;
+    for (int32_t k = 0; k < n; ++k) sum = sum + probs[k];
+    const int64_t len = (int64_t)n + 16;
+    h->table_len = (int32_t)len;
+    std::vector<double> lnfact(len, 0.0), lp(len, -INFINITY);
+    for (int32_t k = 0; k < n; ++k) lp[k] = std::log(probs[k] / sum);
+    return upload_int_tables(h, lp, lnfact);
+}
+
+// Host-built accept thresholds of the +-1 nonnegative random walk (examples/poisson_mh.rs:28-77) for any integer
+// target given as a table of log-probabilities.
+int upload_int_tables(mmc_mh *h, const std::vector<double> &lp, const std::vector<double> &lnfact) {
+    const int64_t len = (int64_t)lp.size();
+    h->ln_half = std::log(0.5);
     // table entry [k][dir] = (thr >> 38, thr & (2^38 - 1)):  u53 < thr  <=>  u15 < thr_hi || (u15 == thr_hi && u38 < thr_lo)
     std::vector<uint4> lim(2 * len, make_uint4(0u, 0u, 0u, 0u));
     auto encode = [](uint64_t thr) {
@@ -257,6 +282,7 @@ int mmc_mh_create(mmc_mh **out, const mmc_target_desc *target, const mmc_proposa
     if (rc) return rc;
     MMC_REQUIRE(out && target && proposal && init_host && chains > 0 && dim > 0, "mmc_mh_create: bad arguments");
     const bool poisson = target->kind == MMC_T_POISSON;
+    MMC_REQUIRE(target->kind != MMC_T_CATEGORICAL, "use mmc_mh_create_categorical for the Categorical target");
     if (poisson) {
         MMC_REQUIRE(proposal->kind == MMC_Q_NONNEG_RW && state_dtype == MMC_U64 && dim == 1,
                     "Poisson target needs the nonnegative random-walk proposal, u64 state and dim 1");
@@ -290,6 +316,34 @@ int mmc_mh_create(mmc_mh **out, const mmc_target_desc *target, const mmc_proposa
     return MMC_OK;
 }
 
+int mmc_mh_create_categorical(mmc_mh **out, const double *probs, int32_t n_categories, const void *init_host, int64_t chains) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(out && probs && init_host && chains > 0 && n_categories > 0 && n_categories <= 4000,
+                "mmc_mh_create_categorical: bad arguments (1..4000 categories)");
+    const uint64_t *init = static_cast<const uint64_t *>(init_host);
+    for (int64_t c = 0; c < chains; ++c)
+        MMC_REQUIRE(init[c] < (uint64_t)n_categories, "chain %lld starts at category %llu >= %d", (long long)c,
+                    (unsigned long long)init[c], n_categories);
+    mmc_mh *h = new mmc_mh();
+    h->target.kind = MMC_T_CATEGORICAL;
+    h->target.dim = 1;
+    h->proposal.kind = MMC_Q_NONNEG_RW;
+    h->chains = chains;
+    h->dim = 1;
+    h->dtype = MMC_U64;
+    auto fail = [&](int code) { mmc_mh_destroy(h); return code; };
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    e = cudaMalloc(&h->d_state, (size_t)chains * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_state, init_host, (size_t)chains * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "mmc_mh_create_categorical", __FILE__, __LINE__));
+    rc = build_categorical_tables(h, probs, n_categories);
+    if (rc) return fail(rc);
+    *out = h;
+    return MMC_OK;
+}
+
 int mmc_mh_seed(mmc_mh *h, uint64_t seed) {
     MMC_REQUIRE(h, "null handle");
     h->seed = seed;
@@ -311,6 +365,7 @@ int mmc_mh_set_out_pitch(mmc_mh *h, int64_t pitch_steps) {
 
 int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode) {
     MMC_REQUIRE(h && (mode == 0 || mode == 1), "accept mode must be 0 or 1");
+    MMC_REQUIRE(mode == 1 || h->target.kind != MMC_T_CATEGORICAL, "the Categorical target only has the threshold accept mode");
     h->accept_mode = mode;
     return MMC_OK;
 }
@@ -321,7 +376,7 @@ int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_de
     MMC_REQUIRE(out_dev || n_collect == 0, "mmc_mh_run_dev: out is null");
     MMC_REQUIRE(h->out_pitch == 0 || h->out_pitch >= n_collect, "mmc_mh_run_dev: out pitch %lld < n_collect", (long long)h->out_pitch);
     int rc;
-    if (h->target.kind == MMC_T_POISSON)
+    if (is_int_target(h))
         rc = run_poisson(h, n_collect, n_discard, (uint64_t *)out_dev, replay_dev, (cudaStream_t)stream);
     else
         rc = run_cont(h, n_collect, n_discard, (double *)out_dev, replay_dev, (cudaStream_t)stream);
@@ -382,7 +437,7 @@ static int mh_run_poisson_compact(mmc_mh *h, int64_t n_collect, int64_t n_discar
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
     MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run: an output pitch only applies to mmc_mh_run_dev");
-    if (h->target.kind == MMC_T_POISSON && !replay && h->accept_mode == 1 && n_collect > 0 && !getenv("MMC_NO_COMPACT"))
+    if (is_int_target(h) && !replay && h->accept_mode == 1 && n_collect > 0 && !getenv("MMC_NO_COMPACT"))
         return mh_run_poisson_compact(h, n_collect, n_discard, (uint64_t *)out_host);
     const int64_t steps = n_collect + n_discard;
     const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * 8;
@@ -391,7 +446,7 @@ int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, 
     mmc_replay_mh dev_rp{};
     const mmc_replay_mh *rp = nullptr;
     if (replay) {
-        const bool poisson = h->target.kind == MMC_T_POISSON;
+        const bool poisson = is_int_target(h);
         const size_t n_u = (size_t)h->chains * steps;
         if (poisson) {
             MMC_REQUIRE(replay->flip && replay->u, "Poisson MH replay needs flip and u");
@@ -426,7 +481,7 @@ int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, 
 
 int mmc_mh_d2h_bytes_per_draw(mmc_mh *h) {
     if (!h) return MMC_ERR_INVALID;
-    if (h->target.kind == MMC_T_POISSON && h->accept_mode == 1 && !getenv("MMC_NO_COMPACT")) return h->table_len <= 256 ? 1 : 2;
+    if (is_int_target(h) && h->accept_mode == 1 && !getenv("MMC_NO_COMPACT")) return h->table_len <= 256 ? 1 : 2;
     return 8 * h->dim;
 }
 

@@ -87,6 +87,27 @@ class PoissonTarget(_Target):
         return (self.lam,)
 
 
+class Categorical:
+    """Categorical::new(probs), src/distributions.rs:422-477: a Target<usize> with logp(k) = ln(probs[k] / sum(probs))
+    for k < len(probs) and -inf beyond; `probs` holds the normalised values like the reference's public field."""
+    dim = 1
+
+    def __init__(self, probs):
+        self.raw_probs = np.ascontiguousarray(probs, dtype=np.float64)
+        if self.raw_probs.ndim != 1 or self.raw_probs.size == 0:
+            raise ValueError("probs must be a non-empty vector")
+        total = 0.0
+        for p in self.raw_probs:     # left fold, src/distributions.rs:432
+            total = total + float(p)
+        self.probs = self.raw_probs / total
+
+    def logp(self, index: int) -> float:
+        return float(np.log(self.probs[index])) if 0 <= index < self.probs.size else float("-inf")
+
+    def unnorm_logp(self, position) -> float:
+        return self.logp(int(position[0]))
+
+
 class NonnegativeProposal:
     """NonnegativeProposal, examples/poisson_mh.rs:28-77."""
 

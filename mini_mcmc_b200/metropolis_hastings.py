@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .distributions import PoissonTarget
+from .distributions import Categorical, NonnegativeProposal, PoissonTarget
 
 
 class MetropolisHastings:
@@ -16,7 +16,8 @@ class MetropolisHastings:
 
     def __init__(self, target, proposal, initial_states):
         self.target, self.proposal = target, proposal
-        poisson = isinstance(target, PoissonTarget)
+        categorical = isinstance(target, Categorical)
+        poisson = isinstance(target, PoissonTarget) or categorical
         self._np_dtype = np.uint64 if poisson else np.float64
         init = np.ascontiguousarray(initial_states, dtype=self._np_dtype)
         if init.ndim != 2:
@@ -25,6 +26,13 @@ class MetropolisHastings:
         if getattr(target, "dim", 0) == 0:
             target.dim = self.dim
         self._h = C.c_void_p()
+        if categorical:
+            if not isinstance(proposal, NonnegativeProposal) or self.dim != 1:
+                raise ValueError("the Categorical target runs with NonnegativeProposal and a 1-d integer state")
+            probs = np.ascontiguousarray(target.raw_probs, dtype=np.float64)
+            L.check(L.lib.mmc_mh_create_categorical(C.byref(self._h), L.vp(probs), C.c_int32(probs.shape[0]), L.vp(init),
+                                                    C.c_int64(self.n_chains)))
+            return
         tdesc, qdesc = target.desc(), proposal.proposal_desc()
         L.check(L.lib.mmc_mh_create(C.byref(self._h), C.byref(tdesc), C.byref(qdesc), L.vp(init),
                                     C.c_int64(self.n_chains), C.c_int32(self.dim),

@@ -551,3 +551,28 @@ def gibbs_run(kind, params, init, n_collect, n_discard, cond_seed=None, tapes=No
                              _p(unifs, C.c_double), _p(out, C.c_double))
     assert rc == 0
     return dict(out=out, state=state, tapes=(normals, unifs))
+
+
+# ------------------------------------------------------------------ MH over Categorical (src/distributions.rs:422-477)
+def mh_categorical_run_replay(probs, state, n_collect, n_discard, flip, u):
+    probs = _f64(probs)
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy().reshape(-1)
+    chains = state.shape[0]
+    flip = np.ascontiguousarray(flip, dtype=np.uint8)
+    u = _f64(u)
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_categorical_run_replay(_p(probs, C.c_double), C.c_int64(probs.shape[0]), _p(state, C.c_uint64), C.c_int64(chains),
+                                        C.c_int64(n_collect), C.c_int64(n_discard), _p(flip, C.c_uint8), _p(u, C.c_double),
+                                        _p(out, C.c_uint64))
+    return out, state
+
+
+def mh_categorical_run_philox(probs, state, n_collect, n_discard, seed, chain_offset=0, step_base=0):
+    probs = _f64(probs)
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy().reshape(-1)
+    chains = state.shape[0]
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_categorical_run_philox(_p(probs, C.c_double), C.c_int64(probs.shape[0]), _p(state, C.c_uint64), C.c_int64(chains),
+                                        C.c_int64(chain_offset), C.c_int64(step_base), C.c_int64(n_collect), C.c_int64(n_discard),
+                                        C.c_uint64(seed), _p(out, C.c_uint64))
+    return out, state

@@ -742,3 +742,72 @@ ORC_API int orc_gibbs_run(int kind, const double *p, double *state, int64_t chai
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ MH over Categorical (src/distributions.rs:422-477)
+ * Target<usize, T>::unnorm_logp(position) = ln(probs[position[0]]) for position[0] < len, -inf beyond (:457-476), with
+ * probs normalised by their left-fold sum in Categorical::new (:431-440); proposal = NonnegativeProposal
+ * (examples/poisson_mh.rs:28-77); transition = MHMarkovChain::step (src/metropolis_hastings.rs:303-315). */
+static inline double orc_cat_logp(const double *probs, double sum, int64_t K, uint64_t k) {
+    return k < (uint64_t)K ? log(probs[k] / sum) : -INFINITY;
+}
+static inline uint64_t orc_mh_cat_step(const double *probs, double sum, int64_t K, uint64_t x, int flip, double u) {
+    uint64_t y = (x == 0) ? 1 : (flip ? x + 1 : x - 1);
+    double cur_lp = orc_cat_logp(probs, sum, K, x);
+    double prop_lp = orc_cat_logp(probs, sum, K, y);
+    double qf = orc_nonneg_logq(x, y);
+    double qb = orc_nonneg_logq(y, x);
+    double r = (prop_lp + qb) - (cur_lp + qf);
+    return (r > log(u)) ? y : x;
+}
+static inline double orc_fold_sum(const double *probs, int64_t K) {
+    double sum = 0.0;
+    for (int64_t k = 0; k < K; ++k) sum = sum + probs[k];
+    return sum;
+}
+
+ORC_API int orc_mh_categorical_run_replay(const double *probs, int64_t K, uint64_t *state, int64_t chains, int64_t n_collect,
+                                          int64_t n_discard, const uint8_t *flip, const double *u, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+    const double sum = orc_fold_sum(probs, K);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        uint64_t x = state[c];
+        for (int64_t i = 0; i < steps; ++i) {
+            x = orc_mh_cat_step(probs, sum, K, x, flip[c * steps + i], u[c * steps + i]);
+            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = x;
+        }
+        state[c] = x;
+    }
+    return 0;
+}
+
+/* native Philox keying: the octet contract of the integer MH kernel (see orc_mh_poisson_run_philox) */
+ORC_API int orc_mh_categorical_run_philox(const double *probs, int64_t K, uint64_t *state, int64_t chains, int64_t chain_offset,
+                                          int64_t step_base, int64_t n_collect, int64_t n_discard, uint64_t seed, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const double sum = orc_fold_sum(probs, K);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        uint64_t x = state[c];
+        const uint64_t gc = (uint64_t)(c + chain_offset);
+        for (int64_t s = 0; s < steps; ++s) {
+            const uint64_t gs = (uint64_t)(step_base + s);
+            const uint32_t i = (uint32_t)(gs & 7);
+            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 3), 0u};
+            uint32_t w[4], v[4];
+            orc_philox4x32_10(key, ctr, w);
+            ctr[3] = 1u + (i >> 1);
+            orc_philox4x32_10(key, ctr, v);
+            const uint32_t h = (w[i >> 1] >> (16u * (i & 1u))) & 0xffffu;
+            const int flip = (int)(h >> 15);
+            const uint64_t bits = (i & 1u) ? (((uint64_t)v[3] << 32) | v[2]) : (((uint64_t)v[1] << 32) | v[0]);
+            const uint64_t u53 = ((uint64_t)(h & 0x7fffu) << 38) | (bits >> 26);
+            const double u = (double)u53 * (1.0 / 9007199254740992.0);
+            x = orc_mh_cat_step(probs, sum, K, x, flip, u);
+            if (s >= n_discard) out[c * n_collect + (s - n_discard)] = x;
+        }
+        state[c] = x;
+    }
+    return 0;
+}

@@ -168,3 +168,46 @@ def test_poisson_host_paths_agree(mm, monkeypatch):
     a = mm.MetropolisHastings(mm.PoissonTarget(400.0), mm.NonnegativeProposal(), init).seed(3).run(300, 10)
     exp, _ = oracle.mh_poisson_run_philox(400.0, init[:, 0], 300, 10, seed=3)
     np.testing.assert_array_equal(a, exp)
+
+
+# ---------------------------------------------------------------- Categorical target (src/distributions.rs:422-477)
+@pytest.mark.parametrize("probs", [[0.2, 0.3, 0.5], [5.0, 1.0, 0.0, 2.0, 2.0], list(np.linspace(1.0, 3.0, 300))])
+def test_categorical_mh_bit_exact_with_oracle(mm, probs):
+    rng = np.random.default_rng(len(probs))
+    K = len(probs)
+    chains, nc, nd = 200, 230, 57
+    valid = [k for k in range(K) if probs[k] > 0]
+    init = rng.choice(valid, size=(chains, 1)).astype(np.uint64)
+    # native Philox stream vs the oracle's integer twin (same octet contract as the Poisson kernel), with a shard offset
+    mh = mm.MetropolisHastings(mm.Categorical(probs), mm.NonnegativeProposal(), init).seed(21).set_chain_offset(5000)
+    out = mh.run(nc, nd)
+    exp, exp_state = oracle.mh_categorical_run_philox(probs, init, nc, nd, seed=21, chain_offset=5000)
+    np.testing.assert_array_equal(out, exp)
+    np.testing.assert_array_equal(mh.current_state().reshape(-1), exp_state)
+    # continuation keeps the step counter
+    out2 = mh.run(40, 0)
+    exp2, _ = oracle.mh_categorical_run_philox(probs, exp_state, 40, 0, seed=21, chain_offset=5000, step_base=nc + nd)
+    np.testing.assert_array_equal(out2, exp2)
+    # replayed flips / uniforms (what a reference run with its own RNG streams would feed)
+    flip = rng.integers(0, 2, size=(chains, nc + nd)).astype(np.uint8)
+    u = rng.random((chains, nc + nd))
+    mh2 = mm.MetropolisHastings(mm.Categorical(probs), mm.NonnegativeProposal(), init)
+    out3 = mh2.run(nc, nd, replay=dict(flip=flip, u=u))
+    exp3, _ = oracle.mh_categorical_run_replay(probs, init, nc, nd, flip, u)
+    np.testing.assert_array_equal(out3, exp3)
+    assert out.max() < K
+
+
+def test_categorical_mh_frequencies_and_guards(mm):
+    probs = [0.2, 0.3, 0.5]
+    mh = mm.MetropolisHastings(mm.Categorical(probs), mm.NonnegativeProposal(), np.zeros((4096, 1), dtype=np.uint64)).seed(1)
+    out = mh.run(2000, 200)
+    freq = np.bincount(out.ravel().astype(np.int64), minlength=3) / out.size
+    np.testing.assert_allclose(freq, probs, atol=5e-3)
+    cat = mm.Categorical([2.0, 3.0, 5.0])
+    np.testing.assert_allclose(cat.probs, probs)                       # normalised like Categorical::new
+    assert cat.logp(3) == float("-inf") and abs(cat.logp(2) - np.log(0.5)) < 1e-15
+    with pytest.raises(Exception):
+        mm.MetropolisHastings(cat, mm.NonnegativeProposal(), np.full((2, 1), 3, dtype=np.uint64))   # start outside the support
+    with pytest.raises(Exception):
+        mh.set_accept_mode(0)
