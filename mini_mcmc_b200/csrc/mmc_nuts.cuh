@@ -401,6 +401,7 @@ struct NutsWarp {
                 }
                 if (lvl == j) break;
                 if (ts) {  // park the finished first half at this level and build the next leaf
+                    __syncwarp();  // every lane has consumed the previous occupant of this level (s_n / s_na / s_a reads above)
                     store_level(lvl, 0, tfx);
                     store_level(lvl, 1, tfm);
                     store_level(lvl, 2, prop);
