@@ -401,7 +401,9 @@ struct NutsWarp {
                 }
                 if (lvl == j) break;
                 if (ts) {  // park the finished first half at this level and build the next leaf
+#ifndef MMC_NUTS_NO_LEVEL_SYNC
                     __syncwarp();  // every lane has consumed the previous occupant of this level (s_n / s_na / s_a reads above)
+#endif
                     store_level(lvl, 0, tfx);
                     store_level(lvl, 1, tfm);
                     store_level(lvl, 2, prop);

@@ -158,6 +158,9 @@ def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32"):
     init = mm.init_device(chains, D, 42).cpu().numpy()
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype=scalar, max_depth=10).set_seed(7)
     out = torch.empty((chains, n_collect, D), dtype=torch.float32, device="cuda")
+    w = mm.NUTS(mm.RosenbrockND(), init[:2048], 0.95, scalar_dtype=scalar, max_depth=10).set_seed(8)
+    w.run_device(20, 20, progress=True)   # warm-up: module load, scratch allocation
+    del w
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
