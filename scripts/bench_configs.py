@@ -204,6 +204,7 @@ def main():
     if WORLD > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+        dist.all_reduce(torch.zeros(1, device="cuda"))   # communicator set-up is not part of any measurement
     if RANK == 0:
         print(json.dumps(dict(gpu=torch.cuda.get_device_name(0), world=WORLD)), flush=True)
     for c in args.configs.split(","):
