@@ -295,6 +295,7 @@ void mmc_tracker_destroy(mmc_tracker *t);
 typedef struct mmc_gibbs mmc_gibbs;
 #define MMC_G_CONSTANT 1
 #define MMC_G_MIXTURE2 2
+#define MMC_G_CUSTOM_BASE 1000 /* kinds returned by mmc_register_gibbs_conditional */
 typedef struct { int32_t kind; int32_t reserved; double params[8]; } mmc_conditional_desc;
 typedef struct { const double *normals; const double *unifs; double *trace; } mmc_replay_gibbs;
 int mmc_gibbs_create(mmc_gibbs **out, const mmc_conditional_desc *cond, const double *init_host, int64_t chains, int32_t dim);
@@ -305,6 +306,11 @@ int mmc_gibbs_run(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *ou
 int mmc_gibbs_run_dev(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_dev, const mmc_replay_gibbs *replay_dev,
                       void *stream);
 int mmc_gibbs_get_state(mmc_gibbs *h, double *state_host);
+/* Custom conditionals (the reference's `Conditional<S>` is user code, src/distributions.rs:485-487): a device functor
+ * compiled by the user (include/minimcmc_target.cuh, MMC_REGISTER_GIBBS_CONDITIONAL) registers its launcher here and
+ * gets the kind to put into mmc_conditional_desc.kind; params[8] are handed to the functor's constructor. */
+typedef int (*mmc_gibbs_launch_fn)(const void *gibbs_params, const double *cond_params, void *stream);
+int mmc_register_gibbs_conditional(const char *name, int32_t dim, mmc_gibbs_launch_fn fn);
 void mmc_gibbs_destroy(mmc_gibbs *h);
 
 /* ------------------------------------------------------------------ sample sinks

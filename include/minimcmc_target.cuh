@@ -21,6 +21,20 @@
 // instantiated for the functor, so a custom target runs at the same speed as a built-in one.
 #pragma once
 
+//
+// Gibbs conditionals (the reference's `Conditional<S>`, src/distributions.rs:485-487) register the same way:
+//
+//     struct MyConditional {
+//         static constexpr int kDim = 2;
+//         double rho;
+//         __host__ explicit MyConditional(const double *p) : rho(p[0]) {}
+//         // new value of coordinate i given the whole state; draws come from rng.normal() / rng.uniform()
+//         __device__ double sample(int i, const double (&state)[kDim], mmc::GibbsRng &rng) const { ... }
+//     };
+//     MMC_REGISTER_GIBBS_CONDITIONAL(my_conditional, MyConditional)
+//
+// `my_conditional_register()` returns the kind (>= MMC_G_CUSTOM_BASE) for mmc_conditional_desc.kind.
+#include "../mini_mcmc_b200/csrc/mmc_gibbs.cuh"
 #include "../mini_mcmc_b200/csrc/mmc_hmc.cuh"
 #include "../mini_mcmc_b200/csrc/mmc_targets.cuh"
 
@@ -35,4 +49,13 @@
     }                                                                                                                \
     extern "C" int NAME##_register(void) {                                                                          \
         return mmc_register_hmc_target(#NAME, FUNCTOR<mmc::Fast>::kDim, NAME##_mmc_launch);                         \
+    }
+
+#define MMC_REGISTER_GIBBS_CONDITIONAL(NAME, FUNCTOR)                                                               \
+    static int NAME##_mmc_gibbs_launch(const void *pv, const double *cp, void *stream) {                            \
+        const mmc::GibbsParams &p = *static_cast<const mmc::GibbsParams *>(pv);                                     \
+        return mmc::launch_gibbs_generic<FUNCTOR>(FUNCTOR(cp), p, static_cast<cudaStream_t>(stream));               \
+    }                                                                                                                \
+    extern "C" int NAME##_register(void) {                                                                          \
+        return mmc_register_gibbs_conditional(#NAME, FUNCTOR::kDim, NAME##_mmc_gibbs_launch);                       \
     }

@@ -5,22 +5,15 @@
 // reference's tests and examples/mixture_gibbs.rs:24-72 (state = [x, z]).  Compiled with -fmad=false: the f64
 // operation sequence is the reference's.  RNG contract (native mode): Philox counter (chain, step, sub = coordinate):
 // words (0,1) -> 53-bit uniform, Box-Muller on words (0,1),(2,3) -> normal z-score.
-#include "mmc_common.cuh"
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mmc_gibbs.cuh"
 
 namespace mmc {
 namespace {
 
-struct GibbsParams {
-    double *state;          // [chains, D] in/out
-    double *out;            // [chains, out_pitch, D]
-    const double *normals;  // replay [chains, steps]
-    const double *unifs;    // replay [chains, steps]
-    double *trace;          // optional [chains, steps, 2]: the (z-score, uniform) each sweep consumed
-    int64_t chains, chain_offset, step_base, n_collect, n_discard, out_pitch;
-    int32_t kind, D;
-    double p[8];
-    uint2 key;
-};
 
 __device__ __forceinline__ double mix_pdf(double x, double mu, double sigma) {
     const double var = sigma * sigma;
@@ -101,6 +94,17 @@ struct mmc_gibbs {
 };
 
 namespace {
+struct CustomConditional {
+    std::string name;
+    int dim;
+    mmc_gibbs_launch_fn fn;
+};
+std::mutex g_cond_mutex;
+std::vector<CustomConditional> &cond_registry() {
+    static std::vector<CustomConditional> r;
+    return r;
+}
+
 int grow(double **buf, size_t *have, size_t want) {
     if (want <= *have) return MMC_OK;
     if (*buf) cudaFree(*buf);
@@ -127,7 +131,15 @@ int mmc_gibbs_create(mmc_gibbs **out, const mmc_conditional_desc *cond, const do
     int rc = ensure_device();
     if (rc) return rc;
     MMC_REQUIRE(out && cond && init_host && chains > 0 && dim > 0, "mmc_gibbs_create: bad arguments");
-    MMC_REQUIRE(cond->kind == MMC_G_CONSTANT || cond->kind == MMC_G_MIXTURE2, "unknown conditional kind %d", cond->kind);
+    if (cond->kind >= MMC_G_CUSTOM_BASE) {
+        std::lock_guard<std::mutex> lock(g_cond_mutex);
+        const size_t idx = (size_t)(cond->kind - MMC_G_CUSTOM_BASE);
+        MMC_REQUIRE(idx < cond_registry().size(), "conditional kind %d is not registered", cond->kind);
+        MMC_REQUIRE(cond_registry()[idx].dim == dim, "conditional '%s' has dim %d, the initial states have dim %d",
+                    cond_registry()[idx].name.c_str(), cond_registry()[idx].dim, dim);
+    } else {
+        MMC_REQUIRE(cond->kind == MMC_G_CONSTANT || cond->kind == MMC_G_MIXTURE2, "unknown conditional kind %d", cond->kind);
+    }
     MMC_REQUIRE(cond->kind != MMC_G_MIXTURE2 || dim == 2, "the mixture conditional has state [x, z]: dim must be 2");
     MMC_REQUIRE(cond->kind != MMC_G_MIXTURE2 || (cond->params[1] > 0.0 && cond->params[3] > 0.0), "mixture std deviations must be > 0");
     mmc_gibbs *h = new mmc_gibbs();
@@ -189,6 +201,18 @@ int mmc_gibbs_run_dev(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double
     p.key = seed_key(h->seed);
     const unsigned grid = (unsigned)((h->chains + 127) / 128);
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->cond.kind >= MMC_G_CUSTOM_BASE) {
+        MMC_REQUIRE(!replay && !p.trace, "replay tapes are only defined for the built-in mixture conditional");
+        mmc_gibbs_launch_fn fn;
+        {
+            std::lock_guard<std::mutex> lock(g_cond_mutex);
+            fn = cond_registry()[(size_t)(h->cond.kind - MMC_G_CUSTOM_BASE)].fn;
+        }
+        int rc = fn(&p, h->cond.params, stream);
+        if (rc) return rc;
+        h->step += n_collect + n_discard;
+        return MMC_OK;
+    }
     if (h->cond.kind == MMC_G_CONSTANT) gibbs_constant_kernel<<<grid, 128, 0, s>>>(p);
     else if (replay) gibbs_mixture_kernel<true><<<grid, 128, 0, s>>>(p);
     else gibbs_mixture_kernel<false><<<grid, 128, 0, s>>>(p);
@@ -229,6 +253,20 @@ int mmc_gibbs_run(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *ou
         MMC_CUDA(cudaMemcpyAsync(replay->trace, h->d_tape[2], (size_t)h->chains * steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MMC_CUDA(cudaStreamSynchronize(h->stream));
     return MMC_OK;
+}
+
+int mmc_register_gibbs_conditional(const char *name, int32_t dim, mmc_gibbs_launch_fn fn) {
+    MMC_REQUIRE(name && fn && dim > 0, "mmc_register_gibbs_conditional: bad arguments");
+    std::lock_guard<std::mutex> lock(g_cond_mutex);
+    auto &r = cond_registry();
+    for (size_t i = 0; i < r.size(); ++i)
+        if (r[i].name == name) {
+            r[i].dim = dim;
+            r[i].fn = fn;
+            return MMC_G_CUSTOM_BASE + (int)i;
+        }
+    r.push_back({name, dim, fn});
+    return MMC_G_CUSTOM_BASE + (int)r.size() - 1;
 }
 
 int mmc_gibbs_get_state(mmc_gibbs *h, double *state_host) {

@@ -238,3 +238,25 @@ class MixtureConditional:
         for i, v in enumerate((self.mu0, self.sigma0, self.mu1, self.sigma1, self.pi0)):
             d.params[i] = v
         return d
+
+
+class CustomConditional:
+    """A user-compiled device conditional registered through include/minimcmc_target.cuh
+    (MMC_REGISTER_GIBBS_CONDITIONAL): `library` is the shared object built from the user's .cu file, `name` the
+    registered identifier, `params` fill mmc_conditional_desc.params (up to 8 doubles)."""
+
+    def __init__(self, library: str, name: str, params=()):
+        import ctypes
+
+        self._user_lib = ctypes.CDLL(library, mode=ctypes.RTLD_GLOBAL)
+        kind = getattr(self._user_lib, f"{name}_register")()
+        if kind < 1000:
+            raise RuntimeError(f"registering custom conditional {name!r} failed with code {kind}")
+        self.kind, self._p = int(kind), tuple(float(v) for v in params)
+
+    def cond_desc(self):
+        d = L.ConditionalDesc()
+        d.kind = self.kind
+        for i, v in enumerate(self._p):
+            d.params[i] = v
+        return d

@@ -108,16 +108,21 @@ def c3(args):
     ms = timed(lambda: h.run_device(nc, nd, out=out), warm=1, reps=3)
     tr = chains * (nc + nd) * WORLD
     rhat, ess = mm.split_rhat_mean_ess(out, group=None if WORLD > 1 else False)
-    cpu_rate = cores = None
+    cpu_rate = cores = cpu_ess = None
     if RANK == 0 and not args.no_cpu:
-        def f(o):
-            o.hmc_run_reference(o.rosenbrock_nd(3), init[:4096], 0.01, L, 100, 0, seed=1, want_out=False)
-            return 4096 * 100
+        cpu_out = {}
+        def f(o):   # the full schedule on a bounded number of chains: transitions/s and ESS/s of the CPU path
+            cpu_out["x"], _ = o.hmc_run_reference(o.rosenbrock_nd(3), init[:8192], 0.01, L, nc, nd, seed=1)
+            return 8192 * (nc + nd)
         cpu_rate, cores = cpu(f)
+        import oracle
+        _, cess = oracle.split_rhat_mean_ess(cpu_out["x"])
+        cpu_ess = float(cess.min()) / (8192 * (nc + nd) / cpu_rate)
     emit(config="C3 rosenbrock3d_hmc 262144 chains/GPU, L=50, run(400,50) (weak)", kernel_ms=ms,
          transitions_per_s=tr / ms * 1e3, grad_evals_per_s=tr * (L + 1) / ms * 1e3,
          tflops_per_gpu=tr / WORLD * 2442 / ms / 1e9, fp32_frac_of_74p4=tr / WORLD * 2442 / ms / 1e9 / 74.4,
-         ess_min=float(ess.min()), ess_per_s=float(ess.min()) / ms * 1e3, cpu_transitions_per_s=cpu_rate, cpu_cores=cores)
+         ess_min=float(ess.min()), ess_per_s=float(ess.min()) / ms * 1e3, cpu_transitions_per_s=cpu_rate, cpu_cores=cores,
+         cpu_ess_per_s=cpu_ess, cpu_sample="8192 chains, same run(400,50); ESS/s = min-ESS of those chains / their wall time")
     del out
 
 
@@ -180,18 +185,24 @@ def c5(args):
     rhat, ess = mm.split_rhat_mean_ess(out, group=None if WORLD > 1 else False)   # NCCL all-reduce of the partials when sharded
     barrier()
     stats_ms = (time.perf_counter() - t0) * 1e3
-    cpu_rate = cores = None
+    cpu_rate = cores = cpu_ess = None
     if RANK == 0 and not args.no_cpu:
-        def f(o):
-            r = o.nuts_run(o.rosenbrock_nd(D), init[:256], 0.95, 100, 100, seed=7, progress=True, scalar_f32=True, max_depth=10)
-            return int(r["n_grad"].sum())
+        cpu_out = {}
+        def f(o):   # the full schedule on 2048 chains
+            r = o.nuts_run(o.rosenbrock_nd(D), init[:2048], 0.95, nc, nd, seed=7, progress=True, scalar_f32=True, max_depth=10)
+            cpu_out["x"], cpu_out["g"] = r["out"], int(r["n_grad"].sum())
+            return cpu_out["g"]
         cpu_rate, cores = cpu(f)
+        import oracle
+        _, cess = oracle.split_rhat_mean_ess(cpu_out["x"])
+        cpu_ess = float(cess.min()) / (cpu_out["g"] / cpu_rate)
     emit(config=f"C5 NUTS RosenbrockND D=100, 65536 chains total ({chains}/GPU, strong), run_progress(400,400)", sample_ms=ms,
          grad_evals_per_s=g[0].item() / ms * 1e3, transitions_per_s=g[1].item() / ms * 1e3,
          tflops_per_gpu=g[0].item() / WORLD * 2285 / ms / 1e9, stats_ms=stats_ms, ess_min=float(ess.min()),
          ess_per_s_sampling=float(ess.min()) / ms * 1e3, ess_per_s_incl_stats=float(ess.min()) / (ms + stats_ms) * 1e3,
          rhat_min=float(rhat.min()), rhat_max=float(rhat.max()), depth_hist=cnt["depth_hist"],
-         cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores)
+         cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores, cpu_ess_per_s=cpu_ess,
+         cpu_sample="2048 chains, same run_progress(400,400); ESS/s = min-ESS of those chains / their wall time")
 
 
 def main():
