@@ -5,7 +5,10 @@
 #include <vector>
 
 #include "mmc_dense.cuh"
+#include <type_traits>
+
 #include "mmc_hmc.cuh"
+#include "mmc_hmc_pair.cuh"
 #include "mmc_hmc_warp.cuh"
 #include "mmc_targets.cuh"
 
@@ -80,6 +83,20 @@ int dispatch(const mmc_hmc *h, const HmcParams &p, bool replay, cudaStream_t s) 
     const mmc_target_desc &t = h->target;
     switch (t.kind) {
     case MMC_T_ROSENBROCK_ND:
+        // throughput mode, native draws: two chains per thread on packed f32x2 instructions (mmc_hmc_pair.cuh);
+        // the scalar kernel stays in charge of replay / trace / exact runs
+        if (std::is_same<A, Fast>::value && !replay && !p.trace && !getenv("MMC_HMC_NO_PAIR")) {
+            switch (t.dim) {
+            case 2: return launch_hmc_pair<RosenbrockND2<2>>({}, p, s);
+            case 3: return launch_hmc_pair<RosenbrockND2<3>>({}, p, s);
+            case 4: return launch_hmc_pair<RosenbrockND2<4>>({}, p, s);
+            case 5: return launch_hmc_pair<RosenbrockND2<5>>({}, p, s);
+            case 8: return launch_hmc_pair<RosenbrockND2<8>>({}, p, s);
+            case 10: return launch_hmc_pair<RosenbrockND2<10>>({}, p, s);
+            case 16: return launch_hmc_pair<RosenbrockND2<16>>({}, p, s);
+            default: break;
+            }
+        }
         switch (t.dim) {
         case 2: return launch_hmc<RosenbrockND<A, 2>, A>({}, p, replay, s);
         case 3: return launch_hmc<RosenbrockND<A, 3>, A>({}, p, replay, s);

@@ -1,0 +1,148 @@
+// K2, packed variant: one thread owns TWO chains and every arithmetic instruction of the trajectory is a packed
+// f32x2 operation (FFMA2 / FADD2 / FMUL2, sm_100+).  The FP32 pipe retires the same 128 FMA/clk/SM either way
+// (measured: 72 vs 74 TFLOP/s for FFMA vs FFMA2 streams), but a packed instruction occupies ONE issue slot for two
+// lanes of work, which leaves issue slots for the non-FMA instructions of the loop: the scalar kernel is issue bound
+// (86 % of issue slots busy at 76 % FMA-pipe utilisation).  Same formulas as hmc_run_kernel<Target, Fast>; the sums
+// are associated as fused chains, so results agree with the scalar kernel to rounding (not bit for bit).
+#pragma once
+
+#include "mmc_hmc.cuh"
+
+namespace mmc {
+
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_bcast(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+
+// RosenbrockND (mmc_targets.cuh) on packed pairs with the operation count trimmed for the FMA pipe: the same
+// formulas, accumulated as fused chains (acc += u^2; acc += 100 t^2;  g_i = 400 x_i t_i + (2 u_i - 200 t_{i-1})).
+// Returns -logp (the caller only needs the negated value).
+template <int D>
+struct RosenbrockND2 {
+    static constexpr int kDim = D;
+    __device__ __forceinline__ F2 neg_logp_grad(const F2 (&x)[D], F2 (&g)[D]) const {
+        const F2 one = f2_bcast(1.0f), c100 = f2_bcast(100.0f), c400 = f2_bcast(400.0f), c2 = f2_bcast(2.0f),
+                 cm2 = f2_bcast(-2.0f), cm200 = f2_bcast(-200.0f), cm1 = f2_bcast(-1.0f);
+        F2 acc, t_prev;
+#pragma unroll
+        for (int i = 0; i + 1 < D; ++i) {
+            const F2 t = fma2(mul2(x[i], cm1), x[i], x[i + 1]);     // x_{i+1} - x_i^2
+            const F2 u = sub2(one, x[i]);
+            acc = (i == 0) ? mul2(u, u) : fma2(u, u, acc);
+            acc = fma2(mul2(t, t), c100, acc);
+            const F2 two_u = fma2(x[i], cm2, c2);
+            const F2 tail = (i == 0) ? two_u : fma2(cm200, t_prev, two_u);
+            g[i] = fma2(mul2(x[i], t), c400, tail);
+            t_prev = t;
+        }
+        g[D - 1] = mul2(cm200, t_prev);
+        return acc;
+    }
+};
+
+template <class Target2>
+__global__ void __launch_bounds__(128) hmc_run_pair_kernel(const Target2 tgt, const HmcParams p) {
+    constexpr int D = Target2::kDim;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c0 = 2 * t;
+    unsigned int n_acc = 0;
+    if (c0 < p.chains) {
+        const bool two = c0 + 1 < p.chains;
+        const int64_t c1 = two ? c0 + 1 : c0;   // an odd tail shadows its own chain in the upper lane (never stored)
+        F2 x[D], pos[D], mom[D], g[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = f2_pack(p.positions[c0 * D + i], p.positions[c1 * D + i]);
+        const F2 eps2 = f2_bcast(p.eps), eps_half2 = f2_bcast(p.eps * 0.5f), half2 = f2_bcast(0.5f), zero = f2_bcast(0.0f);
+        const int64_t steps = p.n_collect + p.n_discard;
+        const uint64_t g0 = (uint64_t)(c0 + p.chain_offset), g1 = (uint64_t)(c1 + p.chain_offset);
+        for (int64_t s = 0; s < steps; ++s) {
+            const uint32_t gstep = (uint32_t)(p.step_base + s);
+            float m0[D], m1[D];
+            philox_normals_f32<D>(p.key, g0, gstep, m0);
+            philox_normals_f32<D>(p.key, g1, gstep, m1);
+            const float u0 = u24_half_open(philox_scalar_words(p.key, g0, gstep).x);
+            const float u1 = u24_half_open(philox_scalar_words(p.key, g1, gstep).x);
+            const F2 nlp_cur = tgt.neg_logp_grad(x, g);
+            F2 ke = zero;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                mom[i] = f2_pack(m0[i], m1[i]);
+                pos[i] = x[i];
+                ke = fma2(mom[i], mom[i], ke);
+            }
+            const F2 h_cur = fma2(ke, half2, nlp_cur);
+            F2 nlp_prop = nlp_cur;
+            // leapfrog with the two half-kicks between consecutive gradient evaluations merged into one full kick
+            // (p += eps g; identical in exact arithmetic, src/hmc.rs:397-431 keeps them separate)
+            if (p.n_leapfrog > 0) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) mom[i] = fma2(g[i], eps_half2, mom[i]);
+            }
+            for (int l = 0; l + 1 < p.n_leapfrog; ++l) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) pos[i] = fma2(mom[i], eps2, pos[i]);
+                nlp_prop = tgt.neg_logp_grad(pos, g);
+#pragma unroll
+                for (int i = 0; i < D; ++i) mom[i] = fma2(g[i], eps2, mom[i]);
+            }
+            if (p.n_leapfrog > 0) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) pos[i] = fma2(mom[i], eps2, pos[i]);
+                nlp_prop = tgt.neg_logp_grad(pos, g);
+#pragma unroll
+                for (int i = 0; i < D; ++i) mom[i] = fma2(g[i], eps_half2, mom[i]);
+            }
+            F2 ke2 = zero;
+#pragma unroll
+            for (int i = 0; i < D; ++i) ke2 = fma2(mom[i], mom[i], ke2);
+            const F2 h_prop = fma2(ke2, half2, nlp_prop);
+            float a0, a1;
+            f2_unpack(sub2(h_cur, h_prop), a0, a1);
+            const bool acc0 = a0 >= logf(u0), acc1 = a1 >= logf(u1);
+            n_acc += (unsigned)acc0 + (unsigned)(acc1 && two);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float xl, xh, pl, ph;
+                f2_unpack(x[i], xl, xh);
+                f2_unpack(pos[i], pl, ph);
+                x[i] = f2_pack(acc0 ? pl : xl, acc1 ? ph : xh);
+            }
+            if (s >= p.n_discard && p.out) {
+                float *o0 = p.out + (c0 * p.out_pitch + (s - p.n_discard)) * D;
+                float *o1 = p.out + (c1 * p.out_pitch + (s - p.n_discard)) * D;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float xl, xh;
+                    f2_unpack(x[i], xl, xh);
+                    o0[i] = xl;
+                    if (two) o1[i] = xh;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float xl, xh;
+            f2_unpack(x[i], xl, xh);
+            p.positions[c0 * D + i] = xl;
+            if (two) p.positions[c1 * D + i] = xh;
+        }
+    }
+    n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+    if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(p.accept_count, (unsigned long long)n_acc);
+}
+
+template <class Target2>
+int launch_hmc_pair(const Target2 &tgt, const HmcParams &p, cudaStream_t stream) {
+    const int block = 128;
+    const int64_t threads = (p.chains + 1) / 2;
+    hmc_run_pair_kernel<Target2><<<(unsigned)((threads + block - 1) / block), block, 0, stream>>>(tgt, p);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+}  // namespace mmc

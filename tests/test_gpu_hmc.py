@@ -156,3 +156,32 @@ def test_hmc_warp_kernel_general_dim(mm, D):
     exp2, _, _ = oracle.hmc_run_replay(oracle.rosenbrock_nd(D), init, eps, L, 2, 0, m2.cpu().numpy(), u2.cpu().numpy())
     ok = np.isclose(got, exp2, rtol=1e-5, atol=1e-5).all(axis=(1, 2))
     assert ok.mean() > 0.9
+
+
+@pytest.mark.parametrize("D", [2, 3, 5])
+def test_hmc_packed_throughput_kernel_matches_oracle(mm, monkeypatch, D):
+    """Throughput mode runs two chains per thread on packed f32x2 instructions (csrc/mmc_hmc_pair.cuh): the native run
+    equals the oracle's replay of the exported draws to fp32 rounding, for an odd chain count, any sharding, L = 0."""
+    chains, L, n_collect, n_discard = 1001, 12, 3, 2
+    init = (oracle.init_positions(chains, D, 11) * 0.5).astype(np.float32)
+    h = mm.HMC(mm.RosenbrockND(), init, 0.01, L).set_seed(77).set_chain_offset(40)
+    mom, u = h.export_tape(0, n_collect + n_discard)
+    got = h.run(n_collect, n_discard)
+    exp, _, _ = oracle.hmc_run_replay(oracle.rosenbrock_nd(D), init, 0.01, L, n_collect, n_discard,
+                                      mom.cpu().numpy(), u.cpu().numpy())
+    close = np.isclose(got, exp, rtol=1e-4, atol=1e-4).all(axis=(1, 2))
+    assert close.mean() > 0.99
+    # the pairing of chains into threads cannot matter: odd split points, same draws
+    a = mm.HMC(mm.RosenbrockND(), init[:401], 0.01, L).set_seed(77).set_chain_offset(40)
+    b = mm.HMC(mm.RosenbrockND(), init[401:], 0.01, L).set_seed(77).set_chain_offset(441)
+    np.testing.assert_array_equal(np.concatenate([a.run(n_collect, n_discard), b.run(n_collect, n_discard)]), got)
+    # the scalar throughput kernel (one chain per thread) agrees to rounding
+    monkeypatch.setenv("MMC_HMC_NO_PAIR", "1")
+    ref = mm.HMC(mm.RosenbrockND(), init, 0.01, L).set_seed(77).set_chain_offset(40).run(n_collect, n_discard)
+    monkeypatch.delenv("MMC_HMC_NO_PAIR")
+    assert np.isclose(got, ref, rtol=1e-4, atol=1e-4).all(axis=(1, 2)).mean() > 0.99
+    # L = 0: every proposal equals the current point and is accepted
+    z = mm.HMC(mm.RosenbrockND(), init, 0.01, 0).set_seed(1)
+    np.testing.assert_array_equal(z.run(2, 0), np.repeat(init[:, None, :], 2, axis=1))
+    acc, tot = z.accept_counts()
+    assert acc == tot == 2 * chains
