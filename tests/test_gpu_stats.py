@@ -32,6 +32,9 @@ def _ar1(rng, c, n, p, phi, offset=0.0):
     (37, 64, 3, 0.5, 1.0),       # small p: several split chains staged per round, ragged last round
     (40, 400, 2, 0.95, 0.0),     # small p and many lag blocks
     (300, 40, 1, 0.2, 0.0),      # p = 1, more rounds than CTAs would need at K = 16
+    (37, 64, 4, 0.5, 1.0),       # even p: packed two-parameters-per-thread kernel, ragged last round
+    (9, 600, 6, 0.97, -3.0),     # packed kernel, many lag blocks
+    (5, 100, 256, 0.3, 0.0),     # packed kernel, wide rows (128 parameter pairs)
 ])
 def test_split_rhat_ess_matches_oracle(mm, c, n, p, phi, offset):
     rng = np.random.default_rng(c * 1000 + n)
