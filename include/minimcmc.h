@@ -283,6 +283,23 @@ int mmc_tracker_summary(mmc_tracker *t, float *rhat_host, float *max_rhat, float
 int mmc_tracker_get(mmc_tracker *t, float *mean_host, float *mean_sq_host, float *p_accept_host);
 void mmc_tracker_destroy(mmc_tracker *t);
 
+/* ------------------------------------------------------------------ run_progress
+ * Replaces ChainRunner::run_progress (MetropolisHastings / GibbsSampler, src/core.rs:208-360), HMC::run_progress
+ * (src/hmc.rs:222-294) and NUTS::run_progress (src/nuts.rs:194-338): same sample as run(), plus RunStats, plus live
+ * statistics.  The sampler runs in blocks of `block` steps (<= 0: about 1/16 of the run, multiples of 32) that write into
+ * windows of one device tensor; after every block the device tracker folds the new draws and `cb(done, total, p_accept,
+ * max_rhat, user)` is called (the numbers the reference's progress bars print, `p(accept)≈{:.2} max(rhat)≈{:.2}`).  MH,
+ * Gibbs and NUTS track every step, burn-in included, with one ChainTracker per chain + collect_rhat (total = n_collect +
+ * n_discard); HMC tracks the post-burn-in positions and the collected draws with a MultiChainTracker (total = n_collect).
+ * cb and stats may be NULL.  The draws equal those of the corresponding run() call. */
+typedef void (*mmc_progress_fn)(int64_t done, int64_t total, float p_accept, float max_rhat, void *user);
+int mmc_mh_run_progress(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, int64_t block, mmc_progress_fn cb,
+                        void *user, mmc_run_stats *stats);
+int mmc_hmc_run_progress(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, int64_t block, mmc_progress_fn cb,
+                         void *user, mmc_run_stats *stats);
+int mmc_nuts_run_progress(mmc_nuts *h, int64_t n_collect, int64_t n_discard, float *out_host, int64_t block, mmc_progress_fn cb,
+                          void *user, mmc_run_stats *stats);
+
 /* ------------------------------------------------------------------ Gibbs
  * Replaces GibbsSampler::new / set_seed / run(_progress) and GibbsMarkovChain::step (src/gibbs.rs:89-205): each step
  * sweeps the coordinates in order, state[i] = conditional.sample(i, state).  `Conditional` is user code in the
@@ -305,6 +322,8 @@ int mmc_gibbs_set_out_pitch(mmc_gibbs *h, int64_t pitch_steps); /* see mmc_mh_se
 int mmc_gibbs_run(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_host, const mmc_replay_gibbs *replay);
 int mmc_gibbs_run_dev(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_dev, const mmc_replay_gibbs *replay_dev,
                       void *stream);
+int mmc_gibbs_run_progress(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_host, int64_t block,
+                           mmc_progress_fn cb, void *user, mmc_run_stats *stats); /* see "run_progress" above */
 int mmc_gibbs_get_state(mmc_gibbs *h, double *state_host);
 /* Custom conditionals (the reference's `Conditional<S>` is user code, src/distributions.rs:485-487): a device functor
  * compiled by the user (include/minimcmc_target.cuh, MMC_REGISTER_GIBBS_CONDITIONAL) registers its launcher here and

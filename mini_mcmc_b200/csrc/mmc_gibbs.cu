@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "mmc_gibbs.cuh"
+#include "mmc_progress.cuh"
 
 namespace mmc {
 namespace {
@@ -253,6 +254,21 @@ int mmc_gibbs_run(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *ou
         MMC_CUDA(cudaMemcpyAsync(replay->trace, h->d_tape[2], (size_t)h->chains * steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MMC_CUDA(cudaStreamSynchronize(h->stream));
     return MMC_OK;
+}
+
+int mmc_gibbs_run_progress(mmc_gibbs *h, int64_t n_collect, int64_t n_discard, double *out_host, int64_t block, mmc_progress_fn cb,
+                           void *user, mmc_run_stats *stats) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_gibbs_run_progress: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_gibbs_run_progress: an output pitch is set on this handle");
+    ProgressSpec sp{h->chains, h->dim, MMC_F64, MMC_TRACK_PER_CHAIN, true, h->d_state};
+    auto run_block = [&](int64_t k, void *dst, int64_t pitch, bool) {
+        h->out_pitch = pitch;
+        const int rc = mmc_gibbs_run_dev(h, k, 0, static_cast<double *>(dst), nullptr, h->stream);
+        h->out_pitch = 0;
+        return rc;
+    };
+    auto discard = [&](int64_t k) { return mmc_gibbs_run_dev(h, 0, k, nullptr, nullptr, h->stream); };
+    return run_progress_blocks(sp, n_collect, n_discard, out_host, block, cb, user, stats, h->stream, run_block, discard);
 }
 
 int mmc_register_gibbs_conditional(const char *name, int32_t dim, mmc_gibbs_launch_fn fn) {

@@ -9,6 +9,7 @@
 
 #include "mmc_hmc.cuh"
 #include "mmc_hmc_pair.cuh"
+#include "mmc_progress.cuh"
 #include "mmc_hmc_warp.cuh"
 #include "mmc_targets.cuh"
 
@@ -359,6 +360,21 @@ int mmc_hmc_run(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_hos
                                  h->stream));
     MMC_CUDA(cudaStreamSynchronize(h->stream));
     return MMC_OK;
+}
+
+int mmc_hmc_run_progress(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out_host, int64_t block, mmc_progress_fn cb,
+                         void *user, mmc_run_stats *stats) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_hmc_run_progress: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_hmc_run_progress: an output pitch is set on this handle");
+    ProgressSpec sp{h->chains, h->dim, MMC_F32, MMC_TRACK_MULTI, false, h->d_pos};
+    auto run_block = [&](int64_t k, void *dst, int64_t pitch, bool) {
+        h->out_pitch = pitch;
+        const int rc = mmc_hmc_run_dev(h, k, 0, static_cast<float *>(dst), nullptr, h->stream);
+        h->out_pitch = 0;
+        return rc;
+    };
+    auto discard = [&](int64_t k) { return mmc_hmc_run_dev(h, 0, k, nullptr, nullptr, h->stream); };
+    return run_progress_blocks(sp, n_collect, n_discard, out_host, block, cb, user, stats, h->stream, run_block, discard);
 }
 
 int mmc_hmc_get_positions(mmc_hmc *h, float *positions_host) {

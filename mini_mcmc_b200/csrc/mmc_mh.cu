@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mmc_mh.cuh"
+#include "mmc_progress.cuh"
 
 using namespace mmc;
 
@@ -483,6 +484,21 @@ int mmc_mh_d2h_bytes_per_draw(mmc_mh *h) {
     if (!h) return MMC_ERR_INVALID;
     if (is_int_target(h) && h->accept_mode == 1 && !getenv("MMC_NO_COMPACT")) return h->table_len <= 256 ? 1 : 2;
     return 8 * h->dim;
+}
+
+int mmc_mh_run_progress(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, int64_t block, mmc_progress_fn cb,
+                        void *user, mmc_run_stats *stats) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run_progress: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run_progress: an output pitch is set on this handle");
+    ProgressSpec sp{h->chains, h->dim, h->dtype, MMC_TRACK_PER_CHAIN, true, h->d_state};
+    auto run_block = [&](int64_t k, void *dst, int64_t pitch, bool) {
+        h->out_pitch = pitch;
+        const int rc = mmc_mh_run_dev(h, k, 0, dst, nullptr, h->stream);
+        h->out_pitch = 0;
+        return rc;
+    };
+    auto discard = [&](int64_t k) { return mmc_mh_run_dev(h, 0, k, nullptr, nullptr, h->stream); };
+    return run_progress_blocks(sp, n_collect, n_discard, out_host, block, cb, user, stats, h->stream, run_block, discard);
 }
 
 int mmc_mh_get_state(mmc_mh *h, void *state_host) {

@@ -2,6 +2,7 @@
 #include <vector>
 
 #include "mmc_nuts_inst.cuh"
+#include "mmc_progress.cuh"
 
 using namespace mmc;
 
@@ -187,6 +188,29 @@ int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t prog
     if (out_bytes) MMC_CUDA(cudaMemcpyAsync(out_host, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     MMC_CUDA(cudaStreamSynchronize(h->stream));
     return MMC_OK;
+}
+
+int mmc_nuts_run_progress(mmc_nuts *h, int64_t n_collect, int64_t n_discard, float *out_host, int64_t block, mmc_progress_fn cb,
+                          void *user, mmc_run_stats *stats) {
+    MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_nuts_run_progress: bad arguments");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_nuts_run_progress: an output pitch is set on this handle");
+    ProgressSpec sp{h->chains, h->dim, MMC_F32, MMC_TRACK_PER_CHAIN, true, h->d_pos};
+    const int64_t saved_until = h->adapt_until;
+    const int32_t saved_resume = h->resume;
+    auto run_block = [&](int64_t k, void *dst, int64_t pitch, bool first) {
+        // the reference compares the chain's absolute step count m with this call's n_discard (src/nuts.rs:681); later
+        // blocks continue without init_chain so that the blocks reproduce the single-launch run
+        h->out_pitch = pitch;
+        h->adapt_until = n_discard;
+        h->resume = first ? 0 : 1;
+        const int rc = mmc_nuts_run_dev(h, k, 0, 1, static_cast<float *>(dst), nullptr, h->stream);
+        h->out_pitch = 0;
+        h->adapt_until = saved_until;
+        h->resume = saved_resume;
+        return rc;
+    };
+    auto discard = [&](int64_t k) { return mmc_nuts_run_dev(h, 0, k, 1, nullptr, nullptr, h->stream); };
+    return run_progress_blocks(sp, n_collect, n_discard, out_host, block, cb, user, stats, h->stream, run_block, discard);
 }
 
 int mmc_nuts_get_state(mmc_nuts *h, double *state_host) {

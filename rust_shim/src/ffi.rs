@@ -10,6 +10,7 @@ use std::ffi::{c_char, c_void, CStr};
 #[repr(C)] pub struct mmc_replay_hmc { pub momenta: *const f32, pub u: *const f32, pub trace: *mut f32 }
 #[repr(C)] pub struct mmc_replay_nuts { pub normals: *const f64, pub cap_normals: i64, pub exps: *const f64, pub cap_exps: i64, pub unifs: *const f64, pub cap_unifs: i64 }
 #[repr(C)] pub struct mmc_basic_stats { pub min: f32, pub median: f32, pub max: f32, pub mean: f32, pub std: f32 }
+#[repr(C)] pub struct mmc_run_stats { pub ess: mmc_basic_stats, pub rhat: mmc_basic_stats }
 pub enum mmc_mh {} pub enum mmc_hmc {} pub enum mmc_nuts {} pub enum mmc_tracker {}
 
 extern "C" {
@@ -31,7 +32,14 @@ extern "C" {
     pub fn mmc_nuts_destroy(h: *mut mmc_nuts);
     pub fn mmc_split_rhat_ess(sample: *const f32, c: i64, n: i64, p: i64, rhat: *mut f32, ess: *mut f32) -> i32;
     pub fn mmc_basic_stats_of(data: *const f32, len: i64, out: *mut mmc_basic_stats) -> i32;
-    // run_progress: block-wise device runs + device-side trackers (src/stats.rs:26-307)
+    // run_progress in one call: blocks of steps, device trackers, callback per block, RunStats at the end
+    pub fn mmc_hmc_run_progress(h: *mut mmc_hmc, n_collect: i64, n_discard: i64, out: *mut f32, block: i64,
+        cb: Option<extern "C" fn(done: i64, total: i64, p_accept: f32, max_rhat: f32, user: *mut c_void)>, user: *mut c_void, stats: *mut mmc_run_stats) -> i32;
+    pub fn mmc_mh_run_progress(h: *mut mmc_mh, n_collect: i64, n_discard: i64, out: *mut c_void, block: i64,
+        cb: Option<extern "C" fn(done: i64, total: i64, p_accept: f32, max_rhat: f32, user: *mut c_void)>, user: *mut c_void, stats: *mut mmc_run_stats) -> i32;
+    pub fn mmc_nuts_run_progress(h: *mut mmc_nuts, n_collect: i64, n_discard: i64, out: *mut f32, block: i64,
+        cb: Option<extern "C" fn(done: i64, total: i64, p_accept: f32, max_rhat: f32, user: *mut c_void)>, user: *mut c_void, stats: *mut mmc_run_stats) -> i32;
+    // building blocks of run_progress for device-resident use: block-wise device runs + device-side trackers (src/stats.rs:26-307)
     pub fn mmc_hmc_run_dev(h: *mut mmc_hmc, n_collect: i64, n_discard: i64, out_dev: *mut f32, replay: *const mmc_replay_hmc, stream: *mut c_void) -> i32;
     pub fn mmc_hmc_set_out_pitch(h: *mut mmc_hmc, pitch_steps: i64) -> i32;
     pub fn mmc_hmc_positions_dev(h: *mut mmc_hmc, positions_dev: *mut *mut f32) -> i32;
