@@ -271,6 +271,23 @@ struct NutsWarp {
         return (double)u24_half_open(hw);
     }
 
+    // the 53 random bits behind the next f64 uniform (native mode only; same counter stream as draw_uniform)
+    __device__ __forceinline__ uint64_t draw_u53() {
+        ++n_unif;
+        const uint32_t batch = q >> 6;
+        if (batch != q_batch) {
+            ubatch = philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step_word,
+                                                     kSubUnif + batch * 32 + (uint32_t)lane));
+            q_batch = batch;
+        }
+        const int src = (q >> 1) & 31;
+        const bool hi = q & 1;
+        const uint32_t lo = __shfl_sync(kFull, hi ? ubatch.z : ubatch.x, src);
+        const uint32_t hw = __shfl_sync(kFull, hi ? ubatch.w : ubatch.y, src);
+        ++q;
+        return (((uint64_t)hw << 32) | lo) >> 11;
+    }
+
     // ---- leapfrog, src/nuts.rs:979-996 (in place); returns logp'
     __device__ __forceinline__ float leapfrog(float (&x)[E], float (&m)[E], float (&g)[E], ST eps) {
         const float e = (float)eps;
@@ -382,13 +399,20 @@ struct NutsWarp {
                     // merge pending first half A = stack[lvl] with the later half T
                     const int an = s_n[lvl], ana = s_na[lvl];
                     const ST aa = (ST)s_a[lvl];
-                    const double u = draw_uniform(true);
-                    // u < n'' / max(n' + n'', 1) in f64 (src/nuts.rs:910-911); the quotient is exactly 0 or 1 in the
-                    // two common cases, which avoids the f64 division without changing the decision
+                    // u < n'' / max(n' + n'', 1) in f64 (src/nuts.rs:910-911)
                     bool take_b;
-                    if (tn == 0) take_b = false;
-                    else if (an == 0) take_b = u < 1.0;
-                    else take_b = u < ((double)tn / (double)(an + tn));
+                    if (kReplay) {
+                        const double u = draw_uniform(true);
+                        if (tn == 0) take_b = false;
+                        else if (an == 0) take_b = u < 1.0;
+                        else take_b = u < ((double)tn / (double)(an + tn));
+                    } else {
+                        // native draws are k 2^-53 with a 53-bit integer k: k (n' + n'') < n'' 2^53 is the same test
+                        // evaluated exactly (the f64 quotient is rounded, which can only matter when u equals the rounded
+                        // quotient itself, a 2^-53 event) and keeps the FP64 division out of the merge path
+                        const uint64_t k53 = draw_u53();
+                        take_b = tn != 0 && (an == 0 || k53 * (uint64_t)(an + tn) < ((uint64_t)tn << 53));
+                    }
                     load_level(lvl, 0, tfx);
                     load_level(lvl, 1, tfm);
                     if (!take_b) load_level(lvl, 2, prop);
