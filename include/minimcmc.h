@@ -215,6 +215,15 @@ int mmc_nuts_set_seed(mmc_nuts *h, uint64_t seed);
 int mmc_nuts_set_chain_offset(mmc_nuts *h, int64_t offset);
 int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact);
 int mmc_nuts_set_out_pitch(mmc_nuts *h, int64_t pitch_steps); /* see mmc_mh_set_out_pitch */
+/* Lane layout of the tree kernel.  0 (default) = automatic: several chains per warp (G lanes per chain, 32 / G chains
+ * advancing in lock step and sharing the tree bookkeeping) wherever that layout is compiled in for the target
+ * (RosenbrockND D <= 128: G = 4 / 8 / 16, StdNormal D <= 32, the 2-D targets: G = 4), else one chain per warp;
+ * 32 = always one chain per warp; any other value must be the G compiled in for the target.  Both layouts implement
+ * the same algorithm on the same Philox counters and replay tapes; f32 sums are grouped differently, so native draws
+ * agree between layouts only up to fp32 rounding (amplified by the dynamics).  mmc_nuts_get_layout reports the lanes
+ * per chain of the last launch. */
+int mmc_nuts_set_layout(mmc_nuts *h, int32_t lanes_per_chain);
+int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain);
 /* Splitting one run over several launches (run_progress in blocks): adapt_until = absolute step count m up to which
  * dual averaging adapts (-1 = the reference's rule `m <= n_discard` of each call, src/nuts.rs:681); resume = 1 makes
  * the following runs continue the chains without init_chain (src/nuts.rs:528-545), so that the blocks reproduce the

@@ -1,7 +1,7 @@
 // NUTS C ABI (see include/minimcmc.h) — host side of K4.
 #include <vector>
 
-#include "mmc_nuts_inst.cuh"
+#include "mmc_nuts_group_inst.cuh"
 #include "mmc_progress.cuh"
 
 using namespace mmc;
@@ -19,6 +19,8 @@ struct mmc_nuts {
     int64_t out_pitch = 0;     // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
     int64_t adapt_until = -1;  // -1: the reference's rule (m <= n_discard of the call)
     int32_t resume = 0;        // 1: the next run continues the chains without init_chain
+    int32_t layout = 0;        // lanes per chain requested: 0 = auto, 32 = one chain per warp, else the group kernel's G
+    int32_t lanes_used = 0;    // lanes per chain of the last launch
     float *d_pos = nullptr;
     double *d_state = nullptr;            // [chains, 5]
     unsigned long long *d_counters = nullptr;  // [8 + 32]
@@ -107,6 +109,22 @@ int mmc_nuts_set_exact(mmc_nuts *h, int32_t exact) {
     return MMC_OK;
 }
 
+int mmc_nuts_set_layout(mmc_nuts *h, int32_t lanes_per_chain) {
+    MMC_REQUIRE(h, "null handle");
+    const int avail = nuts_group_lanes(h->target);
+    MMC_REQUIRE(lanes_per_chain == kNutsLayoutAuto || lanes_per_chain == kNutsLayoutWarp || lanes_per_chain == avail,
+                "mmc_nuts_set_layout: %d lanes per chain is not compiled in for this target (0 = auto, 32 = warp per chain%s%d)",
+                lanes_per_chain, avail ? ", group = " : "; no group layout, ", avail);
+    h->layout = lanes_per_chain;
+    return MMC_OK;
+}
+
+int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain) {
+    MMC_REQUIRE(h && lanes_per_chain, "mmc_nuts_get_layout: bad arguments");
+    *lanes_per_chain = h->lanes_used;
+    return MMC_OK;
+}
+
 int mmc_nuts_set_out_pitch(mmc_nuts *h, int64_t pitch_steps) {
     MMC_REQUIRE(h && pitch_steps >= 0, "mmc_nuts_set_out_pitch: bad arguments");
     h->out_pitch = pitch_steps;
@@ -150,7 +168,12 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     p.target_accept = h->target_accept;
     p.key = seed_key(h->seed);
     NutsLaunch L{h->target, h->scalar_dtype == MMC_F64, replay, sm_count()};
-    auto dispatch = h->exact ? nuts_dispatch_exact : nuts_dispatch_fast;
+    // several chains per warp wherever that layout is compiled in for the target, unless the caller pins the layout
+    const int group_lanes = nuts_group_lanes(h->target);
+    const bool group = h->layout == kNutsLayoutAuto ? group_lanes != 0 : h->layout != kNutsLayoutWarp;
+    h->lanes_used = group ? group_lanes : 32;
+    auto dispatch = group ? (h->exact ? nuts_group_dispatch_exact : nuts_group_dispatch_fast)
+                          : (h->exact ? nuts_dispatch_exact : nuts_dispatch_fast);
     int64_t grid = 0;
     size_t scratch_floats = 0;
     int rc = dispatch(L, p, &grid, &scratch_floats, true, s);

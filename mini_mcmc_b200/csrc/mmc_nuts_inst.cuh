@@ -15,6 +15,9 @@ struct NutsLaunch {
     int sm_count;
 };
 
+// mmc_nuts_set_layout values (include/minimcmc.h)
+constexpr int kNutsLayoutAuto = 0, kNutsLayoutWarp = 32;
+
 template <class A>
 DiffGaussian2D<A> nuts_make_diff_gaussian(const mmc_target_desc &t) {
     // DiffableGaussian2D::new, src/distributions.rs:227-251 (T = f64), then cast to the backend float

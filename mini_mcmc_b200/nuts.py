@@ -1,5 +1,6 @@
-"""`NUTS` mirroring src/nuts.rs (new / set_seed / run / run_progress), backed by the one-chain-per-warp
-tree-doubling kernel of csrc/mmc_nuts.cuh through the C ABI."""
+"""`NUTS` mirroring src/nuts.rs (new / set_seed / run / run_progress), backed by the tree-doubling kernels of
+csrc/mmc_nuts_group.cuh (several chains per warp, the default where compiled in) and csrc/mmc_nuts.cuh (one chain per
+warp) through the C ABI."""
 from __future__ import annotations
 
 import ctypes as C
@@ -52,6 +53,19 @@ class NUTS:
     def set_exact(self, exact: bool):
         L.check(L.lib.mmc_nuts_set_exact(self._h, C.c_int32(int(exact))))
         return self
+
+    def set_layout(self, lanes_per_chain: int):
+        """0 = automatic (several chains per warp where compiled in for the target), 32 = one chain per warp, or the
+        group size compiled in for the target (mmc_nuts_set_layout)."""
+        L.check(L.lib.mmc_nuts_set_layout(self._h, C.c_int32(lanes_per_chain)))
+        return self
+
+    @property
+    def lanes_per_chain(self) -> int:
+        """Lanes per chain of the last launch (32 = one chain per warp)."""
+        n = C.c_int32()
+        L.check(L.lib.mmc_nuts_get_layout(self._h, C.byref(n)))
+        return n.value
 
     @staticmethod
     def _replay_struct(replay):

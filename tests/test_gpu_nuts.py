@@ -1,4 +1,5 @@
-"""Parity of the warp-per-chain CUDA NUTS (K4) against the oracle and the reference's golden vectors."""
+"""Parity of the CUDA NUTS kernels (K4: one chain per warp, layout 32; K4b: several chains per warp, layout 0 =
+automatic) against the oracle and the reference's golden vectors."""
 import numpy as np
 import pytest
 
@@ -23,56 +24,65 @@ def _record(otgt, init, delta, n_collect, n_discard, seed, **kw):
     return oracle.nuts_run(otgt, init, delta, n_collect, n_discard, seed=seed, record=True, **kw)
 
 
+LAYOUTS = [32, 0]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("exact", [True, False])
-def test_golden_chain_3_replayed_reference_stream(mm, exact):
+def test_golden_chain_3_replayed_reference_stream(mm, exact, layout):
     """src/nuts.rs:1164-1222 (test_chain_3 / test_run_1): the reference's own SmallRng(42) draws (recorded by
     the oracle) replayed into the CUDA kernel reproduce the reference's golden sample (rel 1e-5 / abs 1e-6)."""
     init = [[-2.0, 1.0]]
     rec = _record(oracle.diff_gaussian2d([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, 5, 5, 41)
     s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype="f64",
-                max_depth=16).set_exact(exact)
+                max_depth=16).set_exact(exact).set_layout(layout)
     got = s.run(5, 5, replay=rec["tapes"])
+    assert s.lanes_per_chain == (32 if layout == 32 else 4)
     assert got.shape == (1, 5, 2)
     np.testing.assert_allclose(got.reshape(-1), CHAIN_3, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(s.state()[0, :4], rec["state"][0, :4], rtol=1e-5 if exact else 1e-3)
 
 
-def test_golden_chain_2_and_chain_1(mm):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_golden_chain_2_and_chain_1(mm, layout):
     # src/nuts.rs:1138-1162 and :1123-1136
     tgt = lambda: mm.DiffableGaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
     otgt = oracle.diff_gaussian2d([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
     rec = _record(otgt, [[0.0, 1.0]], 0.8, 3, 3, 41)
-    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64", max_depth=16).set_exact(True).run(3, 3, replay=rec["tapes"])
+    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64", max_depth=16).set_exact(True).set_layout(layout).run(
+        3, 3, replay=rec["tapes"])
     np.testing.assert_allclose(got.reshape(-1), CHAIN_2, rtol=1e-5, atol=1e-6)
     rec = _record(otgt, [[0.0, 1.0]], 0.8, 1, 0, 41)
-    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64").run(1, 0, replay=rec["tapes"])
+    got = mm.NUTS(tgt(), [[0.0, 1.0]], 0.8, scalar_dtype="f64").set_layout(layout).run(1, 0, replay=rec["tapes"])
     np.testing.assert_allclose(got.reshape(-1), [0.0, 1.0], rtol=1e-5, atol=1e-6)
 
 
-def test_find_reasonable_epsilon_kat(mm):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_find_reasonable_epsilon_kat(mm, layout):
     # src/nuts.rs:1049-1055: x = [0,1], p = [1,0], standard normal -> epsilon = 2.0; the first normals tape
     # entries are the init_chain momentum.
     normals = np.array([[1.0, 0.0, 0.3, -0.2]])
     exps = np.array([[0.5]])
     unifs = np.full((1, 64), 0.25)
-    s = mm.NUTS(mm.StandardNormalTarget(), [[0.0, 1.0]], 0.8, scalar_dtype="f64")
+    s = mm.NUTS(mm.StandardNormalTarget(), [[0.0, 1.0]], 0.8, scalar_dtype="f64").set_layout(layout)
     s.run(1, 0, replay=(normals, exps, unifs))
     st = s.state()[0]
     assert st[0] == 2.0 and abs(st[3] - np.log(20.0)) < 1e-12 and st[4] == 0
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("progress", [False, True])
 @pytest.mark.parametrize("scalar", ["f64", "f32"])
-def test_multi_chain_replay_matches_oracle(mm, progress, scalar):
+def test_multi_chain_replay_matches_oracle(mm, progress, scalar, layout):
     """Many chains, run and run_progress semantics, both scalar types: the iterative device tree must
     consume the tapes exactly like the recursive reference (same draws, same accepted states)."""
     rng = np.random.default_rng(5)
-    chains, n_collect, n_discard = 64, 12, 8
+    chains, n_collect, n_discard = 67, 12, 8   # not a multiple of the chains per warp: the last warp has idle groups
     init = (rng.normal(size=(chains, 2)) + [1.0, 2.0]).astype(np.float32)
     otgt = oracle.diff_gaussian2d([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]])
     rec = _record(otgt, init, 0.8, n_collect, n_discard, 7, progress=progress, scalar_f32=(scalar == "f32"))
     s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype=scalar,
-                max_depth=16).set_exact(True)
+                max_depth=16).set_exact(True).set_layout(layout)
     got = s._run(n_collect, n_discard, int(progress), rec["tapes"], None)
     ok = np.isclose(got, rec["out"], rtol=1e-4, atol=1e-5).all(axis=(1, 2))
     # f32 scalars: expf/logf/powf of the device and of glibc differ in the last ulp, which perturbs epsilon at
@@ -89,17 +99,19 @@ def test_multi_chain_replay_matches_oracle(mm, progress, scalar):
     assert abs(c["n_grad"] - rec["n_grad"].sum()) <= 0.05 * rec["n_grad"].sum()
 
 
-@pytest.mark.parametrize("D", [2, 10, 100])
-def test_rosenbrock_nd_replay_matches_oracle(mm, D):
-    """RosenbrockND as a GradientTarget (config C5 widens examples/minimal_nuts.rs to D = 100): both lane
-    layouts (E = 1 for D <= 32, E = 4 above)."""
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("D", [2, 10, 50, 100, 120])
+def test_rosenbrock_nd_replay_matches_oracle(mm, D, layout):
+    """RosenbrockND as a GradientTarget (config C5 widens examples/minimal_nuts.rs to D = 100): the lane layouts of
+    the warp kernel (E = 1 for D <= 32, E = 4 above) and of the group kernel (4 x 1, 8 x 4, 8 x 8, 8 x 13, 16 x 8)."""
     rng = np.random.default_rng(D)
-    chains, n_collect, n_discard = 24, 6, 6
+    chains, n_collect, n_discard = 26, 6, 6
     init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
     rec = _record(oracle.rosenbrock_nd(D), init, 0.95, n_collect, n_discard, 3, progress=True, scalar_f32=True,
                   max_depth=8, cap_unifs=40000)
-    s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=8).set_exact(True)
+    s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=8).set_exact(True).set_layout(layout)
     got = s._run(n_collect, n_discard, 1, rec["tapes"], None)
+    assert s.lanes_per_chain == (32 if layout == 32 else {2: 4, 10: 8, 50: 8, 100: 8, 120: 16}[D])
     # f32 reductions are ordered differently on the device (butterfly vs sequential), so individual chains may
     # legitimately take a different branch at a near-tie; most must agree to 1e-4
     ok = np.isclose(got, rec["out"], rtol=1e-3, atol=1e-4).all(axis=(1, 2))
@@ -108,13 +120,37 @@ def test_rosenbrock_nd_replay_matches_oracle(mm, D):
     assert first.mean() >= 0.9
 
 
-def test_native_nuts_distribution_and_adaptation(mm):
+@pytest.mark.parametrize("D", [2, 3, 10, 50, 100, 120])
+def test_native_layouts_share_the_philox_contract(mm, D):
+    """The two kernels draw from the same Philox counters (minimcmc.h "RNG contract"), so a short native run gives the
+    same draws up to the f32 rounding of differently grouped sums (a chain near a tie may branch differently)."""
+    rng = np.random.default_rng(100 + D)
+    chains = 301
+    init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
+    outs, eps, grads = [], [], []
+    for layout in (32, 0):
+        s = mm.NUTS(mm.RosenbrockND(), init, 0.9, scalar_dtype="f32", max_depth=8).set_seed(5).set_layout(layout)
+        outs.append(s.run_device(4, 4).cpu().numpy())
+        eps.append(s.state()[:, 0])
+        grads.append(s.counters()["n_grad"])
+        assert (s.lanes_per_chain == 32) == (layout == 32)
+    first = np.isclose(outs[0][:, 0], outs[1][:, 0], rtol=1e-3, atol=1e-4).all(axis=1)
+    assert first.mean() >= 0.9, f"first kept draw: only {first.mean():.3f} of chains agree between the layouts"
+    ok = np.isclose(outs[0], outs[1], rtol=1e-3, atol=1e-4).all(axis=(1, 2))
+    assert ok.mean() >= 0.6, f"only {ok.mean():.3f} of chains agree between the layouts"
+    np.testing.assert_allclose(eps[0][ok], eps[1][ok], rtol=1e-2)
+    assert abs(grads[0] - grads[1]) <= 0.2 * grads[0]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_native_nuts_distribution_and_adaptation(mm, layout):
     """Native Philox path on the golden Gaussian: posterior moments within Monte-Carlo error, step size
     adapted so that the acceptance statistic approaches the target, Rhat ~ 1 (device stats)."""
     chains = 2048
     rng = np.random.default_rng(0)
     init = rng.normal(size=(chains, 2)).astype(np.float32)
     s = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8, scalar_dtype="f32").set_seed(11)
+    s.set_layout(layout)
     sample, stats = s.run_progress(200, 200)
     x = sample.cpu().numpy().reshape(-1, 2).astype(np.float64)
     assert np.abs(x.mean(axis=0) - [1.0, 2.0]).max() < 0.05
@@ -126,10 +162,12 @@ def test_native_nuts_distribution_and_adaptation(mm):
     c = s.counters()
     assert c["n_transitions"] == chains * 400 and sum(c["depth_hist"]) == chains * 400
     # GPU-count invariance: two shards with chain offsets reproduce the same draws
-    a = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[:1000], 0.8).set_seed(11)
-    b = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[1000:], 0.8).set_seed(11).set_chain_offset(1000)
+    # (the split is not a multiple of the chains per warp: a chain's draws do not depend on its neighbours in the warp)
+    a = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[:1003], 0.8).set_seed(11).set_layout(layout)
+    b = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init[1003:], 0.8).set_seed(11).set_chain_offset(1003)
+    b.set_layout(layout)
     both = np.concatenate([a.run_device(20, 20).cpu().numpy(), b.run_device(20, 20).cpu().numpy()])
-    full = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8).set_seed(11)
+    full = mm.NUTS(mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]]), init, 0.8).set_seed(11).set_layout(layout)
     np.testing.assert_array_equal(both, full.run_device(20, 20).cpu().numpy())
 
 
