@@ -36,6 +36,7 @@ int sm_count();
 // Exact: round-to-nearest intrinsics that are never contracted, so a replayed trajectory reproduces
 //        the CPU arithmetic (Rust never fuses) operation by operation.
 struct Fast {
+    static constexpr bool kContract = true;
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
@@ -43,6 +44,7 @@ struct Fast {
     static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
 };
 struct Exact {
+    static constexpr bool kContract = false;
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }

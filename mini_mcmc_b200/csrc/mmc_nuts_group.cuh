@@ -17,20 +17,34 @@
 //   * the binary-counter merge walk visits level l for every leaf: groups still carrying a valid subtree merge at the
 //     set bits of the leaf index and park at the first clear bit; a failed subtree keeps merging at all set bits and
 //     passes through the clear ones - exactly the RNG consumption and alpha / n_alpha sums of the recursion.
-// Direction: the edge being extended is swapped into the "plus" registers for the doubling (the U-turn test
-// (x+ - x-).p- >= 0 && (x+ - x-).p+ >= 0 is symmetric in the two momenta, and -(a - b) == b - a exactly).
+// Registers hold only the edge being extended (x, p, grad), the subtree proposal and, during a merge walk, the first
+// leaf of the subtree; the opposite edge and the current position are parked in per-lane shared-memory columns and
+// swapped in when a group changes direction (the U-turn test (x+ - x-).p- >= 0 && (x+ - x-).p+ >= 0 is symmetric in
+// the two momenta, and -(a - b) == b - a exactly, so it is evaluated as "extended edge vs the other state").
+// Leaves are built in pairs: the level-0 merge of the binary counter happens in registers, only levels >= 1 are
+// parked (levels 1..kGrpSmemLevels in shared memory, deeper ones in an L2-resident scratch).
 #pragma once
 
+#include "mmc_hmc_pair.cuh"  // F2: packed f32x2 helpers
 #include "mmc_nuts.cuh"
 
 namespace mmc {
 
 #ifndef MMC_NUTS_GROUP_MIN_BLOCKS
-#define MMC_NUTS_GROUP_MIN_BLOCKS 2   // <= 255 registers at E = 13 (ten E-vectors live in registers)
+#define MMC_NUTS_GROUP_MIN_BLOCKS 3   // <= 168 registers: 12 warps / SM
+#endif
+#ifndef MMC_NUTS_GROUP_SMEM_LEVELS
+#define MMC_NUTS_GROUP_SMEM_LEVELS 2  // (4 + 3 x 2) parked vectors of 32 E floats per warp: 200 KB / SM at E = 13, 12 warps
 #endif
 constexpr int kGrpWarps = 4;
-constexpr int kGrpSmemLevels = 3;
+constexpr int kGrpSmemLevels = MMC_NUTS_GROUP_SMEM_LEVELS;
 constexpr int kGrpMaxLevels = 16;
+
+// the uniform refill (one Philox block per 2 G draws) is kept out of line: inlined at every draw site it would add
+// ~75 rarely executed instructions to a hot loop whose instruction-cache footprint is what limits its issue rate
+static __device__ __noinline__ uint4 philox_block_call(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    return philox4x32_10(make_uint2(k0, k1), make_uint4(c0, c1, c2, c3));
+}
 
 template <class A, int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -48,6 +62,9 @@ __device__ __forceinline__ void group_sum2(float &a, float &b) {
         b = A::add(b, tb);
     }
 }
+// four interleaved partial sums keep the dependent chain of an E-term accumulation at E / 4 operations
+template <class A>
+__device__ __forceinline__ float fold4(const float (&s)[4]) { return A::add(A::add(s[0], s[1]), A::add(s[2], s[3])); }
 
 // ---------------------------------------------------------------- group-form targets
 // interface: float logp_grad(const float (&x)[E], float (&g)[E], int gl) const; gl = lane inside the group, which
@@ -57,20 +74,21 @@ __device__ __forceinline__ void group_sum2(float &a, float &b) {
 template <class A, int E, int G>
 struct GRosenbrockND {
     static constexpr bool kPartial = true;
+    static constexpr bool kPacked = false;
     int D;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int gl) const {
         const float xn = __shfl_down_sync(kFull, x[0], 1, G);
+        const int nv = D - 1 - gl * E;  // elements e < nv of this lane have a successor (i + 1 < D)
         float t[E];
-        float acc = 0.0f;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const int i = gl * E + e;
-            const bool valid = i + 1 < D;
+            const bool valid = e < nv;
             const float xnext = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : xn;
             const float tt = valid ? cms<A>(xnext, x[e], x[e]) : 0.0f;
             const float u = valid ? A::sub(1.0f, x[e]) : 0.0f;
             t[e] = tt;
-            acc = A::add(acc, A::mad(A::mul(tt, tt), 100.0f, A::mul(u, u)));
+            acc[e & 3] = A::add(acc[e & 3], A::mad(A::mul(tt, tt), 100.0f, A::mul(u, u)));
             g[e] = A::mad(A::mul(400.0f, x[e]), tt, A::mul(2.0f, u));
         }
         float tprev = __shfl_up_sync(kFull, t[E - 1], 1, G);
@@ -80,7 +98,57 @@ struct GRosenbrockND {
             const float tp = e == 0 ? tprev : t[e == 0 ? 0 : e - 1];
             g[e] = A::add(A::mul(-200.0f, tp), g[e]);
         }
-        return -acc;
+        return -fold4<A>(acc);
+    }
+};
+
+// RosenbrockND on packed f32x2 pairs (throughput arithmetic only).  Lane layout "pair interleaved": array slot a of a
+// lane holds element gl E + (a >> 1) + (a & 1) E / 2, so that slots (2k, 2k+1) = elements (k, k + E/2) form one f32x2
+// register pair and the successor / predecessor pairs of the Rosenbrock stencil are the neighbouring pairs (one
+// repacked pair each at the ends).  Same formulas as GRosenbrockND with the products regrouped for FMA chains:
+// t' = mk (x_{i+1} - x_i^2), u' = mk (1 - x_i), g_i = (4 x_i)(100 t'_i) + 2 u'_i - 2 (100 t'_{i-1}); mk = 1 where the
+// element has a successor, else 0.
+template <int E, int G>
+struct GRosenbrockNDP {
+    static constexpr bool kPartial = true;
+    static constexpr bool kPacked = true;
+    static_assert(E % 2 == 0, "packed layout needs an even number of elements per lane");
+    int D;
+    __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int gl) const {
+        constexpr int H = E / 2;
+        const float nvf = (float)(D - 1 - gl * E);  // elements with offset < nv have a successor
+        const F2 one = f2_bcast(1.0f), c100 = f2_bcast(100.0f), c4 = f2_bcast(4.0f), cm2 = f2_bcast(-2.0f), cm1 = f2_bcast(-1.0f);
+        F2 X[H], T100[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) X[k] = f2_pack(x[2 * k], x[2 * k + 1]);
+        const float xn_lane = __shfl_down_sync(kFull, x[0], 1, G);  // element 0 of the next lane
+        F2 acc0 = f2_bcast(0.0f), acc1 = f2_bcast(0.0f);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const F2 XN = (k + 1 < H) ? X[(k + 1 < H) ? k + 1 : k] : f2_pack(x[1], xn_lane);
+            const F2 mk = f2_pack((float)k < nvf ? 1.0f : 0.0f, (float)(k + H) < nvf ? 1.0f : 0.0f);
+            const F2 nX = mul2(X[k], cm1);
+            const F2 T = mul2(fma2(nX, X[k], XN), mk);
+            const F2 U = fma2(nX, mk, mk);
+            T100[k] = mul2(T, c100);
+            if (k & 1) acc1 = fma2(T100[k], T, fma2(U, U, acc1));
+            else acc0 = fma2(T100[k], T, fma2(U, U, acc0));
+            const F2 Gk = fma2(mul2(X[k], c4), T100[k], add2(U, U));
+            f2_unpack(Gk, g[2 * k], g[2 * k + 1]);
+        }
+        float tl_lo, tl_hi;
+        f2_unpack(T100[H - 1], tl_lo, tl_hi);                // 100 t' of elements H - 1 and E - 1
+        float tprev = __shfl_up_sync(kFull, tl_hi, 1, G);     // last element of the previous lane
+        if (gl == 0) tprev = 0.0f;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const F2 TP = (k > 0) ? T100[(k > 0) ? k - 1 : 0] : f2_pack(tprev, tl_lo);
+            const F2 Gk = fma2(cm2, TP, f2_pack(g[2 * k], g[2 * k + 1]));
+            f2_unpack(Gk, g[2 * k], g[2 * k + 1]);
+        }
+        float a_lo, a_hi;
+        f2_unpack(add2(acc0, acc1), a_lo, a_hi);
+        return -(a_lo + a_hi);
     }
 };
 
@@ -88,15 +156,16 @@ struct GRosenbrockND {
 template <class A, int E, int G>
 struct GStdNormal {
     static constexpr bool kPartial = true;
+    static constexpr bool kPacked = false;
     int D;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int gl) const {
-        float acc = 0.0f;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            acc = A::mad(A::mul(x[e], x[e]), 0.5f, acc);
+            acc[e & 3] = A::mad(A::mul(x[e], x[e]), 0.5f, acc[e & 3]);
             g[e] = -x[e];
         }
-        return -acc;
+        return -fold4<A>(acc);
     }
 };
 
@@ -104,6 +173,7 @@ struct GStdNormal {
 template <class T, int E, int G>
 struct GSmall {
     static constexpr bool kPartial = false;
+    static constexpr bool kPacked = false;
     T t;
     __device__ __forceinline__ float logp_grad(const float (&x)[E], float (&g)[E], int gl) const {
         constexpr int K = T::kDim;
@@ -127,14 +197,22 @@ template <class Target, class A, class ST, int E, int G, bool kReplay>
 struct NutsGroup {
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "lanes per chain must be a power of two");
     static constexpr int NG = 32 / G;             // chains per warp
-    static constexpr int Q4 = (E + 3) / 4;        // float4 per lane and vector in the level stacks
-    static constexpr int kVec = Q4 * 4 * 32;      // floats of one parked vector of the whole warp
+    static constexpr int QF = E / 4, RM = E % 4;  // a parked vector: QF float4 slabs + RM float slabs, [slab][lane]
+    static constexpr int kVec = E * 32;           // floats of one parked vector of the whole warp
+    static constexpr int kParked = 4;             // opposite edge (x, p, grad) + current position
+    static constexpr bool kFusedKick = !kReplay && A::kContract;  // native throughput runs only
+    static constexpr bool kPk = Target::kPacked;  // pair-interleaved lane layout, f32x2 arithmetic (see GRosenbrockNDP)
+    static_assert(!kPk || (A::kContract && E % 2 == 0), "the packed layout exists for the throughput policy only");
+    // element offset inside the lane of array slot a
+    static __host__ __device__ constexpr int off(int a) { return kPk ? (a >> 1) + (a & 1) * (E / 2) : a; }
+    static constexpr int kWarpFloats = (kParked + 3 * kGrpSmemLevels) * kVec;
     static constexpr int kScalBytes = kGrpMaxLevels * NG * 16 + 32 * 4;  // per warp: (double alpha, int n, int n_alpha) per level and group + depth histogram
 
     const Target &tgt;
     const NutsParams &p;
     const int lane, gl, grp;
-    float *s_stack;      // shared: [kGrpSmemLevels][3][Q4][32] float4 of this warp; every lane only touches its own column
+    float *s_park;       // shared: [kParked] vectors of this warp; every lane only touches its own column
+    float *s_stack;      // shared: [kGrpSmemLevels][3] vectors (tree levels 1..kGrpSmemLevels)
     float *g_stack;      // global scratch for deeper levels, same layout
     double *s_a;         // [kGrpMaxLevels][NG]
     int *s_n, *s_na;
@@ -148,52 +226,63 @@ struct NutsGroup {
     int64_t cur_n = 0, cur_e = 0, cur_u = 0;
     uint32_t n_grad = 0, n_unif = 0;
 
-    __device__ NutsGroup(const Target &t, const NutsParams &pp, int ln, float *ss, float *gs, void *scal)
-        : tgt(t), p(pp), lane(ln), gl(ln % G), grp(ln / G), s_stack(ss), g_stack(gs) {
+    __device__ NutsGroup(const Target &t, const NutsParams &pp, int ln, float *warp_smem, float *gs, void *scal)
+        : tgt(t), p(pp), lane(ln), gl(ln % G), grp(ln / G), s_park(warp_smem), s_stack(warp_smem + kParked * kVec), g_stack(gs) {
         s_a = reinterpret_cast<double *>(scal);
         s_n = reinterpret_cast<int *>(s_a + kGrpMaxLevels * NG);
         s_na = s_n + kGrpMaxLevels * NG;
         ubatch = make_uint4(0, 0, 0, 0);
     }
 
-    // ---- parked subtree vectors (which: 0 = first-leaf x, 1 = first-leaf p, 2 = proposal)
-    __device__ __forceinline__ void load_level(int lvl, int which, float (&v)[E]) {
-        if (lvl < kGrpSmemLevels) {
-            const float4 *src = reinterpret_cast<const float4 *>(s_stack + (lvl * 3 + which) * kVec) + lane;
+    // ---- parked vectors: explicit shared / global paths so the compiler emits LDS/STS and LDG/STG
+    template <bool kGlobal>
+    __device__ __forceinline__ void load_vec(const float *base, float (&v)[E]) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(base) + lane;
 #pragma unroll
-            for (int k4 = 0; k4 < Q4; ++k4) {
-                const float4 t = src[k4 * 32];
-                if (4 * k4 + 0 < E) v[(4 * k4 + 0) % E] = t.x;
-                if (4 * k4 + 1 < E) v[(4 * k4 + 1) % E] = t.y;
-                if (4 * k4 + 2 < E) v[(4 * k4 + 2) % E] = t.z;
-                if (4 * k4 + 3 < E) v[(4 * k4 + 3) % E] = t.w;
-            }
-        } else {
-            const float4 *src = reinterpret_cast<const float4 *>(g_stack + ((lvl - kGrpSmemLevels) * 3 + which) * kVec) + lane;
+        for (int k4 = 0; k4 < QF; ++k4) {
+            const float4 t = kGlobal ? __ldcg(s4 + k4 * 32) : s4[k4 * 32];
+            v[(4 * k4 + 0) % E] = t.x; v[(4 * k4 + 1) % E] = t.y; v[(4 * k4 + 2) % E] = t.z; v[(4 * k4 + 3) % E] = t.w;
+        }
+        const float *s1 = base + QF * 128 + lane;
 #pragma unroll
-            for (int k4 = 0; k4 < Q4; ++k4) {
-                const float4 t = __ldcg(src + k4 * 32);
-                if (4 * k4 + 0 < E) v[(4 * k4 + 0) % E] = t.x;
-                if (4 * k4 + 1 < E) v[(4 * k4 + 1) % E] = t.y;
-                if (4 * k4 + 2 < E) v[(4 * k4 + 2) % E] = t.z;
-                if (4 * k4 + 3 < E) v[(4 * k4 + 3) % E] = t.w;
-            }
+        for (int r = 0; r < RM; ++r) v[(4 * QF + r) % E] = kGlobal ? __ldcg(s1 + r * 32) : s1[r * 32];
+    }
+    template <bool kGlobal>
+    __device__ __forceinline__ void store_vec(float *base, const float (&v)[E]) {
+        float4 *d4 = reinterpret_cast<float4 *>(base) + lane;
+#pragma unroll
+        for (int k4 = 0; k4 < QF; ++k4) {
+            const float4 t = make_float4(v[(4 * k4 + 0) % E], v[(4 * k4 + 1) % E], v[(4 * k4 + 2) % E], v[(4 * k4 + 3) % E]);
+            if (kGlobal) __stcg(d4 + k4 * 32, t); else d4[k4 * 32] = t;
+        }
+        float *d1 = base + QF * 128 + lane;
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+            if (kGlobal) __stcg(d1 + r * 32, v[(4 * QF + r) % E]); else d1[r * 32] = v[(4 * QF + r) % E];
         }
     }
+    // tree level lvl >= 1 (which: 0 = first-leaf x, 1 = first-leaf p, 2 = proposal)
+    __device__ __forceinline__ void load_level(int lvl, int which, float (&v)[E]) {
+        const int slot = lvl - 1;
+        if (slot < kGrpSmemLevels) load_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
+        else load_vec<true>(g_stack + ((slot - kGrpSmemLevels) * 3 + which) * kVec, v);
+    }
     __device__ __forceinline__ void store_level(int lvl, int which, const float (&v)[E]) {
-        float4 t[Q4];
+        const int slot = lvl - 1;
+        if (slot < kGrpSmemLevels) store_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
+        else store_vec<true>(g_stack + ((slot - kGrpSmemLevels) * 3 + which) * kVec, v);
+    }
+    // parked slots: 0..2 = opposite edge (x, p, grad), 3 = current position
+    __device__ __forceinline__ void load_parked(int which, float (&v)[E]) { load_vec<false>(s_park + which * kVec, v); }
+    __device__ __forceinline__ void store_parked(int which, const float (&v)[E]) { store_vec<false>(s_park + which * kVec, v); }
+    // exchange a working vector with its parked counterpart in the groups with `doit`
+    __device__ __forceinline__ void swap_parked(int which, float (&w)[E], bool doit) {
+        float t[E];
+        load_parked(which, t);
+        if (doit) {
+            store_parked(which, w);
 #pragma unroll
-        for (int k4 = 0; k4 < Q4; ++k4)
-            t[k4] = make_float4(v[(4 * k4 + 0) % E], (4 * k4 + 1 < E) ? v[(4 * k4 + 1) % E] : 0.0f,
-                                (4 * k4 + 2 < E) ? v[(4 * k4 + 2) % E] : 0.0f, (4 * k4 + 3 < E) ? v[(4 * k4 + 3) % E] : 0.0f);
-        if (lvl < kGrpSmemLevels) {
-            float4 *dst = reinterpret_cast<float4 *>(s_stack + (lvl * 3 + which) * kVec) + lane;
-#pragma unroll
-            for (int k4 = 0; k4 < Q4; ++k4) dst[k4 * 32] = t[k4];
-        } else {
-            float4 *dst = reinterpret_cast<float4 *>(g_stack + ((lvl - kGrpSmemLevels) * 3 + which) * kVec) + lane;
-#pragma unroll
-            for (int k4 = 0; k4 < Q4; ++k4) __stcg(dst + k4 * 32, t[k4]);
+            for (int k = 0; k < E; ++k) w[k] = t[k];
         }
     }
 
@@ -203,7 +292,7 @@ struct NutsGroup {
         if (kReplay) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int i = gl * E + e;
+                const int i = gl * E + off(e);
                 m[e] = i < p.D ? (float)p.normals[chain * p.cap_normals + cur_n + i] : 0.0f;
             }
             cur_n += p.D;
@@ -224,14 +313,16 @@ struct NutsGroup {
                 }
             }
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
+            for (int a = 0; a < E; ++a) {
+                constexpr int kN = NQ * 4;
+                const int e = off(a);
                 float v = nb[e];
                 if (E % 4 != 0) {
-                    if (r == 1) v = nb[(e + 1) % (NQ * 4)];
-                    if (r == 2) v = nb[(e + 2) % (NQ * 4)];
-                    if (r == 3) v = nb[(e + 3) % (NQ * 4)];
+                    if (r == 1) v = nb[(e + 1) % kN];
+                    if (r == 2) v = nb[(e + 2) % kN];
+                    if (r == 3) v = nb[(e + 3) % kN];
                 }
-                m[e] = (i0 + e < p.D) ? v : 0.0f;
+                m[a] = (i0 + e < p.D) ? v : 0.0f;
             }
         }
     }
@@ -245,8 +336,8 @@ struct NutsGroup {
         const uint32_t batch = q / (2 * G);  // G blocks = 2 G uniforms per refill, block b G + gl in lane gl
         const bool refill = take && batch != q_batch;
         if (__any_sync(kFull, refill)) {
-            const uint4 nb = philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step_word,
-                                                            kSubUnif + batch * G + (uint32_t)gl));
+            const uint4 nb = philox_block_call(p.key.x, p.key.y, (uint32_t)gchain, (uint32_t)(gchain >> 32), step_word,
+                                               kSubUnif + batch * G + (uint32_t)gl);
             if (refill) {
                 ubatch = nb;
                 q_batch = batch;
@@ -276,34 +367,84 @@ struct NutsGroup {
         if (f64 || sizeof(ST) == 8) return u53_half_open(lo, hw);
         return (double)u24_half_open(hw);
     }
-    __device__ __forceinline__ uint64_t draw_u53(bool take) {  // native mode only
+    // u < n'' / max(n' + n'', 1) in f64 (src/nuts.rs:910-911) for a merge of a parked half with n' = an and the later
+    // half with n'' = tn; consumes one uniform where `take`
+    __device__ __forceinline__ bool draw_take_later(int an, int tn, bool take) {
+        if (kReplay) {
+            const double u = draw_uniform(true, take);
+            if (tn == 0) return false;
+            if (an == 0) return u < 1.0;
+            return u < ((double)tn / (double)(an + tn));
+        }
+        // native draws are k 2^-53 with a 53-bit integer k: k (n' + n'') < n'' 2^53 is the same test evaluated exactly
+        // (the f64 quotient is rounded, which can only matter when u equals the rounded quotient itself)
         uint32_t lo, hw;
         next_words(take, lo, hw);
-        return (((uint64_t)hw << 32) | lo) >> 11;
+        const uint64_t k53 = (((uint64_t)hw << 32) | lo) >> 11;
+        return tn != 0 && (an == 0 || k53 * (uint64_t)(an + tn) < ((uint64_t)tn << 53));
     }
 
     // ---- leapfrog, src/nuts.rs:979-996 (in place); returns logp' (partial when Target::kPartial)
+    // p + (g e) 0.5 in the reference's operation order; the throughput policy folds it into one FMA with e / 2
+    static __device__ __forceinline__ float half_kick(float g, float e, float he, float m) {
+        if (kFusedKick) return fmaf(g, he, m);
+        return A::mad(A::mul(g, e), 0.5f, m);
+    }
     __device__ __forceinline__ float leapfrog(float (&x)[E], float (&m)[E], float (&g)[E], float e) {
+        const float he = 0.5f * e;
+        if constexpr (kPk) {
+            constexpr int H = E / 2;
+            const F2 e2 = f2_bcast(e), he2 = f2_bcast(he), half2 = f2_bcast(0.5f);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const F2 Gk = f2_pack(g[2 * k], g[2 * k + 1]);
+                F2 Mk = f2_pack(m[2 * k], m[2 * k + 1]);
+                Mk = kFusedKick ? fma2(Gk, he2, Mk) : fma2(mul2(Gk, e2), half2, Mk);
+                const F2 Xk = fma2(Mk, e2, f2_pack(x[2 * k], x[2 * k + 1]));
+                f2_unpack(Mk, m[2 * k], m[2 * k + 1]);
+                f2_unpack(Xk, x[2 * k], x[2 * k + 1]);
+            }
+            const float lp = tgt.logp_grad(x, g, gl);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const F2 Gk = f2_pack(g[2 * k], g[2 * k + 1]);
+                F2 Mk = f2_pack(m[2 * k], m[2 * k + 1]);
+                Mk = kFusedKick ? fma2(Gk, he2, Mk) : fma2(mul2(Gk, e2), half2, Mk);
+                f2_unpack(Mk, m[2 * k], m[2 * k + 1]);
+            }
+            return lp;
+        }
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-            m[k] = A::mad(A::mul(g[k], e), 0.5f, m[k]);
+            m[k] = half_kick(g[k], e, he, m[k]);
             x[k] = A::mad(m[k], e, x[k]);
         }
         const float lp = tgt.logp_grad(x, g, gl);
 #pragma unroll
-        for (int k = 0; k < E; ++k) m[k] = A::mad(A::mul(g[k], e), 0.5f, m[k]);
+        for (int k = 0; k < E; ++k) m[k] = half_kick(g[k], e, he, m[k]);
         return lp;
     }
-    __device__ __forceinline__ float sumsq(const float (&m)[E]) {
-        float s = 0.0f;
+    __device__ __forceinline__ float local_sumsq(const float (&m)[E]) {
+        if constexpr (kPk) {
+            F2 s0 = f2_bcast(0.0f), s1 = f2_bcast(0.0f);
 #pragma unroll
-        for (int k = 0; k < E; ++k) s = A::mad(m[k], m[k], s);
-        return group_sum<A, G>(s);
+            for (int k = 0; k < E / 2; ++k) {
+                const F2 Mk = f2_pack(m[2 * k], m[2 * k + 1]);
+                if (k & 1) s1 = fma2(Mk, Mk, s1); else s0 = fma2(Mk, Mk, s0);
+            }
+            float lo, hi;
+            f2_unpack(add2(s0, s1), lo, hi);
+            return lo + hi;
+        }
+        float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int k = 0; k < E; ++k) s[k & 3] = A::mad(m[k], m[k], s[k & 3]);
+        return fold4<A>(s);
     }
+    __device__ __forceinline__ float sumsq(const float (&m)[E]) { return group_sum<A, G>(local_sumsq(m)); }
+    // completes a target evaluation: full logp (lp_io) and sum m^2, one fused butterfly when logp is partial
     __device__ __forceinline__ float finish(float &lp_io, const float (&m)[E]) {
-        float s = 0.0f;
-#pragma unroll
-        for (int k = 0; k < E; ++k) s = A::mad(m[k], m[k], s);
+        float s = local_sumsq(m);
         if (Target::kPartial) group_sum2<A, G>(lp_io, s);
         else s = group_sum<A, G>(s);
         return s;
@@ -313,16 +454,33 @@ struct NutsGroup {
     // state (xo, po); plus: the extended edge is the plus side
     __device__ __forceinline__ bool keep_going(const float (&xw)[E], const float (&xo)[E], const float (&pw)[E],
                                                const float (&po)[E], bool plus) {
-        float dw = 0.0f, dt = 0.0f;
+        // the sign of (x+ - x-) is applied to the two sums instead of every term (negation commutes with rounding)
+        if constexpr (kPk) {
+            F2 w0 = f2_bcast(0.0f), w1 = f2_bcast(0.0f), t0 = f2_bcast(0.0f), t1 = f2_bcast(0.0f);
+#pragma unroll
+            for (int k = 0; k < E / 2; ++k) {
+                const F2 d = sub2(f2_pack(xw[2 * k], xw[2 * k + 1]), f2_pack(xo[2 * k], xo[2 * k + 1]));
+                const F2 PW = f2_pack(pw[2 * k], pw[2 * k + 1]), PO = f2_pack(po[2 * k], po[2 * k + 1]);
+                if (k & 1) { w1 = fma2(d, PW, w1); t1 = fma2(d, PO, t1); }
+                else { w0 = fma2(d, PW, w0); t0 = fma2(d, PO, t0); }
+            }
+            float a_lo, a_hi, b_lo, b_hi;
+            f2_unpack(add2(w0, w1), a_lo, a_hi);
+            f2_unpack(add2(t0, t1), b_lo, b_hi);
+            float a = a_lo + a_hi, b = b_lo + b_hi;
+            group_sum2<A, G>(a, b);
+            return plus ? (a >= 0.0f && b >= 0.0f) : (-a >= 0.0f && -b >= 0.0f);
+        }
+        float dw[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-            float diff = A::sub(xw[k], xo[k]);
-            diff = plus ? diff : -diff;
-            dw = A::mad(diff, pw[k], dw);
-            dt = A::mad(diff, po[k], dt);
+            const float diff = A::sub(xw[k], xo[k]);
+            dw[k & 3] = A::mad(diff, pw[k], dw[k & 3]);
+            dt[k & 3] = A::mad(diff, po[k], dt[k & 3]);
         }
-        group_sum2<A, G>(dw, dt);
-        return dw >= 0.0f && dt >= 0.0f;
+        float a = fold4<A>(dw), b = fold4<A>(dt);
+        group_sum2<A, G>(a, b);
+        return plus ? (a >= 0.0f && b >= 0.0f) : (-a >= 0.0f && -b >= 0.0f);
     }
     __device__ __forceinline__ bool group_all(bool ok) {
         const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
@@ -374,93 +532,121 @@ struct NutsGroup {
         return epsilon;
     }
 
+    // one leaf of a subtree (BuildTree base case, src/nuts.rs:780-826): a leapfrog for the groups with `act` (the
+    // others integrate with step size 0 and ignore the results), then n', s' and min(1, exp(joint - joint0))
+    __device__ __forceinline__ void leaf(float (&cx)[E], float (&cm)[E], float (&cg)[E], float veps, bool act, ST logu,
+                                         ST joint0, int &ln, bool &ls, ST &la) {
+        float lp = leapfrog(cx, cm, cg, act ? veps : 0.0f);
+        const float ss = finish(lp, cm);
+        const float joint_f = A::sub(lp, A::mul(ss, 0.5f));
+        const ST joint = (ST)(double)joint_f;
+        const ST ex = s_exp(joint - joint0);
+        ln = (logu < joint) ? 1 : 0;
+        ls = (logu - (ST)1000.0) < joint;
+        la = ((ST)1.0 < ex || ex != ex) ? (ST)1.0 : ex;  // T::min(1, e): NaN -> 1
+        if (act) ++n_grad;
+    }
+
     // One doubling = build_tree(edge, v, j), src/nuts.rs:764-946, iteratively, for the groups with `run`.
     // cx/cm/cg: the edge to extend (in) and the new edge (out).  For the `run` groups the outputs are the subtree
     // proposal (prop), n', s', alpha and n_alpha; other groups keep their scalars and never read their prop.
     __device__ void doubling(float (&cx)[E], float (&cm)[E], float (&cg)[E], bool plus, int j, ST logu, ST eps, ST joint0,
                              bool run, float (&prop)[E], int &n_out, bool &s_out, ST &alpha_out, int &nalpha_out) {
         const float veps = (float)(plus ? eps : -eps);
-        const uint32_t n_leaves = 1u << j;
-        float tfx[E], tfm[E];  // first leaf of the subtree currently being merged upward (its proposal: `prop`)
+        if (j == 0) {
+            int ln; bool ls; ST la;
+            leaf(cx, cm, cg, veps, run, logu, joint0, ln, ls, la);
+            if (run) {
 #pragma unroll
-        for (int k = 0; k < E; ++k) { tfx[k] = cx[k]; tfm[k] = cm[k]; }
+                for (int k = 0; k < E; ++k) prop[k] = cx[k];
+                n_out = ln; s_out = ls; alpha_out = la; nalpha_out = 1;
+            }
+            return;
+        }
+        const uint32_t n_pairs = 1u << (j - 1);
         int tn = 0, tna = 0;
         ST ta = (ST)0.0;
         bool ts = true;
         bool building = run;
-        for (uint32_t leaf = 0; leaf < n_leaves; ++leaf) {
-            float lp = leapfrog(cx, cm, cg, building ? veps : 0.0f);
-            const float ss = finish(lp, cm);
-            const float joint_f = A::sub(lp, A::mul(ss, 0.5f));
-            const ST joint = (ST)(double)joint_f;
-            const ST ex = s_exp(joint - joint0);
-            if (building) {
-                ++n_grad;
-                tn = (logu < joint) ? 1 : 0;
-                ts = (logu - (ST)1000.0) < joint;
-                ta = ((ST)1.0 < ex || ex != ex) ? (ST)1.0 : ex;  // T::min(1, e): NaN -> 1
-                tna = 1;
+        for (uint32_t pr = 0; pr < n_pairs; ++pr) {
+            // ---- leaves 2 pr and 2 pr + 1; their merge (level 0 of the binary counter) stays in registers
+            float tfx[E], tfm[E];  // first leaf of the subtree being merged upward (its proposal: prop)
+            const bool pending = building;  // groups that have to merge / park the subtree ending in this pair
+            {
+                int ln; bool ls; ST la;
+                leaf(cx, cm, cg, veps, pending, logu, joint0, ln, ls, la);
+                if (pending) { tn = ln; ts = ls; ta = la; tna = 1; }
 #pragma unroll
-                for (int k = 0; k < E; ++k) { tfx[k] = cx[k]; tfm[k] = cm[k]; prop[k] = cx[k]; }
+                for (int k = 0; k < E; ++k) { tfx[k] = cx[k]; tfm[k] = cm[k]; }
+                if (pending) {
+#pragma unroll
+                    for (int k = 0; k < E; ++k) prop[k] = cx[k];
+                }
             }
-            bool pending = building;  // this group still has to merge / park the subtree that ends in this leaf
-            for (int lvl = 0;; ++lvl) {
-                if (!__any_sync(kFull, pending)) break;
+            const bool second = pending && ts;  // a failed first leaf is returned unchanged (src/nuts.rs:858)
+            if (__any_sync(kFull, second)) {
+                int ln; bool ls; ST la;
+                leaf(cx, cm, cg, veps, second, logu, joint0, ln, ls, la);
+                const bool take_b = draw_take_later(tn, ln, second);
+                const bool kg = keep_going(cx, tfx, cm, tfm, plus);
+                if (second) {
+                    if (take_b) {
+#pragma unroll
+                        for (int k = 0; k < E; ++k) prop[k] = cx[k];
+                    }
+                    tn += ln;
+                    ta = ta + la;
+                    tna = 2;
+                    ts = ls && kg;  // s' = s'_1 && s'_2 && stop_criterion(minus, plus), s'_1 = true here
+                }
+            }
+            // ---- levels >= 1: merge at the set bits of the pair index, park at the first clear one
+            bool pend = pending;
+            for (int lvl = 1;; ++lvl) {
+                if (!__any_sync(kFull, pend)) break;
                 if (lvl == j) {  // merged through the top: the subtree of depth j is complete (or failed and fully unwound)
-                    if (pending) building = false;
+                    if (pend) building = false;
                     break;
                 }
-                if ((leaf >> lvl) & 1u) {
+                if ((pr >> (lvl - 1)) & 1u) {
                     // merge the parked first half A = stack[lvl] with the later half T
                     const int an = s_n[lvl * NG + grp], ana = s_na[lvl * NG + grp];
                     const ST aa = (ST)s_a[lvl * NG + grp];
-                    // u < n'' / max(n' + n'', 1) in f64 (src/nuts.rs:910-911)
-                    bool take_b;
-                    if (kReplay) {
-                        const double u = draw_uniform(true, pending);
-                        if (tn == 0) take_b = false;
-                        else if (an == 0) take_b = u < 1.0;
-                        else take_b = u < ((double)tn / (double)(an + tn));
-                    } else {
-                        // native draws are k 2^-53: k (n' + n'') < n'' 2^53 is the same test evaluated exactly
-                        const uint64_t k53 = draw_u53(pending);
-                        take_b = tn != 0 && (an == 0 || k53 * (uint64_t)(an + tn) < ((uint64_t)tn << 53));
-                    }
-                    float lx[E], lm[E];
-                    load_level(lvl, 0, lx);
-                    load_level(lvl, 1, lm);
-                    if (__any_sync(kFull, pending && !take_b)) {
+                    const bool take_b = draw_take_later(an, tn, pend);
+                    if (__any_sync(kFull, pend && !take_b)) {
                         float lprop[E];
                         load_level(lvl, 2, lprop);
-                        if (pending && !take_b) {
+                        if (pend && !take_b) {
 #pragma unroll
                             for (int k = 0; k < E; ++k) prop[k] = lprop[k];
                         }
                     }
-                    if (pending) {
-#pragma unroll
-                        for (int k = 0; k < E; ++k) { tfx[k] = lx[k]; tfm[k] = lm[k]; }
+                    // the first leaf is only read by groups that are still merging (a group that has parked or
+                    // finished never looks at tfx / tfm again), so it is loaded without a select
+                    load_level(lvl, 0, tfx);
+                    load_level(lvl, 1, tfm);
+                    if (pend) {
                         tn += an;
                         ta = aa + ta;
                         tna += ana;
                     }
                     // s' = s'_1 && s'_2 && stop_criterion(minus, plus); parked halves always have s' = true
-                    if (__any_sync(kFull, pending && ts)) {
+                    if (__any_sync(kFull, pend && ts)) {
                         const bool kg = keep_going(cx, tfx, cm, tfm, plus);
-                        if (pending && ts) ts = kg;
+                        if (pend && ts) ts = kg;
                     }
                 } else {
-                    // first half at this level: a valid subtree parks here and the group builds the next leaf;
+                    // first half at this level: a valid subtree parks here and the group builds the next pair;
                     // a failed one is returned unchanged by the parent (src/nuts.rs:858) and keeps unwinding
                     __syncwarp();  // every lane has consumed the previous occupant's scalars (WAR)
-                    if (pending && ts) {
+                    if (pend && ts) {
                         store_level(lvl, 0, tfx);
                         store_level(lvl, 1, tfm);
                         store_level(lvl, 2, prop);
                         if (gl == 0) { s_n[lvl * NG + grp] = tn; s_na[lvl * NG + grp] = tna; s_a[lvl * NG + grp] = (double)ta; }
                     }
                     __syncwarp();
-                    pending = pending && !ts;
+                    pend = pend && !ts;
                 }
             }
             if (!__any_sync(kFull, building)) break;
@@ -476,15 +662,14 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
     constexpr int NG = W::NG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G, grp = lane / G;
-    float *s_stack = nuts_smem + warp * kGrpSmemLevels * 3 * W::kVec;
     const int64_t warp_slot = (int64_t)blockIdx.x * kGrpWarps + warp;
     const int n_glob = p.max_depth > kGrpSmemLevels ? p.max_depth - kGrpSmemLevels : 0;
     float *g_stack = p.scratch + warp_slot * (int64_t)n_glob * 3 * W::kVec;
-    unsigned char *s_scal = reinterpret_cast<unsigned char *>(nuts_smem + kGrpWarps * kGrpSmemLevels * 3 * W::kVec) + warp * W::kScalBytes;
+    unsigned char *s_scal = reinterpret_cast<unsigned char *>(nuts_smem + kGrpWarps * W::kWarpFloats) + warp * W::kScalBytes;
     int *s_hist = reinterpret_cast<int *>(s_scal + kGrpMaxLevels * NG * 16);
     s_hist[lane] = 0;
     __syncwarp();
-    W w(tgt, p, lane, s_stack, g_stack, s_scal);
+    W w(tgt, p, lane, nuts_smem + warp * W::kWarpFloats, g_stack, s_scal);
     unsigned long long n_trans = 0, tot_grad = 0, tot_unif = 0;
 
     while (true) {
@@ -498,46 +683,48 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
         w.gchain = (uint64_t)(c + p.chain_offset);
         w.cur_n = w.cur_e = w.cur_u = 0;
 
-        float pos[E];
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-            const int i = gl * E + k;
-            pos[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
-        }
         double *st = p.state + c * 5;
         ST epsilon = (ST)st[0], epsilon_bar = (ST)st[1], h_bar = (ST)st[2], mu;
         long long m = (long long)st[4];
         const ST gamma = (ST)0.05, kappa = (ST)0.75, delta = (ST)p.target_accept;
         const long long t_0 = 10;
 
-        auto store_draw = [&](int64_t slot) {
+        auto store_row = [&](float *o, const float (&v)[E]) {
             if (!has) return;
-            float *o = p.out + (c * p.out_pitch + slot) * p.D;
 #pragma unroll
             for (int k = 0; k < E; ++k) {
-                const int i = gl * E + k;
-                if (i < p.D) o[i] = pos[k];
+                const int i = gl * E + W::off(k);
+                if (i < p.D) o[i] = v[k];
             }
         };
 
         // ---- init_chain, src/nuts.rs:528-545
-        if (p.resume) {
-            mu = (ST)st[3];
-        } else {
-            if (p.n_collect > 0) store_draw(0);
-            float m0[E];
-            w.step_word = 0;
-            w.q = 0; w.q_batch = 0xffffffffu;
-            w.draw_normals(m0);
-            ST d = epsilon + (ST)1.0;
-            if (d < (ST)0.0) d = -d;
-            const ST tiny = sizeof(ST) == 8 ? (ST)2.220446049250313e-16 : (ST)1.1920929e-07;
-            const bool need = has && d <= tiny;
-            if (__any_sync(kFull, need)) {
-                const ST found = w.find_reasonable_epsilon(pos, m0, need);
-                if (need) epsilon = found;
+        {
+            float pos[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const int i = gl * E + W::off(k);
+                pos[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
             }
-            mu = s_log((ST)10.0 * epsilon);
+            w.store_parked(3, pos);
+            if (p.resume) {
+                mu = (ST)st[3];
+            } else {
+                if (p.n_collect > 0) store_row(p.out + (c * p.out_pitch) * p.D, pos);
+                float m0[E];
+                w.step_word = 0;
+                w.q = 0; w.q_batch = 0xffffffffu;
+                w.draw_normals(m0);
+                ST d = epsilon + (ST)1.0;
+                if (d < (ST)0.0) d = -d;
+                const ST tiny = sizeof(ST) == 8 ? (ST)2.220446049250313e-16 : (ST)1.1920929e-07;
+                const bool need = has && d <= tiny;
+                if (__any_sync(kFull, need)) {
+                    const ST found = w.find_reasonable_epsilon(pos, m0, need);
+                    if (need) epsilon = found;
+                }
+                mu = s_log((ST)10.0 * epsilon);
+            }
         }
 
         const int64_t total = p.n_collect + p.n_discard;
@@ -547,60 +734,51 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
             m += 1;
             w.step_word = (uint32_t)m;
             w.q = 0; w.q_batch = 0xffffffffu;
-            float xm[E], pm[E], gm[E], xp[E], pp[E], gp[E];
-            w.draw_normals(pp);
-            float ulogp = tgt.logp_grad(pos, gp, gl);
+            float cx[E], cm[E], cg[E];  // the edge being extended; the opposite edge is parked in shared memory
+            w.load_parked(3, cx);
+            w.draw_normals(cm);
+            float ulogp = tgt.logp_grad(cx, cg, gl);
             if (has) ++w.n_grad;
-            const float ss0 = w.finish(ulogp, pp);
+            const float ss0 = w.finish(ulogp, cm);
             const float joint_f = A::sub(ulogp, A::mul(ss0, 0.5f));
             const ST joint = (ST)(double)joint_f;
             const ST logu = joint - w.draw_exp1();
-#pragma unroll
-            for (int k = 0; k < E; ++k) {
-                xm[k] = xp[k] = pos[k];
-                pm[k] = pp[k];
-                gm[k] = gp[k];
-            }
+            w.store_parked(0, cx);
+            w.store_parked(1, cm);
+            w.store_parked(2, cg);
             int j = 0;          // warp-uniform: every group still in its transition has done j doublings
             int depth = 0;      // this group's number of doublings
             int n = 1;
             bool s = has;
+            bool side = true;   // which edge the working registers hold (both edges coincide before the first doubling)
             ST alpha = (ST)0.0;
             int n_alpha = 0;
             while (__any_sync(kFull, s)) {
                 const ST u1 = (ST)w.draw_uniform(false, s);
                 const bool plus = u1 < (ST)0.5;
-                if (!plus) {  // extend the minus edge: bring it into the working registers
-#pragma unroll
-                    for (int k = 0; k < E; ++k) {
-                        float t;
-                        t = xm[k]; xm[k] = xp[k]; xp[k] = t;
-                        t = pm[k]; pm[k] = pp[k]; pp[k] = t;
-                        t = gm[k]; gm[k] = gp[k]; gp[k] = t;
+                if (j > 0) {  // change of direction: exchange the working edge with the parked one
+                    const bool turn = s && plus != side;
+                    if (__any_sync(kFull, turn)) {
+                        w.swap_parked(0, cx, turn);
+                        w.swap_parked(1, cm, turn);
+                        w.swap_parked(2, cg, turn);
                     }
                 }
+                if (s) side = plus;
                 float prop[E];
-#pragma unroll
-                for (int k = 0; k < E; ++k) prop[k] = pos[k];
                 int n_prime = 0;
                 bool s_prime = false;
-                w.doubling(xp, pp, gp, plus, j, logu, epsilon, joint, s, prop, n_prime, s_prime, alpha, n_alpha);
+                w.doubling(cx, cm, cg, side, j, logu, epsilon, joint, s, prop, n_prime, s_prime, alpha, n_alpha);
                 const ST ratio = (ST)n_prime / (ST)n;
                 const ST tmp = ((ST)1.0 < ratio) ? (ST)1.0 : ratio;
                 const ST u2 = (ST)w.draw_uniform(false, s);
-                if (s && s_prime && (u2 < tmp)) {
-#pragma unroll
-                    for (int k = 0; k < E; ++k) pos[k] = prop[k];
-                }
-                const bool kg = w.keep_going(xp, xm, pp, pm, plus);
-                if (!plus) {
-#pragma unroll
-                    for (int k = 0; k < E; ++k) {
-                        float t;
-                        t = xm[k]; xm[k] = xp[k]; xp[k] = t;
-                        t = pm[k]; pm[k] = pp[k]; pp[k] = t;
-                        t = gm[k]; gm[k] = gp[k]; gp[k] = t;
-                    }
+                if (s && s_prime && (u2 < tmp)) w.store_parked(3, prop);
+                bool kg;
+                {
+                    float ox[E], om[E];
+                    w.load_parked(0, ox);
+                    w.load_parked(1, om);
+                    kg = w.keep_going(cx, ox, cm, om, side);
                 }
                 j += 1;
                 if (s) {
@@ -622,19 +800,21 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
             } else {
                 epsilon = epsilon_bar;
             }
-            if (it >= p.n_discard) store_draw(it - p.n_discard);
+            if (it >= p.n_discard) {
+                float pos[E];
+                w.load_parked(3, pos);
+                store_row(p.out + (c * p.out_pitch + (it - p.n_discard)) * p.D, pos);
+            }
         }
-        if (has) {
-#pragma unroll
-            for (int k = 0; k < E; ++k) {
-                const int i = gl * E + k;
-                if (i < p.D) p.positions[c * p.D + i] = pos[k];
-            }
-            if (gl == 0) {
-                st[0] = (double)epsilon; st[1] = (double)epsilon_bar; st[2] = (double)h_bar; st[3] = (double)mu;
-                st[4] = (double)m;
-                tot_grad += w.n_grad; tot_unif += w.n_unif;
-            }
+        {
+            float pos[E];
+            w.load_parked(3, pos);
+            store_row(p.positions + c * p.D, pos);
+        }
+        if (has && gl == 0) {
+            st[0] = (double)epsilon; st[1] = (double)epsilon_bar; st[2] = (double)h_bar; st[3] = (double)mu;
+            st[4] = (double)m;
+            tot_grad += w.n_grad; tot_unif += w.n_unif;
         }
         w.n_grad = 0; w.n_unif = 0;
     }

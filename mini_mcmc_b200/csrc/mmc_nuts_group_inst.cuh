@@ -12,7 +12,7 @@ int nuts_group_launch_one(const Target &tgt, NutsParams p, int sm_count, int64_t
                           bool query_only, cudaStream_t stream) {
     using W = NutsGroup<Target, A, ST, E, G, kReplay>;
     auto kernel = nuts_group_kernel<Target, A, ST, E, G, kReplay>;
-    const size_t smem = (size_t)kGrpWarps * ((size_t)kGrpSmemLevels * 3 * W::kVec * sizeof(float) + W::kScalBytes);
+    const size_t smem = (size_t)kGrpWarps * ((size_t)W::kWarpFloats * sizeof(float) + W::kScalBytes);
     MMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGrpWarps * 32, smem));
@@ -62,7 +62,16 @@ int nuts_group_dispatch_target(const NutsLaunch &L, const NutsParams &p, int64_t
         if (t.dim <= 4) MMC_GROUP_LAUNCH(GRosenbrockND, 1, 4, {t.dim});
         if (t.dim <= 32) MMC_GROUP_LAUNCH(GRosenbrockND, 4, 8, {t.dim});
         if (t.dim <= 64) MMC_GROUP_LAUNCH(GRosenbrockND, 8, 8, {t.dim});
-        if (t.dim <= 104) MMC_GROUP_LAUNCH(GRosenbrockND, 13, 8, {t.dim});
+#ifdef MMC_NUTS_GROUP_TUNE_G16   // tuning builds: two chains per warp at D = 100
+        if constexpr (A::kContract) {
+            if (t.dim <= 128) return nuts_group_launch_one<GRosenbrockNDP<8, 16>, A, ST, 8, 16, kReplay>({t.dim}, p, L.sm_count, grid, scratch, query, s);
+        }
+#endif
+        if (t.dim <= 104) {
+            // throughput policy: packed f32x2 kernel, 14 elements (7 register pairs) per lane
+            if constexpr (A::kContract) return nuts_group_launch_one<GRosenbrockNDP<14, 8>, A, ST, 14, 8, kReplay>({t.dim}, p, L.sm_count, grid, scratch, query, s);
+            else MMC_GROUP_LAUNCH(GRosenbrockND, 13, 8, {t.dim});
+        }
         if (t.dim <= 128) MMC_GROUP_LAUNCH(GRosenbrockND, 8, 16, {t.dim});
         break;
     case MMC_T_STD_NORMAL:

@@ -215,6 +215,10 @@ if __name__ == "__main__":
     if "tracker" in which:
         tracker()
         run_progress_overhead()
+    if "nuts1" in which:   # group layout only (tuning builds: MMC_LIB_PATH)
+        print(os.environ.get("MMC_LIB_PATH", "default lib"))
+        nuts(layout=0)
+        nuts(chains=8192, layout=0)
     if "nuts2" in which:   # the two lane layouts side by side
         for layout in (32, 0):
             nuts(layout=layout)

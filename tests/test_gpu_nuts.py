@@ -120,6 +120,25 @@ def test_rosenbrock_nd_replay_matches_oracle(mm, D, layout):
     assert first.mean() >= 0.9
 
 
+@pytest.mark.parametrize("D", [70, 100])
+def test_packed_group_kernel_replay_matches_oracle(mm, D):
+    """Throughput arithmetic (set_exact(False)) on the group layout runs the packed f32x2 kernel for 64 < D <= 104
+    (pair-interleaved lanes, regrouped FMA chains): replaying the oracle's tapes must still reproduce its draws up to
+    f32 rounding amplified by the dynamics."""
+    rng = np.random.default_rng(D)
+    chains, n_collect, n_discard = 26, 6, 6
+    init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
+    rec = _record(oracle.rosenbrock_nd(D), init, 0.95, n_collect, n_discard, 3, progress=True, scalar_f32=True,
+                  max_depth=8, cap_unifs=40000)
+    s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=8).set_exact(False).set_layout(0)
+    got = s._run(n_collect, n_discard, 1, rec["tapes"], None)
+    assert s.lanes_per_chain == 8
+    first = np.isclose(got[:, 0], rec["out"][:, 0], rtol=1e-3, atol=1e-4).all(axis=1)
+    assert first.mean() >= 0.85, f"first kept draw: only {first.mean():.3f} of chains follow the oracle"
+    ok = np.isclose(got, rec["out"], rtol=1e-3, atol=1e-4).all(axis=(1, 2))
+    assert ok.mean() >= 0.6, f"only {ok.mean():.3f} of chains follow the oracle"
+
+
 @pytest.mark.parametrize("D", [2, 3, 10, 50, 100, 120])
 def test_native_layouts_share_the_philox_contract(mm, D):
     """The two kernels draw from the same Philox counters (minimcmc.h "RNG contract"), so a short native run gives the
