@@ -224,6 +224,11 @@ int mmc_nuts_set_out_pitch(mmc_nuts *h, int64_t pitch_steps); /* see mmc_mh_set_
  * per chain of the last launch. */
 int mmc_nuts_set_layout(mmc_nuts *h, int32_t lanes_per_chain);
 int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain);
+/* Load balancing of the several-chains-per-warp kernel: a native run is dispensed to the persistent warps in slices of
+ * slice_steps transitions per group of chains (state handed over through global memory), which evens out the tail
+ * when a shard holds only a few waves of chains.  -1 (default) = a sixteenth of the run (at least 16), 0 = whole runs.  The draws do
+ * not depend on the slicing. */
+int mmc_nuts_set_slicing(mmc_nuts *h, int64_t slice_steps);
 /* Splitting one run over several launches (run_progress in blocks): adapt_until = absolute step count m up to which
  * dual averaging adapts (-1 = the reference's rule `m <= n_discard` of each call, src/nuts.rs:681); resume = 1 makes
  * the following runs continue the chains without init_chain (src/nuts.rs:528-545), so that the blocks reproduce the

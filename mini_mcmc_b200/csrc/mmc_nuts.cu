@@ -26,6 +26,9 @@ struct mmc_nuts {
     unsigned long long *d_counters = nullptr;  // [8 + 32]
     float *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    int *d_flags = nullptr;    // group kernel: completed slices per group of chains
+    size_t flags_bytes = 0;
+    int64_t slice_steps = -1;  // -1: automatic (a sixteenth of the run, at least 16 transitions), 0: off
     cudaStream_t stream = nullptr;
     float *d_out = nullptr;
     size_t d_out_bytes = 0;
@@ -119,6 +122,12 @@ int mmc_nuts_set_layout(mmc_nuts *h, int32_t lanes_per_chain) {
     return MMC_OK;
 }
 
+int mmc_nuts_set_slicing(mmc_nuts *h, int64_t slice_steps) {
+    MMC_REQUIRE(h && slice_steps >= -1, "mmc_nuts_set_slicing: bad arguments");
+    h->slice_steps = slice_steps;
+    return MMC_OK;
+}
+
 int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain) {
     MMC_REQUIRE(h && lanes_per_chain, "mmc_nuts_get_layout: bad arguments");
     *lanes_per_chain = h->lanes_used;
@@ -180,7 +189,18 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     if (rc) return rc;
     if ((rc = grow(&h->d_scratch, &h->scratch_bytes, scratch_floats * sizeof(float) + 16))) return rc;
     p.scratch = h->d_scratch;
-    MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // next-chain ticket
+    if (group && !replay) {
+        // native runs of the group kernel are dispensed in slices of the run (replay cursors live in registers)
+        const int64_t n_iter = n_collect + n_discard;
+        int64_t slice = h->slice_steps >= 0 ? h->slice_steps : (n_iter + 15) / 16;
+        if (slice > 0 && slice < 16) slice = 16;
+        const size_t n_groups = (size_t)(h->chains + 32 / group_lanes - 1) / (32 / group_lanes);
+        if ((rc = grow(&h->d_flags, &h->flags_bytes, n_groups * sizeof(int)))) return rc;
+        MMC_CUDA(cudaMemsetAsync(h->d_flags, 0, n_groups * sizeof(int), s));
+        p.slice_steps = slice;
+        p.flags = h->d_flags;
+    }
+    MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // work-item ticket
     return dispatch(L, p, &grid, &scratch_floats, false, s);
 }
 
@@ -267,6 +287,7 @@ void mmc_nuts_destroy(mmc_nuts *h) {
     cudaFree(h->d_state);
     cudaFree(h->d_counters);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_flags);
     cudaFree(h->d_out);
     for (auto p : h->d_tape) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);

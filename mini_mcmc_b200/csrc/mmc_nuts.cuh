@@ -148,6 +148,10 @@ struct NutsParams {
     int64_t adapt_until;    // dual averaging adapts while m <= adapt_until (= n_discard in the reference, src/nuts.rs:681)
     int32_t progress, max_depth, D;
     int32_t resume;         // 1: continue a run split over several launches (skip init_chain, keep mu)
+    // group kernel only: a group's run is cut into slices of slice_steps iterations that are dispensed by the ticket
+    // counter (all groups' slice 0 first); flags[group] = number of completed slices (0 = slicing off)
+    int64_t slice_steps;
+    int *flags;
     double target_accept;
     uint2 key;
 };

@@ -22,7 +22,7 @@
 // swapped in when a group changes direction (the U-turn test (x+ - x-).p- >= 0 && (x+ - x-).p+ >= 0 is symmetric in
 // the two momenta, and -(a - b) == b - a exactly, so it is evaluated as "extended edge vs the other state").
 // Leaves are built in pairs: the level-0 merge of the binary counter happens in registers, only levels >= 1 are
-// parked (levels 1..kGrpSmemLevels in shared memory, deeper ones in an L2-resident scratch).
+// parked (levels 1..GrpTune<E>::kLevels in shared memory, deeper ones in an L2-resident scratch).
 #pragma once
 
 #include "mmc_hmc_pair.cuh"  // F2: packed f32x2 helpers
@@ -30,14 +30,15 @@
 
 namespace mmc {
 
-#ifndef MMC_NUTS_GROUP_MIN_BLOCKS
-#define MMC_NUTS_GROUP_MIN_BLOCKS 3   // <= 168 registers: 12 warps / SM
-#endif
-#ifndef MMC_NUTS_GROUP_SMEM_LEVELS
-#define MMC_NUTS_GROUP_SMEM_LEVELS 2  // (4 + 3 x 2) parked vectors of 32 E floats per warp: 200 KB / SM at E = 13, 12 warps
+// Occupancy per elements-per-lane E (tuning builds override both): wide lanes (E > 8) keep 168 registers = 12 warps / SM
+// and two tree levels in shared memory ((4 + 3 x 2) parked vectors of 32 E floats per warp: 215 KB / SM at E = 14);
+// narrow lanes fit 128 registers = 16 warps / SM with three levels.
+#ifdef MMC_NUTS_GROUP_MIN_BLOCKS
+template <int E> struct GrpTune { static constexpr int kMinBlocks = MMC_NUTS_GROUP_MIN_BLOCKS; static constexpr int kLevels = MMC_NUTS_GROUP_SMEM_LEVELS; };
+#else
+template <int E> struct GrpTune { static constexpr int kMinBlocks = E > 8 ? 3 : 4; static constexpr int kLevels = E > 8 ? 2 : 3; };
 #endif
 constexpr int kGrpWarps = 4;
-constexpr int kGrpSmemLevels = MMC_NUTS_GROUP_SMEM_LEVELS;
 constexpr int kGrpMaxLevels = 16;
 
 // the uniform refill (one Philox block per 2 G draws) is kept out of line: inlined at every draw site it would add
@@ -205,14 +206,15 @@ struct NutsGroup {
     static_assert(!kPk || (A::kContract && E % 2 == 0), "the packed layout exists for the throughput policy only");
     // element offset inside the lane of array slot a
     static __host__ __device__ constexpr int off(int a) { return kPk ? (a >> 1) + (a & 1) * (E / 2) : a; }
-    static constexpr int kWarpFloats = (kParked + 3 * kGrpSmemLevels) * kVec;
+    static constexpr int kL = GrpTune<E>::kLevels;  // tree levels 1..kL are parked in shared memory
+    static constexpr int kWarpFloats = (kParked + 3 * kL) * kVec;
     static constexpr int kScalBytes = kGrpMaxLevels * NG * 16 + 32 * 4;  // per warp: (double alpha, int n, int n_alpha) per level and group + depth histogram
 
     const Target &tgt;
     const NutsParams &p;
     const int lane, gl, grp;
     float *s_park;       // shared: [kParked] vectors of this warp; every lane only touches its own column
-    float *s_stack;      // shared: [kGrpSmemLevels][3] vectors (tree levels 1..kGrpSmemLevels)
+    float *s_stack;      // shared: [kL][3] vectors (tree levels 1..kL)
     float *g_stack;      // global scratch for deeper levels, same layout
     double *s_a;         // [kGrpMaxLevels][NG]
     int *s_n, *s_na;
@@ -264,13 +266,13 @@ struct NutsGroup {
     // tree level lvl >= 1 (which: 0 = first-leaf x, 1 = first-leaf p, 2 = proposal)
     __device__ __forceinline__ void load_level(int lvl, int which, float (&v)[E]) {
         const int slot = lvl - 1;
-        if (slot < kGrpSmemLevels) load_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
-        else load_vec<true>(g_stack + ((slot - kGrpSmemLevels) * 3 + which) * kVec, v);
+        if (slot < kL) load_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
+        else load_vec<true>(g_stack + ((slot - kL) * 3 + which) * kVec, v);
     }
     __device__ __forceinline__ void store_level(int lvl, int which, const float (&v)[E]) {
         const int slot = lvl - 1;
-        if (slot < kGrpSmemLevels) store_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
-        else store_vec<true>(g_stack + ((slot - kGrpSmemLevels) * 3 + which) * kVec, v);
+        if (slot < kL) store_vec<false>(s_stack + (slot * 3 + which) * kVec, v);
+        else store_vec<true>(g_stack + ((slot - kL) * 3 + which) * kVec, v);
     }
     // parked slots: 0..2 = opposite edge (x, p, grad), 3 = current position
     __device__ __forceinline__ void load_parked(int which, float (&v)[E]) { load_vec<false>(s_park + which * kVec, v); }
@@ -656,14 +658,14 @@ struct NutsGroup {
 };
 
 template <class Target, class A, class ST, int E, int G, bool kReplay>
-__global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nuts_group_kernel(const Target tgt, const NutsParams p) {
+__global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_group_kernel(const Target tgt, const NutsParams p) {
     extern __shared__ __align__(16) float nuts_smem[];
     using W = NutsGroup<Target, A, ST, E, G, kReplay>;
     constexpr int NG = W::NG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G, grp = lane / G;
     const int64_t warp_slot = (int64_t)blockIdx.x * kGrpWarps + warp;
-    const int n_glob = p.max_depth > kGrpSmemLevels ? p.max_depth - kGrpSmemLevels : 0;
+    const int n_glob = p.max_depth > W::kL ? p.max_depth - W::kL : 0;
     float *g_stack = p.scratch + warp_slot * (int64_t)n_glob * 3 * W::kVec;
     unsigned char *s_scal = reinterpret_cast<unsigned char *>(nuts_smem + kGrpWarps * W::kWarpFloats) + warp * W::kScalBytes;
     int *s_hist = reinterpret_cast<int *>(s_scal + kGrpMaxLevels * NG * 16);
@@ -672,11 +674,31 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
     W w(tgt, p, lane, nuts_smem + warp * W::kWarpFloats, g_stack, s_scal);
     unsigned long long n_trans = 0, tot_grad = 0, tot_unif = 0;
 
+    // Work items: (group of NG chains, slice of the run).  Tickets are dispensed in order, every group's slice k before
+    // any slice k + 1, so the warp that holds (g, k - 1) is always resident and a warp that draws (g, k) only has to
+    // wait for its completion flag.  Slicing evens out the tail: with G = 8 a C5 shard of 8,192 chains is just 1.15
+    // waves of whole-run tasks.
+    const int64_t total = p.n_collect + p.n_discard;
+    const int64_t first = (p.progress || p.resume) ? 0 : 1;
+    const int64_t n_groups = (p.chains + NG - 1) / NG;
+    const int64_t n_iter = total > first ? total - first : 0;
+    const int64_t slice_len = (p.slice_steps > 0 && p.slice_steps < n_iter) ? p.slice_steps : (n_iter > 0 ? n_iter : 1);
+    const int64_t n_slices = n_iter > 0 ? (n_iter + slice_len - 1) / slice_len : 1;
     while (true) {
-        long long c0 = 0;
-        if (lane == 0) c0 = (long long)atomicAdd(&p.counters[0], (unsigned long long)NG);
-        c0 = __shfl_sync(kFull, c0, 0);
-        if (c0 >= p.chains) break;
+        long long ticket = 0;
+        if (lane == 0) ticket = (long long)atomicAdd(&p.counters[0], 1ULL);
+        ticket = __shfl_sync(kFull, ticket, 0);
+        if (ticket >= n_groups * n_slices) break;
+        const int64_t slice = ticket / n_groups, group = ticket - slice * n_groups;
+        if (slice > 0) {
+            if (lane == 0) {
+                const volatile int *flag = p.flags + group;
+                while (*flag < (int)slice) __nanosleep(256);
+            }
+            __syncwarp();
+            __threadfence();  // acquire: the previous slice's positions / state (read with ld.cg below)
+        }
+        const long long c0 = group * NG;
         const bool has = c0 + grp < p.chains;
         const long long c = has ? c0 + grp : p.chains - 1;  // idle groups read the last chain and write nothing
         w.chain = c;
@@ -684,8 +706,9 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
         w.cur_n = w.cur_e = w.cur_u = 0;
 
         double *st = p.state + c * 5;
-        ST epsilon = (ST)st[0], epsilon_bar = (ST)st[1], h_bar = (ST)st[2], mu;
-        long long m = (long long)st[4];
+        ST epsilon = (ST)__ldcg(st + 0), epsilon_bar = (ST)__ldcg(st + 1), h_bar = (ST)__ldcg(st + 2), mu;
+        long long m = (long long)__ldcg(st + 4);
+        const bool resume = p.resume || slice > 0;
         const ST gamma = (ST)0.05, kappa = (ST)0.75, delta = (ST)p.target_accept;
         const long long t_0 = 10;
 
@@ -704,11 +727,11 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const int i = gl * E + W::off(k);
-                pos[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
+                pos[k] = i < p.D ? __ldcg(p.positions + c * p.D + i) : 0.0f;
             }
             w.store_parked(3, pos);
-            if (p.resume) {
-                mu = (ST)st[3];
+            if (resume) {
+                mu = (ST)__ldcg(st + 3);
             } else {
                 if (p.n_collect > 0) store_row(p.out + (c * p.out_pitch) * p.D, pos);
                 float m0[E];
@@ -727,9 +750,9 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
             }
         }
 
-        const int64_t total = p.n_collect + p.n_discard;
-        const int64_t first = (p.progress || p.resume) ? 0 : 1;
-        for (int64_t it = first; it < total; ++it) {
+        const int64_t it_begin = first + slice * slice_len;
+        const int64_t it_end = (n_iter > 0 && it_begin + slice_len < total) ? it_begin + slice_len : total;
+        for (int64_t it = it_begin; it < it_end; ++it) {
             // ---- NUTSChain::step, src/nuts.rs:550-691
             m += 1;
             w.step_word = (uint32_t)m;
@@ -817,6 +840,11 @@ __global__ void __launch_bounds__(kGrpWarps * 32, MMC_NUTS_GROUP_MIN_BLOCKS) nut
             tot_grad += w.n_grad; tot_unif += w.n_unif;
         }
         w.n_grad = 0; w.n_unif = 0;
+        if (n_slices > 1) {  // release: publish the slice
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(p.flags + group, (int)slice + 1);
+        }
     }
     if (gl == 0) {
         if (tot_grad) atomicAdd(&p.counters[1], tot_grad);

@@ -21,7 +21,7 @@ int nuts_group_launch_one(const Target &tgt, NutsParams p, int sm_count, int64_t
     const int64_t per_cta = (int64_t)kGrpWarps * W::NG;
     const int64_t need = (p.chains + per_cta - 1) / per_cta;
     if (grid > need) grid = need;
-    const int n_glob = p.max_depth > kGrpSmemLevels ? p.max_depth - kGrpSmemLevels : 0;
+    const int n_glob = p.max_depth > W::kL ? p.max_depth - W::kL : 0;
     *grid_out = grid;
     *scratch_floats = (size_t)grid * kGrpWarps * n_glob * 3 * W::kVec;
     if (query_only) return MMC_OK;
@@ -60,19 +60,29 @@ int nuts_group_dispatch_target(const NutsLaunch &L, const NutsParams &p, int64_t
     switch (t.kind) {
     case MMC_T_ROSENBROCK_ND:
         if (t.dim <= 4) MMC_GROUP_LAUNCH(GRosenbrockND, 1, 4, {t.dim});
+        // throughput policy above 4 dimensions: packed f32x2 kernels (E / 2 register pairs per lane)
+#define MMC_GROUP_LAUNCH_PACKED(E_, G_) \
+    return nuts_group_launch_one<GRosenbrockNDP<E_, G_>, A, ST, E_, G_, kReplay>({t.dim}, p, L.sm_count, grid, scratch, query, s)
+        if constexpr (A::kContract) {
+            if (t.dim <= 32) MMC_GROUP_LAUNCH_PACKED(4, 8);
+            if (t.dim <= 64) MMC_GROUP_LAUNCH_PACKED(8, 8);
+        }
         if (t.dim <= 32) MMC_GROUP_LAUNCH(GRosenbrockND, 4, 8, {t.dim});
         if (t.dim <= 64) MMC_GROUP_LAUNCH(GRosenbrockND, 8, 8, {t.dim});
 #ifdef MMC_NUTS_GROUP_TUNE_G16   // tuning builds: two chains per warp at D = 100
         if constexpr (A::kContract) {
-            if (t.dim <= 128) return nuts_group_launch_one<GRosenbrockNDP<8, 16>, A, ST, 8, 16, kReplay>({t.dim}, p, L.sm_count, grid, scratch, query, s);
+            if (t.dim <= 128) MMC_GROUP_LAUNCH_PACKED(8, 16);
         }
 #endif
         if (t.dim <= 104) {
-            // throughput policy: packed f32x2 kernel, 14 elements (7 register pairs) per lane
-            if constexpr (A::kContract) return nuts_group_launch_one<GRosenbrockNDP<14, 8>, A, ST, 14, 8, kReplay>({t.dim}, p, L.sm_count, grid, scratch, query, s);
+            if constexpr (A::kContract) MMC_GROUP_LAUNCH_PACKED(14, 8);
             else MMC_GROUP_LAUNCH(GRosenbrockND, 13, 8, {t.dim});
         }
-        if (t.dim <= 128) MMC_GROUP_LAUNCH(GRosenbrockND, 8, 16, {t.dim});
+        if (t.dim <= 128) {
+            if constexpr (A::kContract) MMC_GROUP_LAUNCH_PACKED(8, 16);
+            else MMC_GROUP_LAUNCH(GRosenbrockND, 8, 16, {t.dim});
+        }
+#undef MMC_GROUP_LAUNCH_PACKED
         break;
     case MMC_T_STD_NORMAL:
         if (t.dim <= 4) MMC_GROUP_LAUNCH(GStdNormal, 1, 4, {t.dim});

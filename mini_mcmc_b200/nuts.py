@@ -60,6 +60,12 @@ class NUTS:
         L.check(L.lib.mmc_nuts_set_layout(self._h, C.c_int32(lanes_per_chain)))
         return self
 
+    def set_slicing(self, slice_steps: int):
+        """Transitions per work item of the group kernel (-1 = a sixteenth of the run, 0 = whole runs); the draws do not
+        depend on it (mmc_nuts_set_slicing)."""
+        L.check(L.lib.mmc_nuts_set_slicing(self._h, C.c_int64(slice_steps)))
+        return self
+
     @property
     def lanes_per_chain(self) -> int:
         """Lanes per chain of the last launch (32 = one chain per warp)."""

@@ -120,11 +120,11 @@ def test_rosenbrock_nd_replay_matches_oracle(mm, D, layout):
     assert first.mean() >= 0.9
 
 
-@pytest.mark.parametrize("D", [70, 100])
+@pytest.mark.parametrize("D", [10, 50, 70, 100, 120])
 def test_packed_group_kernel_replay_matches_oracle(mm, D):
-    """Throughput arithmetic (set_exact(False)) on the group layout runs the packed f32x2 kernel for 64 < D <= 104
-    (pair-interleaved lanes, regrouped FMA chains): replaying the oracle's tapes must still reproduce its draws up to
-    f32 rounding amplified by the dynamics."""
+    """Throughput arithmetic (set_exact(False)) on the group layout runs the packed f32x2 kernels for D > 4
+    (pair-interleaved lanes 8 x 4, 8 x 8, 8 x 14, 16 x 8, regrouped FMA chains): replaying the oracle's tapes must still
+    reproduce its draws up to f32 rounding amplified by the dynamics."""
     rng = np.random.default_rng(D)
     chains, n_collect, n_discard = 26, 6, 6
     init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
@@ -132,7 +132,7 @@ def test_packed_group_kernel_replay_matches_oracle(mm, D):
                   max_depth=8, cap_unifs=40000)
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=8).set_exact(False).set_layout(0)
     got = s._run(n_collect, n_discard, 1, rec["tapes"], None)
-    assert s.lanes_per_chain == 8
+    assert s.lanes_per_chain == (16 if D > 104 else 8)
     first = np.isclose(got[:, 0], rec["out"][:, 0], rtol=1e-3, atol=1e-4).all(axis=1)
     assert first.mean() >= 0.85, f"first kept draw: only {first.mean():.3f} of chains follow the oracle"
     ok = np.isclose(got, rec["out"], rtol=1e-3, atol=1e-4).all(axis=(1, 2))
@@ -159,6 +159,28 @@ def test_native_layouts_share_the_philox_contract(mm, D):
     assert ok.mean() >= 0.6, f"only {ok.mean():.3f} of chains agree between the layouts"
     np.testing.assert_allclose(eps[0][ok], eps[1][ok], rtol=1e-2)
     assert abs(grads[0] - grads[1]) <= 0.2 * grads[0]
+
+
+@pytest.mark.parametrize("D", [2, 100])
+def test_sliced_runs_reproduce_whole_runs(mm, D):
+    """The group kernel hands a group of chains from warp to warp in slices of the run (mmc_nuts_set_slicing); draws,
+    adaptation state and counters must not depend on the slicing, in both step-count semantics."""
+    rng = np.random.default_rng(7 + D)
+    chains = 1500
+    init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
+    for progress in (True, False):
+        ref = None
+        for slicing in (0, 16, 23, -1):
+            s = mm.NUTS(mm.RosenbrockND(), init, 0.9, scalar_dtype="f32", max_depth=7).set_seed(3).set_slicing(slicing)
+            out = s.run_device(30, 37, progress=progress).cpu().numpy()
+            cur = (out, s.state(), s.positions, s.counters())
+            if ref is None:
+                ref = cur
+                continue
+            np.testing.assert_array_equal(cur[0], ref[0])
+            np.testing.assert_array_equal(cur[1], ref[1])
+            np.testing.assert_array_equal(cur[2], ref[2])
+            assert cur[3] == ref[3]
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
