@@ -63,6 +63,21 @@ __device__ __forceinline__ void group_sum2(float &a, float &b) {
         b = A::add(b, tb);
     }
 }
+// four independent sums in one butterfly: the shuffles of a step overlap instead of serialising
+template <class A, int G>
+__device__ __forceinline__ void group_sum4(float &a, float &b, float &c, float &d) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const float ta = __shfl_xor_sync(kFull, a, o);
+        const float tb = __shfl_xor_sync(kFull, b, o);
+        const float tc = __shfl_xor_sync(kFull, c, o);
+        const float td = __shfl_xor_sync(kFull, d, o);
+        a = A::add(a, ta);
+        b = A::add(b, tb);
+        c = A::add(c, tc);
+        d = A::add(d, td);
+    }
+}
 // four interleaved partial sums keep the dependent chain of an E-term accumulation at E / 4 operations
 template <class A>
 __device__ __forceinline__ float fold4(const float (&s)[4]) { return A::add(A::add(s[0], s[1]), A::add(s[2], s[3])); }
@@ -415,16 +430,17 @@ struct NutsGroup {
                 f2_unpack(Mk, m[2 * k], m[2 * k + 1]);
             }
             return lp;
-        }
+        } else {
 #pragma unroll
-        for (int k = 0; k < E; ++k) {
-            m[k] = half_kick(g[k], e, he, m[k]);
-            x[k] = A::mad(m[k], e, x[k]);
-        }
-        const float lp = tgt.logp_grad(x, g, gl);
+            for (int k = 0; k < E; ++k) {
+                m[k] = half_kick(g[k], e, he, m[k]);
+                x[k] = A::mad(m[k], e, x[k]);
+            }
+            const float lp = tgt.logp_grad(x, g, gl);
 #pragma unroll
-        for (int k = 0; k < E; ++k) m[k] = half_kick(g[k], e, he, m[k]);
-        return lp;
+            for (int k = 0; k < E; ++k) m[k] = half_kick(g[k], e, he, m[k]);
+            return lp;
+        }
     }
     __device__ __forceinline__ float local_sumsq(const float (&m)[E]) {
         if constexpr (kPk) {
@@ -437,11 +453,12 @@ struct NutsGroup {
             float lo, hi;
             f2_unpack(add2(s0, s1), lo, hi);
             return lo + hi;
-        }
-        float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        } else {
+            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int k = 0; k < E; ++k) s[k & 3] = A::mad(m[k], m[k], s[k & 3]);
-        return fold4<A>(s);
+            for (int k = 0; k < E; ++k) s[k & 3] = A::mad(m[k], m[k], s[k & 3]);
+            return fold4<A>(s);
+        }
     }
     __device__ __forceinline__ float sumsq(const float (&m)[E]) { return group_sum<A, G>(local_sumsq(m)); }
     // completes a target evaluation: full logp (lp_io) and sum m^2, one fused butterfly when logp is partial
@@ -456,7 +473,18 @@ struct NutsGroup {
     // state (xo, po); plus: the extended edge is the plus side
     __device__ __forceinline__ bool keep_going(const float (&xw)[E], const float (&xo)[E], const float (&pw)[E],
                                                const float (&po)[E], bool plus) {
-        // the sign of (x+ - x-) is applied to the two sums instead of every term (negation commutes with rounding)
+        float a, b;
+        local_turn(xw, xo, pw, po, a, b);
+        group_sum2<A, G>(a, b);
+        return turn_ok(a, b, plus);
+    }
+    // the sign of (x+ - x-) is applied to the two sums instead of every term (negation commutes with rounding)
+    static __device__ __forceinline__ bool turn_ok(float a, float b, bool plus) {
+        return plus ? (a >= 0.0f && b >= 0.0f) : (-a >= 0.0f && -b >= 0.0f);
+    }
+    // this lane's part of (xw - xo).pw and (xw - xo).po
+    __device__ __forceinline__ void local_turn(const float (&xw)[E], const float (&xo)[E], const float (&pw)[E],
+                                               const float (&po)[E], float &a, float &b) {
         if constexpr (kPk) {
             F2 w0 = f2_bcast(0.0f), w1 = f2_bcast(0.0f), t0 = f2_bcast(0.0f), t1 = f2_bcast(0.0f);
 #pragma unroll
@@ -469,20 +497,19 @@ struct NutsGroup {
             float a_lo, a_hi, b_lo, b_hi;
             f2_unpack(add2(w0, w1), a_lo, a_hi);
             f2_unpack(add2(t0, t1), b_lo, b_hi);
-            float a = a_lo + a_hi, b = b_lo + b_hi;
-            group_sum2<A, G>(a, b);
-            return plus ? (a >= 0.0f && b >= 0.0f) : (-a >= 0.0f && -b >= 0.0f);
-        }
-        float dw[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            a = a_lo + a_hi;
+            b = b_lo + b_hi;
+        } else {
+            float dw[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int k = 0; k < E; ++k) {
-            const float diff = A::sub(xw[k], xo[k]);
-            dw[k & 3] = A::mad(diff, pw[k], dw[k & 3]);
-            dt[k & 3] = A::mad(diff, po[k], dt[k & 3]);
+            for (int k = 0; k < E; ++k) {
+                const float diff = A::sub(xw[k], xo[k]);
+                dw[k & 3] = A::mad(diff, pw[k], dw[k & 3]);
+                dt[k & 3] = A::mad(diff, po[k], dt[k & 3]);
+            }
+            a = fold4<A>(dw);
+            b = fold4<A>(dt);
         }
-        float a = fold4<A>(dw), b = fold4<A>(dt);
-        group_sum2<A, G>(a, b);
-        return plus ? (a >= 0.0f && b >= 0.0f) : (-a >= 0.0f && -b >= 0.0f);
     }
     __device__ __forceinline__ bool group_all(bool ok) {
         const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
@@ -536,13 +563,38 @@ struct NutsGroup {
 
     // one leaf of a subtree (BuildTree base case, src/nuts.rs:780-826): a leapfrog for the groups with `act` (the
     // others integrate with step size 0 and ignore the results), then n', s' and min(1, exp(joint - joint0))
+    // min(1, exp(.)) only feeds the dual-averaging statistic: native throughput runs use the 2-instruction ex2 form
+    static __device__ __forceinline__ ST accept_exp(ST v) {
+        if constexpr (kFusedKick && sizeof(ST) == 4) return (ST)__expf((float)v);
+        else return s_exp(v);
+    }
     __device__ __forceinline__ void leaf(float (&cx)[E], float (&cm)[E], float (&cg)[E], float veps, bool act, ST logu,
                                          ST joint0, int &ln, bool &ls, ST &la) {
         float lp = leapfrog(cx, cm, cg, act ? veps : 0.0f);
         const float ss = finish(lp, cm);
+        leaf_scalars(lp, ss, act, logu, joint0, ln, ls, la);
+    }
+    // the second leaf of a pair: its energy sums and the U-turn sums against the pair's first leaf (fx, fm) share one
+    // butterfly; kg = stop_criterion between the two leaves
+    __device__ __forceinline__ void leaf_turn(float (&cx)[E], float (&cm)[E], float (&cg)[E], float veps, bool act, ST logu,
+                                              ST joint0, const float (&fx)[E], const float (&fm)[E], bool plus, int &ln,
+                                              bool &ls, ST &la, bool &kg) {
+        float lp = leapfrog(cx, cm, cg, act ? veps : 0.0f);
+        float ss = local_sumsq(cm), a, b;
+        local_turn(cx, fx, cm, fm, a, b);
+        if (Target::kPartial) {
+            group_sum4<A, G>(lp, ss, a, b);
+        } else {
+            group_sum2<A, G>(a, b);
+            ss = group_sum<A, G>(ss);
+        }
+        kg = turn_ok(a, b, plus);
+        leaf_scalars(lp, ss, act, logu, joint0, ln, ls, la);
+    }
+    __device__ __forceinline__ void leaf_scalars(float lp, float ss, bool act, ST logu, ST joint0, int &ln, bool &ls, ST &la) {
         const float joint_f = A::sub(lp, A::mul(ss, 0.5f));
         const ST joint = (ST)(double)joint_f;
-        const ST ex = s_exp(joint - joint0);
+        const ST ex = accept_exp(joint - joint0);
         ln = (logu < joint) ? 1 : 0;
         ls = (logu - (ST)1000.0) < joint;
         la = ((ST)1.0 < ex || ex != ex) ? (ST)1.0 : ex;  // T::min(1, e): NaN -> 1
@@ -586,11 +638,10 @@ struct NutsGroup {
                 }
             }
             const bool second = pending && ts;  // a failed first leaf is returned unchanged (src/nuts.rs:858)
-            if (__any_sync(kFull, second)) {
-                int ln; bool ls; ST la;
-                leaf(cx, cm, cg, veps, second, logu, joint0, ln, ls, la);
+            {
+                int ln; bool ls, kg; ST la;
+                leaf_turn(cx, cm, cg, veps, second, logu, joint0, tfx, tfm, plus, ln, ls, la, kg);
                 const bool take_b = draw_take_later(tn, ln, second);
-                const bool kg = keep_going(cx, tfx, cm, tfm, plus);
                 if (second) {
                     if (take_b) {
 #pragma unroll
@@ -615,7 +666,7 @@ struct NutsGroup {
                     const int an = s_n[lvl * NG + grp], ana = s_na[lvl * NG + grp];
                     const ST aa = (ST)s_a[lvl * NG + grp];
                     const bool take_b = draw_take_later(an, tn, pend);
-                    if (__any_sync(kFull, pend && !take_b)) {
+                    {
                         float lprop[E];
                         load_level(lvl, 2, lprop);
                         if (pend && !take_b) {
@@ -633,7 +684,7 @@ struct NutsGroup {
                         tna += ana;
                     }
                     // s' = s'_1 && s'_2 && stop_criterion(minus, plus); parked halves always have s' = true
-                    if (__any_sync(kFull, pend && ts)) {
+                    {
                         const bool kg = keep_going(cx, tfx, cm, tfm, plus);
                         if (pend && ts) ts = kg;
                     }

@@ -9,7 +9,8 @@ fn main() {
     let mut objs = vec![];
     for (src, fmad) in [
         ("mmc_core.cu", true), ("mmc_mh.cu", false), ("mmc_hmc.cu", true), ("mmc_nuts.cu", true),
-        ("mmc_nuts_fast.cu", true), ("mmc_nuts_exact.cu", false), ("mmc_stats.cu", true),
+        ("mmc_nuts_fast.cu", true), ("mmc_nuts_exact.cu", false), ("mmc_nuts_group_fast.cu", true),
+        ("mmc_nuts_group_exact.cu", false), ("mmc_stats.cu", true),
     ] {
         let obj = out.join(src).with_extension("o");
         let mut c = Command::new(&nvcc);

@@ -28,6 +28,10 @@ extern "C" {
     pub fn mmc_hmc_destroy(h: *mut mmc_hmc);
     pub fn mmc_nuts_create(h: *mut *mut mmc_nuts, t: *const mmc_target_desc, init: *const f32, chains: i64, dim: i32, target_accept: f64, scalar_dtype: i32, max_depth: i32) -> i32;
     pub fn mmc_nuts_set_seed(h: *mut mmc_nuts, seed: u64) -> i32;
+    // kernel layout (0 = automatic, 32 = one chain per warp) and work-item slicing; neither changes what is sampled
+    pub fn mmc_nuts_set_layout(h: *mut mmc_nuts, lanes_per_chain: i32) -> i32;
+    pub fn mmc_nuts_get_layout(h: *mut mmc_nuts, lanes_per_chain: *mut i32) -> i32;
+    pub fn mmc_nuts_set_slicing(h: *mut mmc_nuts, slice_steps: i64) -> i32;
     pub fn mmc_nuts_run(h: *mut mmc_nuts, n_collect: i64, n_discard: i64, progress: i32, out: *mut f32, replay: *const mmc_replay_nuts) -> i32;
     pub fn mmc_nuts_destroy(h: *mut mmc_nuts);
     pub fn mmc_split_rhat_ess(sample: *const f32, c: i64, n: i64, p: i64, rhat: *mut f32, ess: *mut f32) -> i32;

@@ -201,6 +201,7 @@ def c5(args):
          tflops_per_gpu=g[0].item() / WORLD * 2285 / ms / 1e9, stats_ms=stats_ms, ess_min=float(ess.min()),
          ess_per_s_sampling=float(ess.min()) / ms * 1e3, ess_per_s_incl_stats=float(ess.min()) / (ms + stats_ms) * 1e3,
          rhat_min=float(rhat.min()), rhat_max=float(rhat.max()), depth_hist=cnt["depth_hist"],
+         lanes_per_chain=s.lanes_per_chain,
          cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores, cpu_ess_per_s=cpu_ess,
          cpu_sample="2048 chains, same run_progress(400,400); ESS/s = min-ESS of those chains / their wall time")
 

@@ -148,6 +148,11 @@ static void test_nuts_run_and_run_progress() {
     EXPECT(plain.first.data == res.first.data, "run_progress draws depend on the block size");
     auto r = nuts2.run(10, 0);                                   // NUTS::run: slot 0 holds the starting position (src/nuts.rs:460)
     EXPECT(r.n_collect == 10, "shape");
+    EXPECT(nuts2.lanes_per_chain() == 4, "2-D targets run 8 chains per warp by default, got %d lanes per chain", nuts2.lanes_per_chain());
+    mmc::NUTS warp(mmc::target(MMC_T_ROSENBROCK_2D, 2, {1.0, 100.0}), init, 4, 2, 0.95);
+    auto w = warp.set_seed(42).set_layout(32).run_progress(50, 50);   // one chain per warp: same algorithm and counters
+    EXPECT(warp.lanes_per_chain() == 32, "layout 32");
+    for (float x : w.first.data) EXPECT(std::isfinite(x), "non-finite draw");
 }
 
 // src/stats.rs:810-834 ess_1: iid draws give ESS ~ chains * n and split-Rhat ~ 1
