@@ -183,6 +183,29 @@ def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32", layout
                           ess_per_s=float(ess.min()) / ms * 1e3, rhat_max=float(rhat.max()), rhat_min=float(rhat.min()))))
 
 
+def nuts_small(chains=1 << 20, layout=0, n_collect=100, n_discard=100):
+    """2-D target of the reference's golden tests: 8 chains per warp (group layout) vs one chain per warp."""
+    rng = np.random.default_rng(0)
+    init = rng.normal(size=(chains, 2)).astype(np.float32)
+    tgt = lambda: mm.DiffableGaussian2D([1.0, 2.0], [[1.0, 2.0], [2.0, 5.0]])
+    w = mm.NUTS(tgt(), init[:4096], 0.8, scalar_dtype="f32").set_seed(1).set_layout(layout)
+    w.run_device(10, 10)
+    s = mm.NUTS(tgt(), init, 0.8, scalar_dtype="f32").set_seed(11).set_layout(layout)
+    out = torch.empty((chains, n_collect, 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    s.run_device(n_collect, n_discard, progress=True, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    c = s.counters()
+    x = out[:, -1].double()
+    print(json.dumps(dict(k="nuts_gauss2d", chains=chains, lanes_per_chain=s.lanes_per_chain, ms=ms, n_grad=c["n_grad"],
+                          grad_evals_per_s=c["n_grad"] / ms * 1e3, transitions_per_s=c["n_transitions"] / ms * 1e3,
+                          mean=[float(v) for v in x.mean(0)], var=[float(v) for v in x.var(0)])))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["poisson", "hmc", "stats"]
     print(torch.cuda.get_device_name(0))
@@ -217,6 +240,11 @@ if __name__ == "__main__":
     if "tracker" in which:
         tracker()
         run_progress_overhead()
+    if "nuts_small" in which:
+        for layout in (32, 0):
+            nuts_small(layout=layout)
+            nuts(D=50, layout=layout)
+        nuts(scalar="f64", layout=0)
     if "nuts1" in which:   # group layout only (tuning builds: MMC_LIB_PATH)
         print(os.environ.get("MMC_LIB_PATH", "default lib"))
         nuts(layout=0)
