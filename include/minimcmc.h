@@ -226,9 +226,15 @@ int mmc_nuts_set_layout(mmc_nuts *h, int32_t lanes_per_chain);
 int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain);
 /* Load balancing of the several-chains-per-warp kernel: a native run is dispensed to the persistent warps in slices of
  * slice_steps transitions per group of chains (state handed over through global memory), which evens out the tail
- * when a shard holds only a few waves of chains.  -1 (default) = a sixteenth of the run (at least 16), 0 = whole runs.  The draws do
+ * when a shard holds only a few waves of chains.  -1 (default) = a sixteenth of the launch's iterations (at least 8), 0 = whole runs.  The draws do
  * not depend on the slicing. */
 int mmc_nuts_set_slicing(mmc_nuts *h, int64_t slice_steps);
+/* Lock-step efficiency of the several-chains-per-warp kernel (opt-in experiment): a warp is as slow as its deepest tree,
+ * and tree depth follows the chain's adapted step size.  With mode = 1 a native run is cut into phases (iterations 32, 96,
+ * 224 and the end of the burn-in) and, between them, a device-side counting sort by log2(step size) re-forms the warps
+ * from chains of similar step size.  0 and -1 (default) = off: on the C5 benchmark the measured effect is within noise
+ * (DESIGN.md K4b).  The draws do not depend on the grouping. */
+int mmc_nuts_set_regroup(mmc_nuts *h, int32_t mode);
 /* Splitting one run over several launches (run_progress in blocks): adapt_until = absolute step count m up to which
  * dual averaging adapts (-1 = the reference's rule `m <= n_discard` of each call, src/nuts.rs:681); resume = 1 makes
  * the following runs continue the chains without init_chain (src/nuts.rs:528-545), so that the blocks reproduce the

@@ -173,6 +173,7 @@ class NUTS {
     // work-item slicing of the several-chains-per-warp kernel; neither changes what is sampled
     NUTS &set_layout(int lanes_per_chain) { check(mmc_nuts_set_layout(h_, lanes_per_chain)); return *this; }
     NUTS &set_slicing(int64_t slice_steps) { check(mmc_nuts_set_slicing(h_, slice_steps)); return *this; }
+    NUTS &set_regroup(int mode) { check(mmc_nuts_set_regroup(h_, mode)); return *this; }
     int lanes_per_chain() { int32_t n = 0; check(mmc_nuts_get_layout(h_, &n)); return n; }
     Sample<float> run(int64_t n_collect, int64_t n_discard) { return run_impl(n_collect, n_discard, 0); }
     // NUTS::run_progress, src/nuts.rs:194-338 (n_collect + n_discard steps)

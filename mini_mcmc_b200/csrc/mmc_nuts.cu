@@ -1,4 +1,5 @@
 // NUTS C ABI (see include/minimcmc.h) — host side of K4.
+#include <climits>
 #include <vector>
 
 #include "mmc_nuts_group_inst.cuh"
@@ -28,7 +29,10 @@ struct mmc_nuts {
     size_t scratch_bytes = 0;
     int *d_flags = nullptr;    // group kernel: completed slices per group of chains
     size_t flags_bytes = 0;
-    int64_t slice_steps = -1;  // -1: automatic (a sixteenth of the run, at least 16 transitions), 0: off
+    int64_t slice_steps = -1;  // -1: automatic (a sixteenth of the launch's iterations, at least 8), 0: off
+    int32_t regroup = -1;      // group kernel: re-form the warps' chain groups by step size between phases (1 = on; -1 / 0 = off)
+    int *d_perm = nullptr;     // [chains] chain order of the current phase, [chains] bin of every chain, [2 kRegroupBins] counts / offsets
+    size_t perm_bytes = 0;
     cudaStream_t stream = nullptr;
     float *d_out = nullptr;
     size_t d_out_bytes = 0;
@@ -49,6 +53,52 @@ int grow(T **ptr, size_t *cap, size_t need) {
     MMC_CUDA(cudaMalloc((void **)ptr, need));
     *cap = need;
     return MMC_OK;
+}
+
+// ---- regrouping of the group kernel's warps (lock-step efficiency)
+// The chains of a warp advance in lock step, so a warp is as slow as its deepest tree; tree depth is governed by the
+// chain's adapted step size (oracle study in DESIGN.md: corr(log eps, leapfrogs per chain) = -0.92; lock-step efficiency
+// 0.73 with index-ordered groups, 0.78-0.86 with groups of similar step size).  Between the phases of a run a counting
+// sort by log2(eps) (2,048 bins of 1/64 octave) builds the chain order of the next launch.  Draws do not depend on the
+// grouping (Philox is keyed by the global chain id), so the order inside a bin is left to the atomics.
+constexpr int kRegroupBins = 2048;
+
+__global__ void nuts_regroup_hist(const double *state, int64_t chains, int64_t adapt_until, int *hist, int *bin_of) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chains) return;
+    // the step size of the next transition: epsilon while dual averaging runs, epsilon_bar afterwards (src/nuts.rs:681-690)
+    const double m = state[c * 5 + 4];
+    const double eps = (m >= (double)adapt_until) ? state[c * 5 + 1] : state[c * 5 + 0];
+    int bin = 0;
+    if (eps > 0.0 && eps < 1e30) {
+        bin = (int)((log2f((float)eps) + 24.0f) * (kRegroupBins / 32.0f));
+        bin = bin < 0 ? 0 : (bin >= kRegroupBins ? kRegroupBins - 1 : bin);
+    }
+    bin_of[c] = bin;
+    atomicAdd(&hist[bin], 1);
+}
+
+__global__ void nuts_regroup_scan(const int *hist, int *offs) {  // one block of 1,024 threads, 2 bins each
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int a = hist[2 * t], b = hist[2 * t + 1];
+    part[t] = a + b;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const int base = part[t] - (a + b);
+    offs[2 * t] = base;
+    offs[2 * t + 1] = base + a;
+}
+
+__global__ void nuts_regroup_scatter(const int *bin_of, int64_t chains, int *offs, int *perm) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chains) return;
+    perm[atomicAdd(&offs[bin_of[c]], 1)] = (int)c;
 }
 
 }  // namespace
@@ -128,6 +178,12 @@ int mmc_nuts_set_slicing(mmc_nuts *h, int64_t slice_steps) {
     return MMC_OK;
 }
 
+int mmc_nuts_set_regroup(mmc_nuts *h, int32_t mode) {
+    MMC_REQUIRE(h && mode >= -1 && mode <= 1, "mmc_nuts_set_regroup: mode must be -1 (auto), 0 (off) or 1 (on)");
+    h->regroup = mode;
+    return MMC_OK;
+}
+
 int mmc_nuts_get_layout(mmc_nuts *h, int32_t *lanes_per_chain) {
     MMC_REQUIRE(h && lanes_per_chain, "mmc_nuts_get_layout: bad arguments");
     *lanes_per_chain = h->lanes_used;
@@ -176,6 +232,8 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     p.D = h->dim;
     p.target_accept = h->target_accept;
     p.key = seed_key(h->seed);
+    p.it_lo = 0;
+    p.it_hi = -1;  // the whole run unless the phased launches below narrow it
     NutsLaunch L{h->target, h->scalar_dtype == MMC_F64, replay, sm_count()};
     // several chains per warp wherever that layout is compiled in for the target, unless the caller pins the layout
     const int group_lanes = nuts_group_lanes(h->target);
@@ -189,19 +247,51 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     if (rc) return rc;
     if ((rc = grow(&h->d_scratch, &h->scratch_bytes, scratch_floats * sizeof(float) + 16))) return rc;
     p.scratch = h->d_scratch;
-    if (group && !replay) {
-        // native runs of the group kernel are dispensed in slices of the run (replay cursors live in registers)
-        const int64_t n_iter = n_collect + n_discard;
+    if (!(group && !replay)) {
+        MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // work-item ticket
+        return dispatch(L, p, &grid, &scratch_floats, false, s);
+    }
+    // Native runs of the group kernel.  The run is cut into phases (one launch each) at iterations 32, 96, 224 and at the
+    // end of the burn-in; from the second phase on the warps' groups are re-formed from chains of similar step size.
+    // Inside a launch the work is dispensed in slices (replay keeps single launches: its cursors live in registers).
+    const int chains_per_warp = 32 / group_lanes;
+    const size_t n_groups = (size_t)(h->chains + chains_per_warp - 1) / chains_per_warp;
+    if ((rc = grow(&h->d_flags, &h->flags_bytes, n_groups * sizeof(int)))) return rc;
+    const int64_t total = n_collect + n_discard, first = (progress || h->resume) ? 0 : 1;
+    const bool regroup = h->regroup > 0 && h->chains <= INT32_MAX;  // opt-in: measured neutral on C5
+    std::vector<int64_t> bounds{first};
+    if (regroup) {
+        for (int64_t b : {(int64_t)32, (int64_t)96, (int64_t)224, n_discard})
+            if (b >= bounds.back() + 16 && b + 16 <= total) bounds.push_back(b);
+        const size_t need = ((size_t)h->chains * 2 + 2 * kRegroupBins) * sizeof(int);
+        if (bounds.size() > 1 && (rc = grow(&h->d_perm, &h->perm_bytes, need))) return rc;
+    }
+    bounds.push_back(total > first ? total : first);
+    for (size_t w = 0; w + 1 < bounds.size(); ++w) {
+        const int64_t lo = bounds[w], hi = bounds[w + 1];
+        if (w > 0) {
+            if (hi <= lo) continue;
+            int *perm = h->d_perm, *bin_of = perm + h->chains, *hist = bin_of + h->chains, *offs = hist + kRegroupBins;
+            const unsigned blocks = (unsigned)((h->chains + 255) / 256);
+            MMC_CUDA(cudaMemsetAsync(hist, 0, kRegroupBins * sizeof(int), s));
+            nuts_regroup_hist<<<blocks, 256, 0, s>>>(h->d_state, h->chains, p.adapt_until, hist, bin_of);
+            nuts_regroup_scan<<<1, 1024, 0, s>>>(hist, offs);
+            nuts_regroup_scatter<<<blocks, 256, 0, s>>>(bin_of, h->chains, offs, perm);
+            MMC_CUDA(cudaGetLastError());
+            p.perm = perm;
+        }
+        const int64_t n_iter = hi - lo;
         int64_t slice = h->slice_steps >= 0 ? h->slice_steps : (n_iter + 15) / 16;
-        if (slice > 0 && slice < 16) slice = 16;
-        const size_t n_groups = (size_t)(h->chains + 32 / group_lanes - 1) / (32 / group_lanes);
-        if ((rc = grow(&h->d_flags, &h->flags_bytes, n_groups * sizeof(int)))) return rc;
-        MMC_CUDA(cudaMemsetAsync(h->d_flags, 0, n_groups * sizeof(int), s));
+        if (slice > 0 && slice < 8) slice = 8;
         p.slice_steps = slice;
         p.flags = h->d_flags;
+        p.it_lo = lo;
+        p.it_hi = w + 2 == bounds.size() ? -1 : hi;
+        MMC_CUDA(cudaMemsetAsync(h->d_flags, 0, n_groups * sizeof(int), s));
+        MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // work-item ticket
+        if ((rc = dispatch(L, p, &grid, &scratch_floats, false, s))) return rc;
     }
-    MMC_CUDA(cudaMemsetAsync(h->d_counters, 0, 8, s));  // work-item ticket
-    return dispatch(L, p, &grid, &scratch_floats, false, s);
+    return MMC_OK;
 }
 
 int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress, float *out_host,
@@ -288,6 +378,7 @@ void mmc_nuts_destroy(mmc_nuts *h) {
     cudaFree(h->d_counters);
     cudaFree(h->d_scratch);
     cudaFree(h->d_flags);
+    cudaFree(h->d_perm);
     cudaFree(h->d_out);
     for (auto p : h->d_tape) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -152,6 +152,10 @@ struct NutsParams {
     // counter (all groups' slice 0 first); flags[group] = number of completed slices (0 = slicing off)
     int64_t slice_steps;
     int *flags;
+    // group kernel only: this launch covers iterations [it_lo, it_hi) of the run (it_hi < 0: to the end) and takes the
+    // chains of its warps from perm (groups of similar step size, see mmc_nuts.cu; nullptr = index order)
+    int64_t it_lo, it_hi;
+    const int *perm;
     double target_accept;
     uint2 key;
 };

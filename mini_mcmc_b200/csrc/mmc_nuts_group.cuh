@@ -732,7 +732,9 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
     const int64_t total = p.n_collect + p.n_discard;
     const int64_t first = (p.progress || p.resume) ? 0 : 1;
     const int64_t n_groups = (p.chains + NG - 1) / NG;
-    const int64_t n_iter = total > first ? total - first : 0;
+    const int64_t it_lo = p.it_lo > first ? p.it_lo : first;                        // this launch: iterations [it_lo, it_hi)
+    const int64_t it_hi = (p.it_hi >= 0 && p.it_hi < total) ? p.it_hi : total;
+    const int64_t n_iter = it_hi > it_lo ? it_hi - it_lo : 0;
     const int64_t slice_len = (p.slice_steps > 0 && p.slice_steps < n_iter) ? p.slice_steps : (n_iter > 0 ? n_iter : 1);
     const int64_t n_slices = n_iter > 0 ? (n_iter + slice_len - 1) / slice_len : 1;
     while (true) {
@@ -751,7 +753,9 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
         }
         const long long c0 = group * NG;
         const bool has = c0 + grp < p.chains;
-        const long long c = has ? c0 + grp : p.chains - 1;  // idle groups read the last chain and write nothing
+        // idle groups read the last entry and write nothing
+        const long long ci = has ? c0 + grp : p.chains - 1;
+        const long long c = p.perm ? (long long)p.perm[ci] : ci;
         w.chain = c;
         w.gchain = (uint64_t)(c + p.chain_offset);
         w.cur_n = w.cur_e = w.cur_u = 0;
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
         double *st = p.state + c * 5;
         ST epsilon = (ST)__ldcg(st + 0), epsilon_bar = (ST)__ldcg(st + 1), h_bar = (ST)__ldcg(st + 2), mu;
         long long m = (long long)__ldcg(st + 4);
-        const bool resume = p.resume || slice > 0;
+        const bool resume = p.resume || slice > 0 || it_lo > first;
         const ST gamma = (ST)0.05, kappa = (ST)0.75, delta = (ST)p.target_accept;
         const long long t_0 = 10;
 
@@ -801,8 +805,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
             }
         }
 
-        const int64_t it_begin = first + slice * slice_len;
-        const int64_t it_end = (n_iter > 0 && it_begin + slice_len < total) ? it_begin + slice_len : total;
+        const int64_t it_begin = it_lo + slice * slice_len;
+        const int64_t it_end = (n_iter > 0 && it_begin + slice_len < it_hi) ? it_begin + slice_len : it_hi;
         for (int64_t it = it_begin; it < it_end; ++it) {
             // ---- NUTSChain::step, src/nuts.rs:550-691
             m += 1;

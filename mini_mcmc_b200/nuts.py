@@ -66,6 +66,12 @@ class NUTS:
         L.check(L.lib.mmc_nuts_set_slicing(self._h, C.c_int64(slice_steps)))
         return self
 
+    def set_regroup(self, mode: int):
+        """Re-form the warps of the group kernel from chains of similar step size between the phases of a run
+        (1 = on, 0 / -1 = off, the default); the draws do not depend on it (mmc_nuts_set_regroup)."""
+        L.check(L.lib.mmc_nuts_set_regroup(self._h, C.c_int32(mode)))
+        return self
+
     @property
     def lanes_per_chain(self) -> int:
         """Lanes per chain of the last launch (32 = one chain per warp)."""

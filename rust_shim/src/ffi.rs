@@ -32,6 +32,7 @@ extern "C" {
     pub fn mmc_nuts_set_layout(h: *mut mmc_nuts, lanes_per_chain: i32) -> i32;
     pub fn mmc_nuts_get_layout(h: *mut mmc_nuts, lanes_per_chain: *mut i32) -> i32;
     pub fn mmc_nuts_set_slicing(h: *mut mmc_nuts, slice_steps: i64) -> i32;
+    pub fn mmc_nuts_set_regroup(h: *mut mmc_nuts, mode: i32) -> i32;
     pub fn mmc_nuts_run(h: *mut mmc_nuts, n_collect: i64, n_discard: i64, progress: i32, out: *mut f32, replay: *const mmc_replay_nuts) -> i32;
     pub fn mmc_nuts_destroy(h: *mut mmc_nuts);
     pub fn mmc_split_rhat_ess(sample: *const f32, c: i64, n: i64, p: i64, rhat: *mut f32, ess: *mut f32) -> i32;

@@ -159,6 +159,8 @@ def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32", layout
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype=scalar, max_depth=10).set_seed(7).set_layout(layout)
     slicing = int(os.environ.get("MMC_NUTS_SLICING", "-1"))
     s.set_slicing(slicing)
+    regroup = int(os.environ.get("MMC_NUTS_REGROUP", "-1"))
+    s.set_regroup(regroup)
     out = torch.empty((chains, n_collect, D), dtype=torch.float32, device="cuda")
     w = mm.NUTS(mm.RosenbrockND(), init[:2048], 0.95, scalar_dtype=scalar, max_depth=10).set_seed(8).set_layout(layout)
     w.run_device(20, 20, progress=True)   # warm-up: module load, scratch allocation
@@ -176,7 +178,7 @@ def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32", layout
     rhat, ess = mm.split_rhat_mean_ess(out)
     torch.cuda.synchronize()
     stats_ms = (time.perf_counter() - t0) * 1e3
-    print(json.dumps(dict(k="nuts_rosen", chains=chains, D=D, scalar=scalar, lanes_per_chain=s.lanes_per_chain, slicing=slicing, ms=ms, n_grad=c["n_grad"],
+    print(json.dumps(dict(k="nuts_rosen", chains=chains, D=D, scalar=scalar, lanes_per_chain=s.lanes_per_chain, slicing=slicing, regroup=regroup, ms=ms, n_grad=c["n_grad"],
                           grad_evals_per_s=c["n_grad"] / ms * 1e3, transitions_per_s=c["n_transitions"] / ms * 1e3,
                           tflops=c["n_grad"] * 2285 / ms / 1e9, depth_hist=c["depth_hist"],
                           eps_median=float(np.median(st[:, 0])), stats_ms=stats_ms, ess_min=float(ess.min()),

@@ -163,16 +163,20 @@ def test_native_layouts_share_the_philox_contract(mm, D):
 
 @pytest.mark.parametrize("D", [2, 100])
 def test_sliced_runs_reproduce_whole_runs(mm, D):
-    """The group kernel hands a group of chains from warp to warp in slices of the run (mmc_nuts_set_slicing); draws,
-    adaptation state and counters must not depend on the slicing, in both step-count semantics."""
+    """The group kernel hands a group of chains from warp to warp in slices of the run (mmc_nuts_set_slicing) and re-forms
+    the groups between phases (mmc_nuts_set_regroup); draws, adaptation state and counters must not depend on either, in
+    both step-count semantics."""
     rng = np.random.default_rng(7 + D)
     chains = 1500
     init = (rng.normal(size=(chains, D)) * 0.3 + 0.5).astype(np.float32)
     for progress in (True, False):
         ref = None
-        for slicing in (0, 16, 23, -1):
+        # (slicing, regroup): regrouping cuts the run into phases at iterations 32, 96, 224 and the end of the burn-in
+        # and re-forms the warps from chains of similar step size (mmc_nuts_set_regroup)
+        for slicing, regroup in ((0, 0), (16, 0), (23, 0), (-1, 0), (-1, 1), (0, 1), (19, 1)):
             s = mm.NUTS(mm.RosenbrockND(), init, 0.9, scalar_dtype="f32", max_depth=7).set_seed(3).set_slicing(slicing)
-            out = s.run_device(30, 37, progress=progress).cpu().numpy()
+            s.set_regroup(regroup)
+            out = s.run_device(60, 120, progress=progress).cpu().numpy()
             cur = (out, s.state(), s.positions, s.counters())
             if ref is None:
                 ref = cur
