@@ -120,6 +120,31 @@ def host_mem_available_bytes():
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
+def other_configs(timeout_s: float = 300.0):
+    """BASELINE.json's other GPU-sized single-GPU configs, C3 (fused HMC, Rosenbrock-3D) and C5 (NUTS, D = 100, on-device
+    split-Rhat / ESS), measured by scripts/bench_configs.py in a CHILD process after this bench's own timed regions:
+    reported next to the headline (C2) so that the driver's run carries them too.  A failure of the child only shows
+    up as an "error" entry; it cannot touch the headline numbers."""
+    try:
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE")}
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py"), "--configs", "c3,c5", "--no-cpu"],
+                           capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+        out = {}
+        for ln in r.stdout.splitlines():
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                continue
+            if isinstance(d, dict) and "config" in d:
+                out[str(d["config"]).split()[0]] = d
+        if not out:
+            return {"error": ((r.stderr or "") + (r.stdout or ""))[-300:] or f"exit code {r.returncode}"}
+        return out
+    except Exception as e:  # noqa: BLE001  (never let the side measurement break the bench line)
+        return {"error": repr(e)[:300]}
+
+
 def run_reference_arm(args):
     """The reference's own CPU algorithm for this path (rayon over chains -> OpenMP over chains), oracle port,
     all host threads, on a bounded sample of the same workload."""
@@ -167,6 +192,7 @@ def main():
     ap.add_argument("--ref-chains", type=int, default=131072, help="chains in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C3 / C5 side measurements (child process)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -300,6 +326,11 @@ def main():
                         "sample": f"{sc} chains x {steps_per_run} steps (1/{CHAINS // sc} of the workload), "
                                   f"{dt:.1f} s of wall time"}
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        torch.cuda.empty_cache()
+        others = other_configs()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -311,6 +342,7 @@ def main():
                        "rng": "Philox4x32-10 keyed (seed, global chain, step)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "other_configs": others,
         }
         print(json.dumps(line), flush=True)
     if distributed:
