@@ -6,7 +6,8 @@
 // E consecutive vector elements per lane (G E >= D).  The tree bookkeeping of the warp kernel (merge walk, level
 // addressing, exp, uniform draws; about two thirds of its ~300 warp-instructions per leapfrog at D = 100) is issued
 // once per warp and therefore shared by 32 / G chains, the reductions are log2 G butterfly steps instead of five, and
-// with E = 13 at D = 100 all but 4 of the 104 element slots carry data (the warp kernel: 100 of 128).
+// at D = 100 a lane carries 13 (reference arithmetic) or 14 (packed f32x2 arithmetic) elements, so 100 of 104 / 112
+// element slots hold data (the warp kernel: 100 of 128).
 //
 // The chains of a warp advance in lock step, one transition at a time.  Control flow is warp-uniform (loops run
 // while ANY group of the warp still needs them, decided by votes) and every state update is predicated with the
@@ -14,15 +15,20 @@
 //   * a group whose transition has ended (U-turn, divergence, max depth) idles until the others end theirs;
 //   * inside a doubling a group that is not building (finished, or its subtree failed) integrates with step size 0,
 //     which leaves (x, p) untouched, and none of its results are committed;
-//   * the binary-counter merge walk visits level l for every leaf: groups still carrying a valid subtree merge at the
-//     set bits of the leaf index and park at the first clear bit; a failed subtree keeps merging at all set bits and
-//     passes through the clear ones - exactly the RNG consumption and alpha / n_alpha sums of the recursion.
+//   * the binary-counter merge walk visits the levels bottom-up after every pair of leaves: groups still carrying a
+//     valid subtree merge at the set bits of the leaf index and park at the first clear bit; a failed subtree keeps
+//     merging at all set bits and passes through the clear ones - exactly the RNG consumption and alpha / n_alpha sums
+//     of the recursion.
 // Registers hold only the edge being extended (x, p, grad), the subtree proposal and, during a merge walk, the first
 // leaf of the subtree; the opposite edge and the current position are parked in per-lane shared-memory columns and
 // swapped in when a group changes direction (the U-turn test (x+ - x-).p- >= 0 && (x+ - x-).p+ >= 0 is symmetric in
 // the two momenta, and -(a - b) == b - a exactly, so it is evaluated as "extended edge vs the other state").
 // Leaves are built in pairs: the level-0 merge of the binary counter happens in registers, only levels >= 1 are
 // parked (levels 1..GrpTune<E>::kLevels in shared memory, deeper ones in an L2-resident scratch).
+// Throughput arithmetic (policy Fast, D > 4) runs on packed f32x2 instructions over pair-interleaved lanes
+// (GRosenbrockNDP).  Native runs are dispensed to the persistent warps as (group of chains, slice of the run) tickets
+// with a completion flag per group, and a launch can be restricted to a window of iterations and take its groups
+// from a permutation of the chains (mmc_nuts_set_slicing / mmc_nuts_set_regroup, host side in mmc_nuts.cu).
 #pragma once
 
 #include "mmc_hmc_pair.cuh"  // F2: packed f32x2 helpers
