@@ -246,11 +246,29 @@ int mmc_nuts_run(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t prog
                  const mmc_replay_nuts *replay);
 int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t progress_semantics, float *out_dev,
                      const mmc_replay_nuts *replay_dev, void *stream);
-/* state_host [chains, 5] = epsilon, epsilon_bar, h_bar, mu, m */
+/* state_host [chains, 5] = epsilon, epsilon_bar, h_bar, mu, m (the pub fields of NUTSChain, src/nuts.rs:361-390) */
 int mmc_nuts_get_state(mmc_nuts *h, double *state_host);
+int mmc_nuts_set_state(mmc_nuts *h, const double *state_host);
 int mmc_nuts_get_positions(mmc_nuts *h, float *positions_host);
+int mmc_nuts_set_positions(mmc_nuts *h, const float *positions_host);   /* NUTSChain.position, src/nuts.rs:363 */
+/* Per-transition trace of the following runs (debug / parity): trace_dev [chains, pitch_steps, 8] f64, caller-owned
+ * device memory, row = iteration of the launch; columns joint_0, logu, n, alpha, n_alpha, tree depth, epsilon used,
+ * uniforms consumed (src/nuts.rs:550-691).  nullptr switches it off. */
+int mmc_nuts_set_trace_dev(mmc_nuts *h, double *trace_dev, int64_t pitch_steps);
+/* Known-answer entry for build_tree (src/nuts.rs:764-946; the reference's test_build_tree, :1057-1121): ONE doubling of
+ * depth j per chain from (the handle's positions, mom_host, grad_host) [chains, dim], scal_host [chains, 4] = logu, v
+ * (+1 / -1), epsilon, joint_0, and the tree's uniforms from unifs_host [chains, cap_unifs], on the kernel, arithmetic
+ * policy and lane layout the handle is set to.  out_vec_host [chains, 5, dim] = the new edge (position, momentum,
+ * gradient), position' and gradient(position'); out_scal_host [chains, 6] = logp(position'), n', s', alpha', n_alpha',
+ * uniforms consumed.  The opposite edge of the 13-tuple is the input, unchanged.  All chains share j. */
+int mmc_nuts_build_tree(mmc_nuts *h, const float *mom_host, const float *grad_host, const double *scal_host, int32_t j,
+                        const double *unifs_host, int64_t cap_unifs, float *out_vec_host, double *out_scal_host);
 /* counters summed over chains since creation: grad evals, transitions, tapes consumed (uniforms) and the
  * histogram of tree depths [max_depth + 1] */
+/* Debug entry: the tree-merge test "k 2^-53 < num / den" (src/nuts.rs:910-911 for a native 53-bit draw k) evaluated on
+ * the device for n triples (host arrays); out_host[i] = 0 / 1. */
+int mmc_debug_nuts_merge_test(const uint64_t *k53_host, const uint32_t *num_host, const uint32_t *den_host, int64_t n,
+                              uint8_t *out_host);
 int mmc_nuts_get_counters(mmc_nuts *h, int64_t *n_grad, int64_t *n_transitions, int64_t *depth_hist, int32_t hist_len);
 void mmc_nuts_destroy(mmc_nuts *h);
 

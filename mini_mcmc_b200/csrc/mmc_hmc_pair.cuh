@@ -45,7 +45,10 @@ struct RosenbrockND2 {
     }
 };
 
-template <class Target2>
+// kReplay: momenta / uniforms come from the caller's tapes (layout of hmc_run_kernel) instead of Philox; p.trace, when
+// set, receives (logp_cur, logp_prop, accept_logp, accepted) per (step, chain) exactly like the scalar kernel, so the
+// production kernel itself is held to the single-transition parity bar (tests/test_gpu_hmc.py).
+template <class Target2, bool kReplay>
 __global__ void __launch_bounds__(128) hmc_run_pair_kernel(const Target2 tgt, const HmcParams p) {
     constexpr int D = Target2::kDim;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,11 +65,21 @@ __global__ void __launch_bounds__(128) hmc_run_pair_kernel(const Target2 tgt, co
         const uint64_t g0 = (uint64_t)(c0 + p.chain_offset), g1 = (uint64_t)(c1 + p.chain_offset);
         for (int64_t s = 0; s < steps; ++s) {
             const uint32_t gstep = (uint32_t)(p.step_base + s);
-            float m0[D], m1[D];
-            philox_normals_f32<D>(p.key, g0, gstep, m0);
-            philox_normals_f32<D>(p.key, g1, gstep, m1);
-            const float u0 = u24_half_open(philox_scalar_words(p.key, g0, gstep).x);
-            const float u1 = u24_half_open(philox_scalar_words(p.key, g1, gstep).x);
+            float m0[D], m1[D], u0, u1;
+            if (kReplay) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    m0[i] = __ldg(p.momenta + (s * p.chains + c0) * D + i);
+                    m1[i] = __ldg(p.momenta + (s * p.chains + c1) * D + i);
+                }
+                u0 = __ldg(p.u + s * p.chains + c0);
+                u1 = __ldg(p.u + s * p.chains + c1);
+            } else {
+                philox_normals_f32<D>(p.key, g0, gstep, m0);
+                philox_normals_f32<D>(p.key, g1, gstep, m1);
+                u0 = u24_half_open(philox_scalar_words(p.key, g0, gstep).x);
+                u1 = u24_half_open(philox_scalar_words(p.key, g1, gstep).x);
+            }
             const F2 nlp_cur = tgt.neg_logp_grad(x, g);
             F2 ke = zero;
 #pragma unroll
@@ -105,6 +118,14 @@ __global__ void __launch_bounds__(128) hmc_run_pair_kernel(const Target2 tgt, co
             f2_unpack(sub2(h_cur, h_prop), a0, a1);
             const bool acc0 = a0 >= logf(u0), acc1 = a1 >= logf(u1);
             n_acc += (unsigned)acc0 + (unsigned)(acc1 && two);
+            if (kReplay && p.trace) {  // traces only exist for replay runs (mmc_hmc_run_dev)
+                float c_lo, c_hi, q_lo, q_hi;
+                f2_unpack(nlp_cur, c_lo, c_hi);
+                f2_unpack(nlp_prop, q_lo, q_hi);
+                float4 *tr = reinterpret_cast<float4 *>(p.trace) + s * p.chains;
+                tr[c0] = make_float4(-c_lo, -q_lo, a0, acc0 ? 1.0f : 0.0f);
+                if (two) tr[c1] = make_float4(-c_hi, -q_hi, a1, acc1 ? 1.0f : 0.0f);
+            }
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 float xl, xh, pl, ph;
@@ -137,10 +158,12 @@ __global__ void __launch_bounds__(128) hmc_run_pair_kernel(const Target2 tgt, co
 }
 
 template <class Target2>
-int launch_hmc_pair(const Target2 &tgt, const HmcParams &p, cudaStream_t stream) {
+int launch_hmc_pair(const Target2 &tgt, const HmcParams &p, bool replay, cudaStream_t stream) {
     const int block = 128;
     const int64_t threads = (p.chains + 1) / 2;
-    hmc_run_pair_kernel<Target2><<<(unsigned)((threads + block - 1) / block), block, 0, stream>>>(tgt, p);
+    const unsigned grid = (unsigned)((threads + block - 1) / block);
+    if (replay) hmc_run_pair_kernel<Target2, true><<<grid, block, 0, stream>>>(tgt, p);
+    else hmc_run_pair_kernel<Target2, false><<<grid, block, 0, stream>>>(tgt, p);
     MMC_CUDA(cudaGetLastError());
     return MMC_OK;
 }

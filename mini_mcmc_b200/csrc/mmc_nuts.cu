@@ -38,6 +38,8 @@ struct mmc_nuts {
     size_t d_out_bytes = 0;
     double *d_tape[3] = {nullptr, nullptr, nullptr};
     size_t d_tape_bytes[3] = {0, 0, 0};
+    double *trace_dev = nullptr;  // caller-owned per-transition trace of the next runs (mmc_nuts_set_trace_dev)
+    int64_t trace_pitch = 0;
 };
 
 namespace {
@@ -101,9 +103,37 @@ __global__ void nuts_regroup_scatter(const int *bin_of, int64_t chains, int *off
     perm[atomicAdd(&offs[bin_of[c]], 1)] = (int)c;
 }
 
+__global__ void nuts_merge_test_kernel(const uint64_t *k53, const uint32_t *num, const uint32_t *den, int64_t n, uint8_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = u53_below_ratio(k53[i], num[i], den[i]) ? 1 : 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Debug entry: evaluates the tree-merge acceptance test "k 2^-53 < num / den" (src/nuts.rs:910-911 with a native 53-bit
+// draw) on the device for n triples; tests/test_gpu_nuts.py checks it against exact integer arithmetic up to the tree
+// sizes of max_depth = 16.
+int mmc_debug_nuts_merge_test(const uint64_t *k53_host, const uint32_t *num_host, const uint32_t *den_host, int64_t n,
+                              uint8_t *out_host) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(k53_host && num_host && den_host && out_host && n > 0, "mmc_debug_nuts_merge_test: bad arguments");
+    unsigned char *d = nullptr;
+    MMC_CUDA(cudaMalloc((void **)&d, (size_t)n * 17));
+    uint64_t *dk = reinterpret_cast<uint64_t *>(d);
+    uint32_t *dn = reinterpret_cast<uint32_t *>(d + n * 8), *dd = dn + n;
+    uint8_t *dout = d + n * 16;
+    cudaMemcpy(dk, k53_host, (size_t)n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dn, num_host, (size_t)n * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dd, den_host, (size_t)n * 4, cudaMemcpyHostToDevice);
+    nuts_merge_test_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dk, dn, dd, n, dout);
+    const cudaError_t e = cudaMemcpy(out_host, dout, (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "mmc_debug_nuts_merge_test", __FILE__, __LINE__);
+    return MMC_OK;
+}
 
 int mmc_nuts_create(mmc_nuts **out, const mmc_target_desc *target, const float *init_host, int64_t chains,
                     int32_t dim, double target_accept_p, int32_t scalar_dtype, int32_t max_depth) {
@@ -234,6 +264,10 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     p.key = seed_key(h->seed);
     p.it_lo = 0;
     p.it_hi = -1;  // the whole run unless the phased launches below narrow it
+    p.trace = h->trace_dev;
+    p.trace_pitch = h->trace_pitch;
+    MMC_REQUIRE(!p.trace || p.trace_pitch >= n_collect + n_discard, "mmc_nuts_run_dev: trace pitch %lld < %lld iterations",
+                (long long)p.trace_pitch, (long long)(n_collect + n_discard));
     NutsLaunch L{h->target, h->scalar_dtype == MMC_F64, replay, sm_count()};
     // several chains per warp wherever that layout is compiled in for the target, unless the caller pins the layout
     const int group_lanes = nuts_group_lanes(h->target);
@@ -344,6 +378,92 @@ int mmc_nuts_run_progress(mmc_nuts *h, int64_t n_collect, int64_t n_discard, flo
     };
     auto discard = [&](int64_t k) { return mmc_nuts_run_dev(h, 0, k, 1, nullptr, nullptr, h->stream); };
     return run_progress_blocks(sp, n_collect, n_discard, out_host, block, cb, user, stats, h->stream, run_block, discard);
+}
+
+int mmc_nuts_set_trace_dev(mmc_nuts *h, double *trace_dev, int64_t pitch_steps) {
+    MMC_REQUIRE(h && pitch_steps >= 0 && (!trace_dev || pitch_steps > 0), "mmc_nuts_set_trace_dev: bad arguments");
+    h->trace_dev = trace_dev;
+    h->trace_pitch = pitch_steps;
+    return MMC_OK;
+}
+
+int mmc_nuts_set_state(mmc_nuts *h, const double *state_host) {
+    MMC_REQUIRE(h && state_host, "mmc_nuts_set_state: bad arguments");
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(h->d_state, state_host, (size_t)h->chains * 5 * 8, cudaMemcpyHostToDevice));
+    return MMC_OK;
+}
+
+int mmc_nuts_set_positions(mmc_nuts *h, const float *positions_host) {
+    MMC_REQUIRE(h && positions_host, "mmc_nuts_set_positions: bad arguments");
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(h->d_pos, positions_host, (size_t)h->chains * h->dim * sizeof(float), cudaMemcpyHostToDevice));
+    return MMC_OK;
+}
+
+// Debug / known-answer entry: ONE build_tree(position, momentum, grad, logu, v, j, epsilon, joint_0) per chain
+// (src/nuts.rs:764-946, test_build_tree :1057-1121) on the kernels and lane layout the handle would run, with the
+// uniforms read from a per-chain tape.  The positions of the handle are the input positions and are left unchanged.
+int mmc_nuts_build_tree(mmc_nuts *h, const float *mom_host, const float *grad_host, const double *scal_host, int32_t j,
+                        const double *unifs_host, int64_t cap_unifs, float *out_vec_host, double *out_scal_host) {
+    MMC_REQUIRE(h && mom_host && grad_host && scal_host && unifs_host && out_vec_host && out_scal_host && cap_unifs > 0,
+                "mmc_nuts_build_tree: bad arguments");
+    MMC_REQUIRE(j >= 0 && j <= h->max_depth, "mmc_nuts_build_tree: depth %d outside [0, max_depth = %d]", j, h->max_depth);
+    const size_t nv = (size_t)h->chains * h->dim;
+    float *d_vec = nullptr;   // mom, grad, out_vec[5]
+    double *d_scal = nullptr; // scal[4], out_scal[6], unifs[cap]
+    cudaStream_t s = h->stream;
+    int rc = MMC_OK;
+    auto done = [&](int code) {
+        cudaFree(d_vec);
+        cudaFree(d_scal);
+        return code;
+    };
+    MMC_CUDA(cudaMalloc((void **)&d_vec, nv * 7 * sizeof(float)));
+    if (cudaMalloc((void **)&d_scal, (size_t)h->chains * (10 + cap_unifs) * 8) != cudaSuccess) return done(MMC_ERR_CUDA);
+    double *d_si = d_scal, *d_so = d_scal + h->chains * 4, *d_un = d_scal + h->chains * 10;
+    cudaMemcpyAsync(d_vec, mom_host, nv * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_vec + nv, grad_host, nv * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_si, scal_host, (size_t)h->chains * 4 * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_un, unifs_host, (size_t)h->chains * cap_unifs * 8, cudaMemcpyHostToDevice, s);
+    NutsParams p{};
+    p.positions = h->d_pos;
+    p.state = h->d_state;
+    p.normals = d_un; p.exps = d_un; p.unifs = d_un;  // only the uniform tape is read
+    p.cap_normals = p.cap_exps = p.cap_unifs = cap_unifs;
+    p.counters = h->d_counters;
+    p.chains = h->chains;
+    p.chain_offset = h->chain_offset;
+    p.max_depth = h->max_depth;
+    p.D = h->dim;
+    p.target_accept = h->target_accept;
+    p.key = seed_key(h->seed);
+    p.it_hi = -1;
+    p.progress = 1;
+    p.tree_mom = d_vec;
+    p.tree_grad = d_vec + nv;
+    p.tree_scal = d_si;
+    p.tree_out_vec = d_vec + 2 * nv;
+    p.tree_out_scal = d_so;
+    p.tree_j = j;
+    NutsLaunch L{h->target, h->scalar_dtype == MMC_F64, true, sm_count()};
+    const int group_lanes = nuts_group_lanes(h->target);
+    const bool group = h->layout == kNutsLayoutAuto ? group_lanes != 0 : h->layout != kNutsLayoutWarp;
+    h->lanes_used = group ? group_lanes : 32;
+    auto dispatch = group ? (h->exact ? nuts_group_dispatch_exact : nuts_group_dispatch_fast)
+                          : (h->exact ? nuts_dispatch_exact : nuts_dispatch_fast);
+    int64_t grid = 0;
+    size_t scratch_floats = 0;
+    if ((rc = dispatch(L, p, &grid, &scratch_floats, true, s))) return done(rc);
+    if ((rc = grow(&h->d_scratch, &h->scratch_bytes, scratch_floats * sizeof(float) + 16))) return done(rc);
+    p.scratch = h->d_scratch;
+    cudaMemsetAsync(h->d_counters, 0, 8, s);
+    if ((rc = dispatch(L, p, &grid, &scratch_floats, false, s))) return done(rc);
+    cudaMemcpyAsync(out_vec_host, d_vec + 2 * nv, nv * 5 * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_scal_host, d_so, (size_t)h->chains * 6 * 8, cudaMemcpyDeviceToHost, s);
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return done(cuda_fail(e, "mmc_nuts_build_tree", __FILE__, __LINE__));
+    return done(MMC_OK);
 }
 
 int mmc_nuts_get_state(mmc_nuts *h, double *state_host) {

@@ -124,6 +124,14 @@ struct WSmall {
     }
 };
 
+// k 2^-53 < num / den evaluated exactly for a 53-bit k: k den < num 2^53 in 128 bits (k den needs 53 + log2 den bits,
+// which passes 64 from tree depth 11 on; max_depth goes up to 16)
+__device__ __forceinline__ bool u53_below_ratio(uint64_t k53, uint32_t num, uint32_t den) {
+    const uint64_t lo = k53 * (uint64_t)den, hi = __umul64hi(k53, (uint64_t)den);
+    const uint64_t rlo = (uint64_t)num << 53, rhi = (uint64_t)num >> 11;
+    return hi < rhi || (hi == rhi && lo < rlo);
+}
+
 // ---------------------------------------------------------------- scalar helpers (type T of the reference)
 __device__ __forceinline__ float s_exp(float v) { return expf(v); }
 __device__ __forceinline__ double s_exp(double v) { return exp(v); }
@@ -158,6 +166,19 @@ struct NutsParams {
     const int *perm;
     double target_accept;
     uint2 key;
+    // optional per-transition trace [chains, trace_pitch, 8] = joint_0, logu, n, alpha, n_alpha, depth, epsilon used,
+    // uniforms consumed; row = iteration index of the launch (mmc_nuts_set_trace_dev)
+    double *trace;
+    int64_t trace_pitch;
+    // build_tree debug mode (mmc_nuts_build_tree; replay instantiations only): one doubling of depth tree_j per chain
+    // from (positions, tree_mom, tree_grad) with tree_scal [chains, 4] = logu, v, epsilon, joint_0 and the uniforms of the
+    // replay tape; tree_out_vec [chains, 5, D] = new edge x, p, grad, proposal x', grad(x'); tree_out_scal [chains, 6] =
+    // logp(x'), n', s', alpha', n_alpha', uniforms consumed
+    const float *tree_mom, *tree_grad;
+    const double *tree_scal;
+    float *tree_out_vec;
+    double *tree_out_scal;
+    int32_t tree_j;
 };
 
 template <class Target, class A, class ST, int E, bool kReplay>
@@ -419,7 +440,7 @@ struct NutsWarp {
                         // evaluated exactly (the f64 quotient is rounded, which can only matter when u equals the rounded
                         // quotient itself, a 2^-53 event) and keeps the FP64 division out of the merge path
                         const uint64_t k53 = draw_u53();
-                        take_b = tn != 0 && (an == 0 || k53 * (uint64_t)(an + tn) < ((uint64_t)tn << 53));
+                        take_b = tn != 0 && (an == 0 || u53_below_ratio(k53, (uint32_t)tn, (uint32_t)(an + tn)));
                     }
                     load_level(lvl, 0, tfx);
                     load_level(lvl, 1, tfm);
@@ -481,6 +502,40 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
             const int i = lane * E + k;
             pos[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
         }
+        if constexpr (kReplay) {
+            if (p.tree_scal) {  // build_tree debug mode: one doubling, src/nuts.rs:764-946
+                float cm[E], cg[E], prop[E], gp[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const int i = lane * E + k;
+                    cm[k] = i < p.D ? p.tree_mom[c * p.D + i] : 0.0f;
+                    cg[k] = i < p.D ? p.tree_grad[c * p.D + i] : 0.0f;
+                }
+                const double *sc = p.tree_scal + c * 4;
+                int n_prime = 0, n_alpha = 0;
+                bool s_prime = false;
+                ST alpha = (ST)0.0;
+                w.doubling(pos, cm, cg, sc[1] < 0.0 ? -1 : 1, p.tree_j, (ST)sc[0], (ST)sc[2], (ST)sc[3], prop, n_prime, s_prime,
+                           alpha, n_alpha);
+                const float lpp = w.full_logp(tgt.logp_grad(prop, gp, lane));
+                float *ov = p.tree_out_vec + c * 5 * p.D;
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const int i = lane * E + k;
+                    if (i < p.D) {
+                        ov[i] = pos[k]; ov[p.D + i] = cm[k]; ov[2 * p.D + i] = cg[k]; ov[3 * p.D + i] = prop[k];
+                        ov[4 * p.D + i] = gp[k];
+                    }
+                }
+                if (lane == 0) {
+                    double *os = p.tree_out_scal + c * 6;
+                    os[0] = (double)lpp; os[1] = (double)n_prime; os[2] = s_prime ? 1.0 : 0.0; os[3] = (double)alpha;
+                    os[4] = (double)n_alpha; os[5] = (double)w.cur_u;
+                }
+                w.n_grad = 0; w.n_unif = 0;
+                continue;
+            }
+        }
         double *st = p.state + c * 5;
         ST epsilon = (ST)st[0], epsilon_bar = (ST)st[1], h_bar = (ST)st[2], mu;
         long long m = (long long)st[4];
@@ -519,6 +574,8 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
             m += 1;
             w.step_word = (uint32_t)m;
             w.q = 0; w.q_batch = 0xffffffffu;
+            const ST eps_used = epsilon;
+            const int64_t unifs_before = w.cur_u;
             float mom0[E], grad[E];
             w.draw_normals(mom0);
             float ulogp = tgt.logp_grad(pos, grad, lane);
@@ -561,6 +618,11 @@ __global__ void __launch_bounds__(kNutsWarps * 32, MMC_NUTS_MIN_BLOCKS) nuts_run
             }
             if (lane == (j < 31 ? j : 31)) ++my_depth_count;
             ++n_trans;
+            if (p.trace && lane == 0) {
+                double *tr = p.trace + (c * p.trace_pitch + it) * 8;
+                tr[0] = (double)joint; tr[1] = (double)logu; tr[2] = (double)n; tr[3] = (double)alpha; tr[4] = (double)n_alpha;
+                tr[5] = (double)j; tr[6] = (double)eps_used; tr[7] = kReplay ? (double)(w.cur_u - unifs_before) : (double)w.q;
+            }
             // dual averaging, src/nuts.rs:676-690
             ST eta = (ST)1.0 / (ST)(m + t_0);
             h_bar = ((ST)1.0 - eta) * h_bar + eta * (delta - alpha / (ST)n_alpha);

@@ -404,7 +404,7 @@ struct NutsGroup {
         uint32_t lo, hw;
         next_words(take, lo, hw);
         const uint64_t k53 = (((uint64_t)hw << 32) | lo) >> 11;
-        return tn != 0 && (an == 0 || k53 * (uint64_t)(an + tn) < ((uint64_t)tn << 53));
+        return tn != 0 && (an == 0 || u53_below_ratio(k53, (uint32_t)tn, (uint32_t)(an + tn)));
     }
 
     // ---- leapfrog, src/nuts.rs:979-996 (in place); returns logp' (partial when Target::kPartial)
@@ -766,6 +766,44 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
         w.gchain = (uint64_t)(c + p.chain_offset);
         w.cur_n = w.cur_e = w.cur_u = 0;
 
+        if constexpr (kReplay) {
+            if (p.tree_scal) {  // build_tree debug mode: one doubling of depth tree_j per chain, src/nuts.rs:764-946
+                float cx[E], cm[E], cg[E], prop[E], gp[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const int i = gl * E + W::off(k);
+                    cx[k] = i < p.D ? p.positions[c * p.D + i] : 0.0f;
+                    cm[k] = i < p.D ? p.tree_mom[c * p.D + i] : 0.0f;
+                    cg[k] = i < p.D ? p.tree_grad[c * p.D + i] : 0.0f;
+                    prop[k] = 0.0f;
+                }
+                const double *sc = p.tree_scal + c * 4;
+                int n_prime = 0, n_alpha = 0;
+                bool s_prime = false;
+                ST alpha = (ST)0.0;
+                w.doubling(cx, cm, cg, !(sc[1] < 0.0), p.tree_j, (ST)sc[0], (ST)sc[2], (ST)sc[3], has, prop, n_prime, s_prime,
+                           alpha, n_alpha);
+                const float lpp = w.full_logp(tgt.logp_grad(prop, gp, gl));
+                if (has) {
+                    float *ov = p.tree_out_vec + c * 5 * p.D;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) {
+                        const int i = gl * E + W::off(k);
+                        if (i < p.D) {
+                            ov[i] = cx[k]; ov[p.D + i] = cm[k]; ov[2 * p.D + i] = cg[k]; ov[3 * p.D + i] = prop[k];
+                            ov[4 * p.D + i] = gp[k];
+                        }
+                    }
+                    if (gl == 0) {
+                        double *os = p.tree_out_scal + c * 6;
+                        os[0] = (double)lpp; os[1] = (double)n_prime; os[2] = s_prime ? 1.0 : 0.0; os[3] = (double)alpha;
+                        os[4] = (double)n_alpha; os[5] = (double)w.cur_u;
+                    }
+                }
+                w.n_grad = 0; w.n_unif = 0;
+                continue;
+            }
+        }
         double *st = p.state + c * 5;
         ST epsilon = (ST)__ldcg(st + 0), epsilon_bar = (ST)__ldcg(st + 1), h_bar = (ST)__ldcg(st + 2), mu;
         long long m = (long long)__ldcg(st + 4);
@@ -818,6 +856,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
             m += 1;
             w.step_word = (uint32_t)m;
             w.q = 0; w.q_batch = 0xffffffffu;
+            const ST eps_used = epsilon;
+            const int64_t unifs_before = w.cur_u;
             float cx[E], cm[E], cg[E];  // the edge being extended; the opposite edge is parked in shared memory
             w.load_parked(3, cx);
             w.draw_normals(cm);
@@ -873,6 +913,11 @@ __global__ void __launch_bounds__(kGrpWarps * 32, GrpTune<E>::kMinBlocks) nuts_g
             }
             if (has && gl == 0) atomicAdd(&s_hist[depth < 31 ? depth : 31], 1);
             if (has && gl == 0) ++n_trans;
+            if (p.trace && has && gl == 0) {
+                double *tr = p.trace + (c * p.trace_pitch + it) * 8;
+                tr[0] = (double)joint; tr[1] = (double)logu; tr[2] = (double)n; tr[3] = (double)alpha; tr[4] = (double)n_alpha;
+                tr[5] = (double)depth; tr[6] = (double)eps_used; tr[7] = kReplay ? (double)(w.cur_u - unifs_before) : (double)w.q;
+            }
             // dual averaging, src/nuts.rs:676-690
             ST eta = (ST)1.0 / (ST)(m + t_0);
             h_bar = ((ST)1.0 - eta) * h_bar + eta * (delta - alpha / (ST)n_alpha);

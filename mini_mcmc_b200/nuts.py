@@ -174,6 +174,74 @@ class NUTS:
         L.check(L.lib.mmc_nuts_get_state(self._h, L.vp(st)))
         return st
 
+    def set_state(self, state):
+        """Overwrite the chains' adaptation state ([chains, 5], see state()): with set_continuation(adapt_until, resume=1)
+        the next run continues from exactly this state (single-transition parity tests, checkpoint / resume)."""
+        st = np.ascontiguousarray(state, dtype=np.float64)
+        if st.shape != (self.n_chains, 5):
+            raise ValueError("state must be [chains, 5]")
+        L.check(L.lib.mmc_nuts_set_state(self._h, L.vp(st)))
+        return self
+
+    def set_positions(self, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.float32)
+        if pos.shape != (self.n_chains, self.dim):
+            raise ValueError("positions must be [chains, dim]")
+        L.check(L.lib.mmc_nuts_set_positions(self._h, L.vp(pos)))
+        return self
+
+    def set_continuation(self, adapt_until: int, resume: bool):
+        L.check(L.lib.mmc_nuts_set_continuation(self._h, C.c_int64(adapt_until), C.c_int32(int(resume))))
+        return self
+
+    def step_traced(self, state, tapes, n_discard: int = 0):
+        """ONE NUTSChain::step (src/nuts.rs:550-691) per chain from the current positions and the given adaptation state,
+        with the draws read from per-chain tapes (normals [chains, >= D], exps [chains, >= 1], unifs [chains, cap]).
+        Returns (positions', state', trace [chains, 8] = joint_0, logu, n, alpha, n_alpha, depth, epsilon used, uniforms
+        consumed).  n_discard only enters the dual-averaging rule (m <= n_discard adapts)."""
+        import torch
+
+        self.set_state(state)
+        trace = torch.zeros((self.n_chains, 1, 8), dtype=torch.float64, device="cuda")
+        L.check(L.lib.mmc_nuts_set_trace_dev(self._h, L.vp(trace), C.c_int64(1)))
+        self.set_continuation(n_discard, True)
+        try:
+            out = self._run(1, 0, 1, tapes, None)
+        finally:
+            L.check(L.lib.mmc_nuts_set_trace_dev(self._h, None, C.c_int64(0)))
+            self.set_continuation(-1, False)
+        return out[:, 0], self.state(), trace.cpu().numpy()[:, 0]
+
+    def build_tree(self, mom, grad, logu, v, j: int, epsilon, joint_0, unifs):
+        """build_tree (src/nuts.rs:764-946) once per chain on the device kernels (mmc_nuts_build_tree): positions are the
+        handle's, mom / grad [chains, D], logu / v / epsilon / joint_0 scalars or [chains], unifs [chains, cap].
+        Returns the reference's 13 outputs (dict of [chains, D] / [chains] arrays) plus n_unifs."""
+        mom = np.ascontiguousarray(mom, dtype=np.float32)
+        grad = np.ascontiguousarray(grad, dtype=np.float32)
+        unifs = np.ascontiguousarray(unifs, dtype=np.float64)
+        scal = np.empty((self.n_chains, 4), dtype=np.float64)
+        scal[:, 0], scal[:, 1], scal[:, 2], scal[:, 3] = logu, v, epsilon, joint_0
+        def call(depth):
+            vec = np.empty((self.n_chains, 5, self.dim), dtype=np.float32)
+            out = np.empty((self.n_chains, 6), dtype=np.float64)
+            L.check(L.lib.mmc_nuts_build_tree(self._h, L.vp(mom), L.vp(grad), L.vp(scal), C.c_int32(depth), L.vp(unifs),
+                                              C.c_int64(unifs.shape[1]), L.vp(vec), L.vp(out)))
+            return vec, out
+
+        vec, out = call(j)
+        # the edge of the 13-tuple that faces the starting point is the subtree's FIRST leaf (src/nuts.rs:812-826 sets
+        # both edges to it and only the outer one moves afterwards) = the device's build_tree of depth 0
+        inner = vec if j == 0 else call(0)[0]
+        minus = (scal[:, 1] < 0)[:, None]
+        res = dict(
+            position_minus=np.where(minus, vec[:, 0], inner[:, 0]), mom_minus=np.where(minus, vec[:, 1], inner[:, 1]),
+            grad_minus=np.where(minus, vec[:, 2], inner[:, 2]), position_plus=np.where(minus, inner[:, 0], vec[:, 0]),
+            mom_plus=np.where(minus, inner[:, 1], vec[:, 1]), grad_plus=np.where(minus, inner[:, 2], vec[:, 2]),
+            position_prime=vec[:, 3], grad_prime=vec[:, 4], logp_prime=out[:, 0], n_prime=out[:, 1].astype(np.int64),
+            s_prime=out[:, 2] != 0, alpha_prime=out[:, 3], n_alpha_prime=out[:, 4].astype(np.int64),
+            n_unifs=out[:, 5].astype(np.int64))
+        return res
+
     @property
     def positions(self) -> np.ndarray:
         out = np.empty((self.n_chains, self.dim), dtype=np.float32)

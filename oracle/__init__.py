@@ -317,6 +317,58 @@ def nuts_build_tree(target: Target, x, p, g, logu, v, j, epsilon, joint_0, rng_s
     return res
 
 
+def nuts_build_tree_tape(target: Target, x, p, g, logu, v, j, epsilon, joint_0, unifs, scalar_f32=False):
+    """build_tree (src/nuts.rs:764-946) for many chains with per-chain uniform tapes.  x, p, g [chains, D]; logu, v,
+    epsilon, joint_0 scalars or [chains]; unifs [chains, cap].  Returns dict of [chains, D] vectors and [chains] scalars
+    (the 13 outputs of the reference plus the number of uniforms consumed)."""
+    x, p, g = _f32(x), _f32(p), _f32(g)
+    chains, D = x.shape
+    scal_in = np.empty((chains, 4), dtype=np.float64)
+    scal_in[:, 0], scal_in[:, 1], scal_in[:, 2], scal_in[:, 3] = logu, v, epsilon, joint_0
+    unifs = _f64(unifs).copy()
+    vec = np.empty((chains, 8, D), dtype=np.float32)
+    scal = np.empty((chains, 6), dtype=np.float64)
+    margin = np.empty(chains, dtype=np.float64)
+    lib().orc_nuts_build_tree_tape(*target.args(), C.c_int64(chains), _p(x, C.c_float), _p(p, C.c_float),
+                                   _p(g, C.c_float), _p(scal_in, C.c_double), int(j), int(scalar_f32),
+                                   _p(unifs, C.c_double), C.c_int64(unifs.shape[1]), _p(vec, C.c_float),
+                                   _p(scal, C.c_double), _p(margin, C.c_double))
+    names = ["position_minus", "mom_minus", "grad_minus", "position_plus", "mom_plus", "grad_plus",
+             "position_prime", "grad_prime"]
+    res = {n: vec[:, i] for i, n in enumerate(names)}
+    res.update(logp_prime=scal[:, 0], n_prime=scal[:, 1].astype(np.int64), s_prime=scal[:, 2] != 0,
+               alpha_prime=scal[:, 3], n_alpha_prime=scal[:, 4].astype(np.int64), n_unifs=scal[:, 5].astype(np.int64),
+               margin=margin)
+    return res
+
+
+def smallrng_f64(seed, n):
+    """n draws of rng.random::<f64>() from SmallRng::seed_from_u64(seed) (the stream build_tree consumes in
+    src/nuts.rs:1066-1085)."""
+    return SmallRng(seed).f64(n)
+
+
+def nuts_step_trace(target: Target, positions, state, target_accept, tapes, *, n_discard=0, scalar_f32=False,
+                    max_depth=0):
+    """ONE NUTS transition per chain from (positions, state) with the draws read from per-chain tapes
+    (normals [chains, >= D], exps [chains, >= 1], unifs [chains, cap]).  Returns dict(positions, state, trace) with
+    trace [chains, 8] = joint_0, logu, n, alpha, n_alpha, depth, epsilon used, uniforms consumed; margin [chains] = the
+    smallest relative distance of any slice / accept / U-turn comparison of the transition from its threshold."""
+    pos = _f32(positions).copy()
+    chains, D = pos.shape
+    st = _f64(state).copy()
+    normals, exps, unifs = (_f64(t).copy() for t in tapes)
+    trace = np.zeros((chains, 8), dtype=np.float64)
+    margin = np.zeros(chains, dtype=np.float64)
+    rc = lib().orc_nuts_step_trace(*target.args(), _p(pos, C.c_float), C.c_int64(chains), C.c_double(target_accept),
+                                   int(scalar_f32), C.c_int64(n_discard), int(max_depth), _p(normals, C.c_double),
+                                   C.c_int64(normals.shape[1]), _p(exps, C.c_double), C.c_int64(exps.shape[1]),
+                                   _p(unifs, C.c_double), C.c_int64(unifs.shape[1]), _p(st, C.c_double),
+                                   _p(trace, C.c_double), _p(margin, C.c_double))
+    assert rc == 0
+    return dict(positions=pos, state=st, trace=trace, margin=margin)
+
+
 def nuts_run(target: Target, positions, target_accept, n_collect, n_discard, *, seed=0, progress=False,
              scalar_f32=False, max_depth=0, tapes=None, record=False, cap_unifs=None, state=None):
     """Multi-chain NUTS.  tapes = (normals, exps, unifs) per chain -> replay mode; otherwise reference

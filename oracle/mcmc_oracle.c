@@ -387,7 +387,15 @@ typedef struct {
     double *normals, *exps, *unifs; /* tape (read) or recording buffers (write, may be NULL) */
     int64_t n_normals, n_exps, n_unifs;
     int64_t cap_normals, cap_exps, cap_unifs;
+    /* test bookkeeping (not part of the algorithm): the smallest relative distance of any accept / slice / U-turn
+     * comparison of the current transition from its threshold, when track_margin is set.  Parity tests use it to
+     * tell a chain that legitimately branches at an fp32 near-tie from a wrong result. */
+    int track_margin;
+    double min_margin;
 } orc_src;
+static inline void orc_margin(orc_src *s, double m) {
+    if (s->track_margin && m < s->min_margin) s->min_margin = m;
+}
 
 #define ST double
 #define SFX(n) n##_f64
@@ -448,6 +456,92 @@ ORC_API void orc_nuts_build_tree(int kind, int D, const double *params, int n_pa
     scal_out[0] = r.logp_prime; scal_out[1] = (double)r.n_prime; scal_out[2] = (double)r.s_prime;
     scal_out[3] = r.alpha; scal_out[4] = (double)r.n_alpha;
     tree_free_f64(&r);
+}
+
+/* build_tree for many chains with the uniforms read from per-chain tapes (both scalar types): the checker of the
+ * CUDA debug entry mmc_nuts_build_tree.  x, p, g [chains, D]; scal_in [chains, 4] = logu, v, epsilon, joint_0;
+ * vec_out [chains, 8, D] and scal_out [chains, 6] = logp', n', s', alpha', n_alpha', uniforms consumed. */
+ORC_API void orc_nuts_build_tree_tape(int kind, int D, const double *params, int n_params, const float *vec,
+                                      const float *mat, int64_t chains, const float *x, const float *p, const float *g,
+                                      const double *scal_in, int j, int scalar_f32, double *unifs, int64_t cap_unifs,
+                                      float *vec_out, double *scal_out, double *margin_out) {
+    orc_zig_init();
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_src src;
+        memset(&src, 0, sizeof(src));
+        src.mode = ORC_SRC_TAPE;
+        src.unifs = unifs + c * cap_unifs;
+        src.cap_unifs = cap_unifs;
+        src.track_margin = margin_out != NULL;
+        src.min_margin = 1e300;
+        const double *si = scal_in + c * 4;
+        double *so = scal_out + c * 6;
+        if (scalar_f32) {
+            tree_f32 r;
+            tree_alloc_f32(&r, D);
+            build_tree_f32(&t, x + c * D, p + c * D, g + c * D, (float)si[0], (int)si[1], j, (float)si[2], (float)si[3], &src, &r, NULL);
+            memcpy(vec_out + c * 8 * D, r.xm, sizeof(float) * D * 8);
+            so[0] = r.logp_prime; so[1] = (double)r.n_prime; so[2] = (double)r.s_prime; so[3] = (double)r.alpha; so[4] = (double)r.n_alpha;
+            tree_free_f32(&r);
+        } else {
+            tree_f64 r;
+            tree_alloc_f64(&r, D);
+            build_tree_f64(&t, x + c * D, p + c * D, g + c * D, si[0], (int)si[1], j, si[2], si[3], &src, &r, NULL);
+            memcpy(vec_out + c * 8 * D, r.xm, sizeof(float) * D * 8);
+            so[0] = r.logp_prime; so[1] = (double)r.n_prime; so[2] = (double)r.s_prime; so[3] = r.alpha; so[4] = (double)r.n_alpha;
+            tree_free_f64(&r);
+        }
+        so[5] = (double)src.n_unifs;
+        if (margin_out) margin_out[c] = src.min_margin;
+    }
+}
+
+/* ONE NUTSChain::step per chain (src/nuts.rs:550-691) from a given position and adaptation state, draws from per-chain
+ * tapes (D normals, one Exp(1), the uniform tape): the checker of the single-transition parity tests.
+ * state_io [chains, 5] as in orc_nuts_run (epsilon must be set); n_discard only enters the dual-averaging rule
+ * (m <= n_discard adapts).  trace_out [chains, 8] = joint_0, logu, n, alpha, n_alpha, depth, epsilon used, uniforms.
+ * margin_out [chains] (optional) = smallest relative distance of any comparison of the transition from its threshold. */
+ORC_API int orc_nuts_step_trace(int kind, int D, const double *params, int n_params, const float *vec, const float *mat,
+                                float *positions, int64_t chains, double target_accept, int scalar_f32, int64_t n_discard,
+                                int max_depth, double *normals, int64_t cap_normals, double *exps, int64_t cap_exps,
+                                double *unifs, int64_t cap_unifs, double *state_io, double *trace_out,
+                                double *margin_out) {
+    orc_zig_init();
+    orc_target t;
+    orc_make_target(&t, kind, D, params, n_params, vec, mat);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t c = 0; c < chains; ++c) {
+        orc_src src;
+        memset(&src, 0, sizeof(src));
+        src.mode = ORC_SRC_TAPE;
+        src.normals = normals + c * cap_normals; src.cap_normals = cap_normals;
+        src.exps = exps + c * cap_exps; src.cap_exps = cap_exps;
+        src.unifs = unifs + c * cap_unifs; src.cap_unifs = cap_unifs;
+        src.track_margin = margin_out != NULL;
+        src.min_margin = 1e300;
+        double *s = state_io + c * 5;
+        int depth = 0;
+        if (scalar_f32) {
+            chain_state_f32 cs;
+            chain_new_f32(&cs, target_accept);
+            cs.epsilon = (float)s[0]; cs.epsilon_bar = (float)s[1]; cs.h_bar = (float)s[2]; cs.mu = (float)s[3];
+            cs.m = (int64_t)s[4]; cs.n_discard = n_discard;
+            chain_step_traced_f32(&t, &cs, positions + c * D, &src, max_depth, NULL, &depth, trace_out + c * 8);
+            s[0] = cs.epsilon; s[1] = cs.epsilon_bar; s[2] = cs.h_bar; s[3] = cs.mu; s[4] = (double)cs.m;
+        } else {
+            chain_state_f64 cs;
+            chain_new_f64(&cs, target_accept);
+            cs.epsilon = s[0]; cs.epsilon_bar = s[1]; cs.h_bar = s[2]; cs.mu = s[3]; cs.m = (int64_t)s[4];
+            cs.n_discard = n_discard;
+            chain_step_traced_f64(&t, &cs, positions + c * D, &src, max_depth, NULL, &depth, trace_out + c * 8);
+            s[0] = cs.epsilon; s[1] = cs.epsilon_bar; s[2] = cs.h_bar; s[3] = cs.mu; s[4] = (double)cs.m;
+        }
+        if (margin_out) margin_out[c] = src.min_margin;
+    }
+    return 0;
 }
 
 /* Full multi-chain NUTS run.

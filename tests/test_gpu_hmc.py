@@ -42,19 +42,20 @@ def test_hmc_single_transition_replay(mm, name):
         h = mm.HMC(tgt, init, eps, L).set_exact(exact)
         trace = np.zeros((1, chains, 4), dtype=np.float32)
         got = h.run(1, 0, replay=dict(momenta=mom, u=u), trace=trace)
-        scale = np.maximum(1.0, np.abs(exp_tr[..., :2]).max(axis=-1, keepdims=True))
-        # log-probs
-        assert np.abs(trace[..., :2] - exp_tr[..., :2]).max() <= rtol * scale.max() * 4
-        np.testing.assert_allclose(trace[..., :2], exp_tr[..., :2], rtol=rtol * 10, atol=rtol * 10)
-        # accept decisions: identical except where accept_logp is within tolerance of ln(u)
+        # log-probs: per chain, relative to max(1, |logp|)
+        for k in (0, 1):
+            err = np.abs(trace[0, :, k].astype(np.float64) - exp_tr[0, :, k]) / np.maximum(1.0, np.abs(exp_tr[0, :, k]))
+            assert err.max() <= rtol, f"{name} exact={exact}: logp[{k}] {err.max():.2e}"
+        # accept decisions: identical except where accept_logp is within the tie margin of ln(u)
         margin = np.abs(exp_tr[..., 2] - np.log(np.maximum(u, 1e-38)))
         differ = trace[..., 3] != exp_tr[..., 3]
         assert not (differ & (margin > 1e-3)).any()
         same = ~differ[0]
-        np.testing.assert_allclose(got[same, 0], exp[same, 0], rtol=rtol * 10, atol=rtol)
+        # states: per chain, relative to max(1, |x|_inf)
+        serr = np.abs(got[same, 0].astype(np.float64) - exp[same, 0]).max(axis=1) / np.maximum(1.0, np.abs(exp[same, 0]).max(axis=1))
+        assert serr.max() <= rtol, f"{name} exact={exact}: state {serr.max():.2e}"
         if exact:
             assert differ.sum() == 0
-            np.testing.assert_allclose(got[:, 0], exp[:, 0], rtol=1e-6, atol=1e-6)
 
 
 def test_hmc_c3_shape_multi_step_replay_exact(mm):

@@ -223,3 +223,25 @@ def test_minimal_nuts_example_shape(mm):
     sample, stats = s.run_progress(400, 400)
     assert tuple(sample.shape) == (4, 400, 2)
     assert np.isfinite(sample.cpu().numpy()).all() and np.isfinite(stats.ess.min)
+
+
+def test_merge_acceptance_test_is_exact_up_to_depth_16(mm):
+    """u < n'' / (n' + n'') for a native 53-bit draw is evaluated as k (n' + n'') < n'' 2^53; the product needs up to
+    53 + 16 bits at max_depth = 16 (a 64-bit product silently wrapped from depth 11 on)."""
+    import ctypes as C
+
+    from mini_mcmc_b200 import _lib as L
+
+    rng = np.random.default_rng(0)
+    n = 20000
+    den = rng.integers(1, 2 ** 16 + 1, size=n).astype(np.uint32)
+    num = (rng.random(n) * (den + 1)).astype(np.uint32).clip(0, den)
+    k53 = rng.integers(0, 2 ** 53, size=n, dtype=np.uint64)
+    # near-ties: k just below / at / above num 2^53 / den
+    q = (num[:3000].astype(object) * (1 << 53)) // den[:3000].astype(object)
+    k53[:3000] = np.array([max(0, min((1 << 53) - 1, int(v) + d)) for v, d in zip(q, rng.integers(-1, 2, size=3000))], dtype=np.uint64)
+    out = np.zeros(n, dtype=np.uint8)
+    L.check(L.lib.mmc_debug_nuts_merge_test(L.vp(k53), L.vp(num), L.vp(den), C.c_int64(n), L.vp(out)))
+    exp = np.array([int(k) * int(d) < (int(m) << 53) for k, m, d in zip(k53, num, den)], dtype=np.uint8)
+    np.testing.assert_array_equal(out, exp)
+    assert exp[den > 2 ** 11].any() and not exp[den > 2 ** 11].all()
