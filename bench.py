@@ -15,6 +15,7 @@ Lines printed (rank 0, ONE JSON line):
             states and D2H of every draw inside the timed region
   roofline  HBM-write roofline of the dominant kernel (mh_poisson_kernel): 8 B per collected transition
   cpu_baseline  the oracle's restatement of the reference CPU path on a bounded sample (rank 0, N = 1 only)
+  other_configs C3 / C4 / C5 (fused HMC, dense tcgen05 HMC, NUTS + NCCL-reduced split-Rhat / ESS) at the same N
 """
 from __future__ import annotations
 
@@ -120,34 +121,28 @@ def host_mem_available_bytes():
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def other_configs(timeout_s: float = 300.0):
-    """BASELINE.json's other GPU-sized single-GPU configs, C3 (fused HMC, Rosenbrock-3D) and C5 (NUTS, D = 100, on-device
-    split-Rhat / ESS), measured by scripts/bench_configs.py in a CHILD process after this bench's own timed regions:
-    reported next to the headline (C2) so that the driver's run carries them too.  A failure of the child only shows
-    up as an "error" entry; it cannot touch the headline numbers."""
+def other_configs():
+    """BASELINE.json's other GPU-sized configs measured IN this process group, at every N, right after the headline's
+    timed regions: C3 (fused HMC, Rosenbrock-3D, weak: 262,144 chains per GPU), C4 (dense Gaussian D = 1024 HMC on the
+    default tcgen05 path, strong: 32,768 chains in total) and C5 (NUTS D = 100, strong: 65,536 chains in total, followed
+    by the NCCL-reduced split-Rhat / ESS call inside its own timed region).  Every entry carries ms (max over ranks), its
+    roofline fraction and its scaling mode, so that the driver's 1 -> 8 run holds the hard configs and the one collective
+    of the engine.  A failing config only produces an "error" entry."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
     try:
-        env = {k: v for k, v in os.environ.items()
-               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE")}
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py"), "--configs", "c3,c5", "--no-cpu"],
-                           capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
-        out = {}
-        for ln in r.stdout.splitlines():
-            try:
-                d = json.loads(ln)
-            except ValueError:
-                continue
-            if isinstance(d, dict) and "config" in d:
-                out[str(d["config"]).split()[0]] = d
-        if not out:
-            return {"error": ((r.stderr or "") + (r.stdout or ""))[-300:] or f"exit code {r.returncode}"}
-        return out
-    except Exception as e:  # noqa: BLE001  (never let the side measurement break the bench line)
+        import bench_configs as bc
+
+        return bc.run_configs(["c3", "c4", "c5"], no_cpu=True)
+    except Exception as e:  # noqa: BLE001  (never let the side measurements break the bench line)
         return {"error": repr(e)[:300]}
 
 
 def run_reference_arm(args):
-    """The reference's own CPU algorithm for this path (rayon over chains -> OpenMP over chains), oracle port,
-    all host threads, on a bounded sample of the same workload."""
+    """The reference's own CPU algorithm for this path (rayon over chains -> OpenMP over chains), oracle port, all host
+    threads.  The FIRST timed step runs the whole workload (1,048,576 chains x 10,000 steps, in batches of --ref-chains
+    chains that reuse one output buffer, so the config is the native arm's); the remaining steps run one batch each (a
+    bounded sample, 1/8 of the workload) so that the default --steps finishes within a few minutes.  value = transitions
+    processed / wall time over all timed steps; the per-step figures are reported separately."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,24 +151,36 @@ def run_reference_arm(args):
     import oracle
 
     cores = oracle.use_all_cores()
-    sample_chains = args.ref_chains
+    sample_chains = min(args.ref_chains, args.chains)
+    n_batches = (args.chains + sample_chains - 1) // sample_chains
     state = np.zeros(sample_chains, dtype=np.uint64)
     out = np.empty((sample_chains, N_COLLECT, 1), dtype=np.uint64)
     for _ in range(max(args.warmup, 0) and 1):
         oracle.mh_poisson_run_reference(LAMBDA, state[: sample_chains // 8], N_COLLECT, N_DISCARD, SEED,
                                         out=out[: sample_chains // 8])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.mh_poisson_run_reference(LAMBDA, state, N_COLLECT, N_DISCARD, SEED, out=out)
-    dt = time.perf_counter() - t0
-    tr = sample_chains * (N_COLLECT + N_DISCARD) * args.steps
+    per_step = []
+    tr = 0
+    t_all = time.perf_counter()
+    for k in range(args.steps):
+        t0 = time.perf_counter()
+        batches = n_batches if (k == 0 and not args.ref_sample_only) else 1
+        for b in range(batches):
+            # chain i of the workload seeds its accept stream with 1 + SEED + i (src/metropolis_hastings.rs:189)
+            oracle.mh_poisson_run_reference(LAMBDA, state, N_COLLECT, N_DISCARD, SEED + b * sample_chains, out=out)
+        per_step.append((batches * sample_chains, time.perf_counter() - t0))
+        tr += batches * sample_chains * (N_COLLECT + N_DISCARD)
+    dt = time.perf_counter() - t_all
     value = tr / dt
-    sample = f"{sample_chains} chains x {N_COLLECT + N_DISCARD} steps per step (1/{CHAINS // sample_chains} of the workload)"
+    full = [c * (N_COLLECT + N_DISCARD) / t for c, t in per_step if c >= args.chains]
+    sample = (f"step 1: the full workload ({args.chains} chains x {N_COLLECT + N_DISCARD} steps in {n_batches} batches of "
+              f"{sample_chains} chains); steps 2..{args.steps}: one batch each (1/{n_batches} of the workload)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 state / f64 accept", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "chains_per_gpu": args.chains, "n_collect": N_COLLECT, "n_discard": N_DISCARD,
+                   "lambda": LAMBDA, "sample": sample},
+        "full_workload_step": {"value": full[0] if full else None, "unit": UNIT, "seconds": per_step[0][1] if full else None},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,7 +199,8 @@ def main():
     ap.add_argument("--ref-chains", type=int, default=131072, help="chains in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-configs", action="store_true", help="skip the C3 / C5 side measurements (child process)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C3 / C4 / C5 side measurements")
+    ap.add_argument("--ref-sample-only", action="store_true", help="reference arm: bounded samples only (no full-workload step)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -210,7 +218,11 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints there)
+        # NCCL's INFO log (communicator set-up: "comm ... rank r nranks N", NVLS / ring choices) goes to STDERR so that
+        # the run stays observable while stdout carries the single JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -308,7 +320,46 @@ def main():
                "note": "draws cross PCIe as u8 and are widened to the caller's u64 [chains, n_collect] array by host "
                        "threads inside mmc_mh_run, overlapped with sampling + copy of the next block of chains"}
         assert abs(float(out_np[::64, -1, 0].astype(np.float64).mean()) - LAMBDA) < 0.2
-        del handles
+        # the ceiling of this path: the reference API returns u64 draws, so the host cores must write 8 B per draw;
+        # measured STREAM-style write peak of this host with the widening pool's thread count (all ranks at once)
+        import ctypes as C
+
+        from mini_mcmc_b200 import _lib as L
+
+        gbs, nthreads = C.c_double(), C.c_int32()
+        barrier()
+        L.lib.mmc_host_write_bandwidth(C.c_uint64(4 << 30), 0, 2, C.byref(gbs), C.byref(nthreads))
+        barrier()
+        host_peak = torch.tensor([gbs.value], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(host_peak)   # the ranks measured concurrently: the sum is what the host sustains
+        host_write = full_bytes * world / (dt / e2e_steps) / 1e9
+        e2e["roofline"] = {"bound": "host_dram_write", "achieved": host_write, "peak": float(host_peak.item()), "unit": "GB/s",
+                           "frac": host_write / max(float(host_peak.item()), 1e-9), "threads_per_rank": nthreads.value,
+                           "numa_nodes": len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+                           if os.path.isdir("/sys/devices/system/node") else None,
+                           "note": "8 B of u64 result per draw written by the host cores (75.5 GB per GPU and step); "
+                                   "peak = non-temporal fill of 4 GiB per rank, all ranks concurrently"}
+        # opt-in compact return type (mmc_mh_run_compact): the same draws as u8, no widening
+        host_u8 = torch.empty((bchains, N_COLLECT, 1), dtype=torch.uint8, pin_memory=True)
+        u8_np = host_u8.numpy()
+        for h in handles:
+            h.set_state(init_np)
+            h.run_compact(N_COLLECT, N_DISCARD, out=u8_np)
+        barrier()
+        t0 = time.perf_counter()
+        for h in handles:
+            h.set_state(init_np)
+            h.run_compact(N_COLLECT, N_DISCARD, out=u8_np)
+        barrier()
+        dtc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+        e2e["compact_u8"] = {"value": chains * steps_per_run * world / float(dtc.item()), "unit": UNIT,
+                             "d2h_bytes_per_step": chains * N_COLLECT * per_draw, "host_result_bytes_per_step": chains * N_COLLECT * per_draw,
+                             "note": "opt-in mmc_mh_run_compact: u8 draws in the caller's pinned array (not the drop-in return type)"}
+        assert abs(float(u8_np[::64, -1, 0].astype(np.float64).mean()) - LAMBDA) < 0.2
+        del handles, host_u8
 
     # ---- CPU baseline (oracle port of the reference CPU path), rank 0, N = 1 only
     cpu_baseline = None
@@ -327,9 +378,9 @@ def main():
                                   f"{dt:.1f} s of wall time"}
 
     others = None
-    if rank == 0 and world == 1 and not args.no_other_configs:
+    if not args.no_other_configs:
         torch.cuda.empty_cache()
-        others = other_configs()
+        others = other_configs()     # every rank takes part (C4 / C5 are sharded over the ranks, C5 ends in an all-reduce)
 
     if rank == 0:
         line = {
@@ -346,6 +397,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if distributed:
+        mm.Communicator.shutdown()
         dist.destroy_process_group()
 
 

@@ -147,6 +147,13 @@ int mmc_mh_run_dev(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_de
                    void *stream);
 /* bytes that cross PCIe per collected draw in mmc_mh_run (8 for the plain u64 copy; 1 or 2 when the Poisson path
  * ships compact draws and widens them to u64 on the host threads) */
+/* Opt-in compact return type for the integer targets (Poisson / Categorical, table accept mode): out_host receives
+ * [chains, n_collect] draws as u8 (tables of <= 256 states) or u16, *elem_bytes says which.  1-2 B per draw cross PCIe and
+ * are written to host memory instead of the 8 B `usize` of the reference API (mmc_mh_run stays the drop-in). */
+int mmc_mh_run_compact(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, int32_t *elem_bytes);
+/* STREAM-style write bandwidth of this host (GB/s; `threads` = 0: the size of the widening pool mmc_mh_run uses): the
+ * roofline of the end-to-end Poisson path, whose u64 result array the host cores have to write. */
+int mmc_host_write_bandwidth(uint64_t bytes, int32_t threads, int32_t reps, double *gb_per_s, int32_t *threads_used);
 int mmc_mh_d2h_bytes_per_draw(mmc_mh *h);
 int mmc_mh_get_state(mmc_mh *h, void *state_host);
 int mmc_mh_set_state(mmc_mh *h, const void *state_host);
@@ -278,7 +285,23 @@ void mmc_nuts_destroy(mmc_nuts *h);
 int mmc_split_rhat_ess(const float *sample_host, int64_t c, int64_t n, int64_t p, float *rhat_host, float *ess_host);
 int mmc_split_rhat_ess_dev(const float *sample_dev, int64_t c, int64_t n, int64_t p, float *rhat_host,
                            float *ess_host, void *stream);
-/* Sharded form (one process per GPU).  `partial` is f64 [2 + n/2][p] in device memory
+/* Sharded form, one call (one process per GPU; src/stats.rs:416-423 over chains that live on several GPUs): `sample_dev`
+ * holds this rank's c_local chains.  The per-parameter moment sums and summed autocovariances of a window of lags are
+ * all-reduced with NCCL (one ncclAllReduce per window, the first fused with the chain count), the Geyer truncation is
+ * checked on the device, and a wider window is computed only if some parameter has not terminated; every rank returns
+ * the same rhat / ess.  The communicator is created from a 128-byte id that rank 0 obtains with mmc_comm_unique_id and
+ * hands to the other ranks by any out-of-band channel (mmc_comm_create calls ncclCommInitRank on the calling thread's
+ * current device), or adopted from an existing ncclComm_t (mmc_comm_wrap; the caller keeps ownership).  NCCL is
+ * resolved at run time (dlopen of the libnccl.so.2 already in the process, else the system one, else MMC_NCCL_LIB). */
+typedef struct mmc_comm mmc_comm;
+int mmc_comm_unique_id(unsigned char *id128);
+int mmc_comm_create(mmc_comm **out, const unsigned char *id128, int32_t nranks, int32_t rank);
+int mmc_comm_wrap(mmc_comm **out, void *nccl_comm);
+int mmc_comm_info(mmc_comm *c, int32_t *nranks, int32_t *rank, int32_t *nccl_version);
+void mmc_comm_destroy(mmc_comm *c);
+int mmc_split_rhat_ess_sharded(const float *sample_dev, int64_t c_local, int64_t n, int64_t p, mmc_comm *comm, void *stream,
+                               float *rhat_host, float *ess_host);
+/* Building blocks of the sharded form.  `partial` is f64 [2 + n/2][p] in device memory
  * (mmc_stats_partial_len values): row 0 = sum_j m_j, row 1 = sum_j m_j^2, row 2 + t = sum_j acov_j(t) over the
  * LOCAL split chains.  Each call computes lags [lag0, lag0 + n_lags) (and rows 0-1 when lag0 == 0), zeroing
  * the rows it produces first.  The caller sums the partials across ranks (ncclAllReduce /

@@ -26,7 +26,7 @@ struct mmc_hmc {
     uint64_t seed = 0;
     int32_t exact = 0;
     int64_t out_pitch = 0;       // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
-    int32_t gemm_path = 0;       // dense Gaussian: 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32
+    int32_t gemm_path = -1;      // dense Gaussian: -1 = auto (tcgen05 CTA pairs when dim % 256 == 0), 0 = FP32 SIMT tiles, 1 / 2 = tcgen05 3xTF32
     DenseState *dense = nullptr;  // only for MMC_T_DENSE_GAUSSIAN
     float *d_pos = nullptr;
     unsigned long long *d_accept = nullptr;
@@ -250,7 +250,7 @@ int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps) {
 }
 
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
-    MMC_REQUIRE(h && path >= 0 && path <= 2, "gemm path must be 0 (FP32 SIMT), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xTF32, CTA pairs)");
+    MMC_REQUIRE(h && path >= -1 && path <= 2, "gemm path must be -1 (auto), 0 (FP32 SIMT), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xTF32, CTA pairs)");
     h->gemm_path = path;
     return MMC_OK;
 }
@@ -278,7 +278,9 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
         a.eps = (float)h->step_size;
         a.n_leapfrog = h->n_leapfrog;
         a.seed = h->seed;
-        a.gemm_path = h->exact ? 0 : h->gemm_path;
+        // the dense contraction goes through the tensor cores by default (north_star); exact runs and dimensions the
+        // 128 x 256 tcgen05 tiles do not divide use the FP32 SIMT tiles
+        a.gemm_path = h->exact ? 0 : (h->gemm_path >= 0 ? h->gemm_path : (h->dim % 256 == 0 ? 2 : 0));
         int rc = dense_run(h->dense, a, (cudaStream_t)stream);
         if (rc) return rc;
         h->step += n_collect + n_discard;

@@ -5,6 +5,7 @@
 // stores while the next block of chains is being sampled and copied.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,16 @@ __attribute__((target("avx2"))) static void widen_u16_avx2(const uint16_t *src, 
         }
     }
     for (; i < n; ++i) dst[i] = src[i];
+}
+#endif
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void fill_stream_avx2(uint64_t *dst, size_t n, uint64_t v) {
+    const __m256i x = _mm256_set1_epi64x((long long)v);
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), x);
+    for (; i < n; ++i) dst[i] = v;
+    _mm_sfence();
 }
 #endif
 
@@ -87,3 +98,39 @@ void widen_to_u64(const void *src, int elem_bytes, uint64_t *dst, size_t n) {
 }
 
 }  // namespace mmc
+
+// STREAM-style write peak of this host: `threads` threads (0 = the widening pool's size) fill a fresh buffer of `bytes`
+// with the same non-temporal 256-bit stores the widening uses; best of `reps` passes.  bench.py reports the end-to-end
+// Poisson number against it (the reference API returns u64 draws, so 8 B per draw must be written by the host cores).
+extern "C" int mmc_host_write_bandwidth(uint64_t bytes, int32_t threads, int32_t reps, double *gb_per_s, int32_t *threads_used) {
+    if (!gb_per_s || bytes < (1u << 20)) return -1;
+    const int nt = threads > 0 ? threads : mmc::widen_threads();
+    const size_t n = (size_t)bytes / 8;
+    uint64_t *buf = static_cast<uint64_t *>(aligned_alloc(4096, n * 8));
+    if (!buf) return -6;
+    double best = 0.0;
+    for (int r = 0; r < (reps > 0 ? reps : 3) + 1; ++r) {   // the first pass faults the pages in and is not timed
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t chunk = ((n + nt - 1) / nt + 63) & ~size_t(63);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) {
+            const size_t b = (size_t)t * chunk, e = std::min(n, b + chunk);
+            if (b >= e) break;
+            th.emplace_back([=]() {
+#if defined(__x86_64__)
+                if (__builtin_cpu_supports("avx2")) { mmc::fill_stream_avx2(buf + b, e - b, (uint64_t)r); return; }
+#endif
+                for (size_t i = b; i < e; ++i) buf[i] = (uint64_t)r;
+            });
+        }
+        for (auto &x : th) x.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r > 0 && dt > 0.0) best = std::max(best, (double)(n * 8) / dt / 1e9);
+    }
+    volatile uint64_t sink = buf[n / 2];
+    (void)sink;
+    free(buf);
+    *gb_per_s = best;
+    if (threads_used) *threads_used = nt;
+    return 0;
+}

@@ -39,6 +39,8 @@ struct mmc_mh {
     size_t d_trace_bytes = 0;
     // compact device->host pipeline (Poisson): double-buffered device + pinned host staging
     void *d_compact[2] = {nullptr, nullptr};
+    void *d_compact_only[2] = {nullptr, nullptr};   // mmc_mh_run_compact: device blocks copied straight to the caller
+    size_t compact_only_bytes = 0;
     void *h_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};
@@ -435,6 +437,51 @@ static int mh_run_poisson_compact(mmc_mh *h, int64_t n_collect, int64_t n_discar
     return check_error_flag(h, h->pipe_stream[0]);
 }
 
+// Opt-in compact output for the integer targets: the draws reach the caller as the u8 / u16 values the kernel emits
+// (1-2 B per draw over PCIe and in host memory instead of the reference API's 8 B `usize`), blocks of chains double
+// buffered like mh_run_poisson_compact but copied straight into the caller's [chains, n_collect] array.
+int mmc_mh_run_compact(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, int32_t *elem_bytes) {
+    MMC_REQUIRE(h && n_collect > 0 && n_discard >= 0 && out_host && elem_bytes, "mmc_mh_run_compact: bad arguments");
+    MMC_REQUIRE(is_int_target(h) && h->accept_mode == 1, "mmc_mh_run_compact: integer targets with table accept mode only");
+    MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run_compact: an output pitch is set on this handle");
+    const int eb = h->table_len <= 256 ? 1 : 2;
+    *elem_bytes = eb;
+    const size_t row_bytes = (size_t)n_collect * eb;
+    int64_t group = (int64_t)((size_t)(384u << 20) / row_bytes);
+    group = (group / 256) * 256;
+    if (group < 256) group = 256;
+    if (group > h->chains) group = h->chains;
+    const size_t need = (size_t)group * row_bytes;
+    if (h->compact_only_bytes < need) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->d_compact_only[k]) cudaFree(h->d_compact_only[k]);
+            h->d_compact_only[k] = nullptr;
+        }
+        h->compact_only_bytes = 0;
+        for (int k = 0; k < 2; ++k) {
+            MMC_CUDA(cudaMalloc(&h->d_compact_only[k], need));
+            if (!h->pipe_stream[k]) MMC_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[k], cudaStreamNonBlocking));
+            if (!h->pipe_event[k]) MMC_CUDA(cudaEventCreateWithFlags(&h->pipe_event[k], cudaEventDisableTiming));
+        }
+        h->compact_only_bytes = need;
+    }
+    const int64_t n_groups = (h->chains + group - 1) / group;
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const int k = (int)(g & 1);
+        const int64_t begin = g * group, cnt = std::min(group, h->chains - begin);
+        if (g >= 2) MMC_CUDA(cudaEventSynchronize(h->pipe_event[k]));   // the copy out of this device buffer has finished
+        int rc = run_poisson(h, n_collect, n_discard, h->d_compact_only[k], nullptr, h->pipe_stream[k], begin, cnt, true);
+        if (rc) return rc;
+        MMC_CUDA(cudaMemcpyAsync(static_cast<unsigned char *>(out_host) + (size_t)begin * row_bytes, h->d_compact_only[k],
+                                 (size_t)cnt * row_bytes, cudaMemcpyDeviceToHost, h->pipe_stream[k]));
+        MMC_CUDA(cudaEventRecord(h->pipe_event[k], h->pipe_stream[k]));
+    }
+    MMC_CUDA(cudaStreamSynchronize(h->pipe_stream[0]));
+    MMC_CUDA(cudaStreamSynchronize(h->pipe_stream[1]));
+    h->step += n_collect + n_discard;
+    return check_error_flag(h, h->pipe_stream[0]);
+}
+
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
     MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run: an output pitch only applies to mmc_mh_run_dev");
@@ -525,6 +572,7 @@ void mmc_mh_destroy(mmc_mh *h) {
     cudaFree(h->d_trace);
     for (int k = 0; k < 2; ++k) {
         cudaFree(h->d_compact[k]);
+        cudaFree(h->d_compact_only[k]);
         if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
         if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
         if (h->pipe_event[k]) cudaEventDestroy(h->pipe_event[k]);

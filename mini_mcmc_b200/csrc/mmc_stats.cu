@@ -19,12 +19,20 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the symbols are resolved with dlopen (see nccl_api)
 
 #include "mmc_common.cuh"
 
 using namespace mmc;
+
+extern "C" int64_t mmc_stats_partial_len(int64_t n, int64_t p);
+extern "C" int mmc_stats_partial_dev(const float *sample_dev, int64_t c_local, int64_t n, int64_t p, int64_t lag0,
+                                     int64_t n_lags, double *partial_dev, void *stream);
 
 namespace {
 
@@ -499,9 +507,253 @@ int launch_pass(const float *sample, int64_t c_local, int64_t n, int64_t p, int6
     return MMC_OK;
 }
 
+// ---------------------------------------------------------------- device-side finalisation
+// Same arithmetic as mmc_stats_finalize (f64 moment algebra, f32 Geyer loop as in src/stats.rs:518-545), one thread per
+// parameter, so that a round of the lag-window protocol costs one small D2H copy (rhat, ess, flag) instead of the whole
+// partial.  ws[0] = number of LOCAL chains summed over the ranks, ws + 1 = the partial rows.
+__global__ void stats_finalize_kernel(const double *__restrict__ ws, int64_t n, int p, int64_t lags_available,
+                                      float *__restrict__ rhat_out, float *__restrict__ ess_out, int *__restrict__ need_more) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p) return;
+    const double *partial = ws + 1;
+    const int64_t N = n / 2;
+    const double C = 2.0 * ws[0];
+    if (lags_available > N) lags_available = N;
+    const double sm = partial[q], sm2 = partial[p + q];
+    const double mbar = sm / C;
+    double ssd = sm2 - C * mbar * mbar;
+    if (ssd < 0.0) ssd = 0.0;
+    const double B = ssd * ((double)N / (C - 1.0));
+    const double W = partial[2 * (int64_t)p + q] / C;
+    const double var = (((double)N - 1.0) / (double)N) * W + B / (double)N;
+    const float within = (float)W, varf = (float)var;
+    rhat_out[q] = __fsqrt_rn(__fdiv_rn(within, varf));
+    auto rho = [&](int64_t t) {
+        const float avg = (float)(partial[(2 + t) * p + q] / C);
+        return __fadd_rn(-__fdiv_rn(__fadd_rn(-avg, within), varf), 1.0f);
+    };
+    float mn = N >= 2 ? __fadd_rn(rho(0), rho(1)) : 0.0f;
+    float o = 0.0f;
+    bool terminated = false;
+    int64_t t = 0;
+    for (; t + 1 < lags_available; t += 2) {
+        float pt = __fadd_rn(rho(t), rho(t + 1));
+        if (pt <= 0.0f) { terminated = true; break; }
+        if (pt > mn) pt = mn;
+        mn = pt;
+        o = __fadd_rn(o, pt);
+    }
+    if (!terminated && t + 1 < N) atomicOr(need_more, 1);
+    const float tau = __fadd_rn(-1.0f, __fmul_rn(2.0f, o));
+    ess_out[q] = __fmul_rn(__fmul_rn(__fdiv_rn(1.0f, tau), (float)C), (float)N);
+}
+
+__global__ void stats_set_count_kernel(double *ws, double c_local, int *need_more) {
+    ws[0] = c_local;
+    *need_more = 0;
+}
+
+// ---------------------------------------------------------------- NCCL (resolved at run time)
+// libminimcmc.so carries no link-time dependency on NCCL: a process that never shards its diagnostics does not need
+// the library, and a process that already holds a copy (torch bundles its own libnccl.so.2) must keep using THAT copy.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+    bool ok = false;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = nullptr;
+        if (const char *path = getenv("MMC_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy this process already uses (e.g. torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        bool all = true;
+        auto sym = [&](const char *name) { void *f = dlsym(h, name); if (!f) all = false; return f; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.CommCount = reinterpret_cast<decltype(api.CommCount)>(sym("ncclCommCount"));
+        api.CommUserRank = reinterpret_cast<decltype(api.CommUserRank)>(sym("ncclCommUserRank"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+        api.ok = all;
+    });
+    return api.ok ? &api : nullptr;
+}
+
+int nccl_fail(NcclApi *api, ncclResult_t r, const char *what) {
+    set_error("NCCL error %d (%s) in %s", (int)r, api && api->GetErrorString ? api->GetErrorString(r) : "?", what);
+    return MMC_ERR_CUDA;
+}
+
+}  // namespace
+
+struct mmc_comm {
+    ncclComm_t comm = nullptr;
+    bool owned = false;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+// grow-only per-process workspace of the diagnostics calls (cudaMalloc / cudaFree cost more than the kernels)
+struct StatsWorkspace {
+    std::mutex mutex;
+    double *ws = nullptr;      // [1 + (2 + N) p] doubles: count slot, partial rows
+    size_t ws_len = 0;
+    float *out = nullptr;      // [2 p] floats (rhat, ess) + 1 int flag, device
+    size_t out_len = 0;
+    float *h_out = nullptr;    // pinned mirror
+    int device = -1;
+};
+StatsWorkspace g_stats_ws;
+
+// The lag-window protocol shared by the single-GPU and the sharded call (src/stats.rs:416-423 + SURVEY B3): local partial
+// sums for a window of lags -> (sharded: ONE all-reduce of the new rows, the first one fused with the moment rows and the
+// chain count) -> Geyer termination checked on the device -> another, twice as wide window only if some parameter has
+// not terminated.
+int split_rhat_ess_protocol(const float *sample_dev, int64_t c_local, int64_t n, int64_t p, mmc_comm *comm, cudaStream_t s,
+                            float *rhat_host, float *ess_host) {
+    const int64_t N = n / 2;
+    const int64_t len = 1 + mmc_stats_partial_len(n, p);
+    NcclApi *api = nullptr;
+    if (comm && comm->nranks >= 1 && comm->comm) {
+        api = nccl_api();
+        MMC_REQUIRE(api, "NCCL is not available (libnccl.so.2 not found; set MMC_NCCL_LIB)");
+    }
+    StatsWorkspace &W = g_stats_ws;
+    std::lock_guard<std::mutex> guard(W.mutex);
+    int dev = 0;
+    MMC_CUDA(cudaGetDevice(&dev));
+    if (dev != W.device || (size_t)len > W.ws_len || (size_t)(2 * p + 1) > W.out_len) {
+        if (W.ws) cudaFree(W.ws);
+        if (W.out) cudaFree(W.out);
+        if (W.h_out) cudaFreeHost(W.h_out);
+        W.ws = nullptr; W.out = nullptr; W.h_out = nullptr; W.ws_len = W.out_len = 0; W.device = dev;
+        MMC_CUDA(cudaMalloc((void **)&W.ws, sizeof(double) * (size_t)len));
+        W.ws_len = (size_t)len;
+        MMC_CUDA(cudaMalloc((void **)&W.out, sizeof(float) * (size_t)(2 * p + 1)));
+        MMC_CUDA(cudaMallocHost((void **)&W.h_out, sizeof(float) * (size_t)(2 * p + 1)));
+        W.out_len = (size_t)(2 * p + 1);
+    }
+    double *d_partial = W.ws + 1;
+    int *d_flag = reinterpret_cast<int *>(W.out + 2 * p);
+    int64_t have = 0, block = kLagBlock;
+    while (have < N) {
+        const int64_t want = std::min<int64_t>(block, N - have);
+        if (have == 0) stats_set_count_kernel<<<1, 1, 0, s>>>(W.ws, (double)c_local, d_flag);
+        else MMC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        int rc = mmc_stats_partial_dev(sample_dev, c_local, n, p, have, want, d_partial, s);
+        if (rc) return rc;
+        if (api) {
+            // round 0: count + moment rows + the first lag rows are one contiguous range; later rounds: the new lag rows
+            double *buf = have == 0 ? W.ws : d_partial + (2 + have) * p;
+            const size_t cnt = have == 0 ? (size_t)(1 + (2 + want) * p) : (size_t)(want * p);
+            const ncclResult_t r = api->AllReduce(buf, buf, cnt, ncclFloat64, ncclSum, comm->comm, s);
+            if (r != ncclSuccess) return nccl_fail(api, r, "ncclAllReduce (split-Rhat / ESS partial sums)");
+        }
+        have += want;
+        stats_finalize_kernel<<<(unsigned)((p + 127) / 128), 128, 0, s>>>(W.ws, n, (int)p, have, W.out, W.out + p, d_flag);
+        MMC_CUDA(cudaGetLastError());
+        MMC_CUDA(cudaMemcpyAsync(W.h_out, W.out, sizeof(float) * (size_t)(2 * p + 1), cudaMemcpyDeviceToHost, s));
+        MMC_CUDA(cudaStreamSynchronize(s));
+        int flag;
+        memcpy(&flag, W.h_out + 2 * p, sizeof(int));
+        if (!flag) break;
+        block *= 2;  // geometric growth keeps the number of rounds logarithmic
+    }
+    if (rhat_host) memcpy(rhat_host, W.h_out, sizeof(float) * (size_t)p);
+    if (ess_host) memcpy(ess_host, W.h_out + p, sizeof(float) * (size_t)p);
+    return MMC_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+// ---------------------------------------------------------------- communicator (NCCL over NVLink / NVSwitch)
+int mmc_comm_unique_id(unsigned char *id128) {
+    MMC_REQUIRE(id128, "mmc_comm_unique_id: null buffer");
+    NcclApi *api = nccl_api();
+    MMC_REQUIRE(api, "NCCL is not available (libnccl.so.2 not found; set MMC_NCCL_LIB)");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId uid;
+    const ncclResult_t r = api->GetUniqueId(&uid);
+    if (r != ncclSuccess) return nccl_fail(api, r, "ncclGetUniqueId");
+    memcpy(id128, &uid, 128);
+    return MMC_OK;
+}
+
+int mmc_comm_create(mmc_comm **out, const unsigned char *id128, int32_t nranks, int32_t rank) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(out && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "mmc_comm_create: bad arguments");
+    NcclApi *api = nccl_api();
+    MMC_REQUIRE(api, "NCCL is not available (libnccl.so.2 not found; set MMC_NCCL_LIB)");
+    ncclUniqueId uid;
+    memcpy(&uid, id128, 128);
+    mmc_comm *c = new mmc_comm();
+    const ncclResult_t r = api->CommInitRank(&c->comm, nranks, uid, rank);   // binds the calling thread's current device
+    if (r != ncclSuccess) { delete c; return nccl_fail(api, r, "ncclCommInitRank"); }
+    c->owned = true;
+    c->nranks = nranks;
+    c->rank = rank;
+    *out = c;
+    return MMC_OK;
+}
+
+int mmc_comm_wrap(mmc_comm **out, void *nccl_comm) {
+    MMC_REQUIRE(out && nccl_comm, "mmc_comm_wrap: bad arguments");
+    NcclApi *api = nccl_api();
+    MMC_REQUIRE(api, "NCCL is not available (libnccl.so.2 not found; set MMC_NCCL_LIB)");
+    mmc_comm *c = new mmc_comm();
+    c->comm = static_cast<ncclComm_t>(nccl_comm);
+    ncclResult_t r = api->CommCount(c->comm, &c->nranks);
+    if (r == ncclSuccess) r = api->CommUserRank(c->comm, &c->rank);
+    if (r != ncclSuccess) { delete c; return nccl_fail(api, r, "ncclCommCount"); }
+    *out = c;
+    return MMC_OK;
+}
+
+int mmc_comm_info(mmc_comm *c, int32_t *nranks, int32_t *rank, int32_t *nccl_version) {
+    MMC_REQUIRE(c, "null communicator");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    if (nccl_version) {
+        int v = 0;
+        NcclApi *api = nccl_api();
+        if (api) api->GetVersion(&v);
+        *nccl_version = v;
+    }
+    return MMC_OK;
+}
+
+void mmc_comm_destroy(mmc_comm *c) {
+    if (!c) return;
+    NcclApi *api = nccl_api();
+    if (c->owned && c->comm && api) api->CommDestroy(c->comm);
+    delete c;
+}
+
+int mmc_split_rhat_ess_sharded(const float *sample_dev, int64_t c_local, int64_t n, int64_t p, mmc_comm *comm, void *stream,
+                               float *rhat_host, float *ess_host) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(sample_dev && c_local > 0 && n >= 2 && p > 0 && comm, "mmc_split_rhat_ess_sharded: bad arguments");
+    return split_rhat_ess_protocol(sample_dev, c_local, n, p, comm, (cudaStream_t)stream, rhat_host, ess_host);
+}
 
 int64_t mmc_stats_partial_len(int64_t n, int64_t p) { return (2 + n / 2) * p; }
 
@@ -584,52 +836,7 @@ int mmc_split_rhat_ess_dev(const float *sample_dev, int64_t c, int64_t n, int64_
     int rc = ensure_device();
     if (rc) return rc;
     MMC_REQUIRE(sample_dev && c > 0 && n >= 2 && p > 0, "mmc_split_rhat_ess_dev: bad arguments");
-    const int64_t N = n / 2;
-    const int64_t len = mmc_stats_partial_len(n, p);
-    cudaStream_t s = (cudaStream_t)stream;
-    // grow-only device workspace shared by the calls of this process (cudaMalloc / cudaFree cost 2-16 ms each on a
-    // busy context, more than the kernel itself); the lock mirrors "a handle is not thread-safe"
-    static std::mutex ws_mutex;
-    static double *ws = nullptr;
-    static size_t ws_len = 0;
-    static int ws_device = -1;
-    std::lock_guard<std::mutex> guard(ws_mutex);
-    int dev = 0;
-    MMC_CUDA(cudaGetDevice(&dev));
-    if (dev != ws_device || (size_t)len > ws_len) {
-        if (ws) cudaFree(ws);
-        ws = nullptr; ws_len = 0; ws_device = dev;
-        MMC_CUDA(cudaMalloc((void **)&ws, sizeof(double) * len));
-        ws_len = (size_t)len;
-    }
-    double *d_partial = ws;
-    const bool dbg = getenv("MMC_STATS_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double tA = now();
-    std::vector<double> h_partial((size_t)len, 0.0);
-    int64_t have = 0, block = kLagBlock;
-    int result = MMC_OK;
-    while (have < N) {
-        const int64_t want = std::min<int64_t>(block, N - have);
-        tA = now();
-        rc = mmc_stats_partial_dev(sample_dev, c, n, p, have, want, d_partial, stream);
-        if (rc) { result = rc; break; }
-        if (dbg) fprintf(stderr, "[stats] launch lags %lld+%lld %.3f ms\n", (long long)have, (long long)want, now() - tA);
-        tA = now();
-        const size_t off = have == 0 ? 0 : (size_t)(2 + have) * p;
-        const size_t cnt = (have == 0 ? 2 * p : 0) + (size_t)want * p;
-        cudaError_t e = cudaMemcpyAsync(h_partial.data() + off, d_partial + off, cnt * sizeof(double),
-                                        cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { result = cuda_fail(e, "stats D2H", __FILE__, __LINE__); break; }
-        if (dbg) fprintf(stderr, "[stats] sync+d2h %.3f ms\n", now() - tA);
-        have += want;
-        const int more = mmc_stats_finalize(h_partial.data(), c, n, p, have, rhat_host, ess_host);
-        if (more < 0) { result = more; break; }
-        if (more == 0) break;
-        block *= 2;  // geometric growth keeps the number of host round trips logarithmic
-    }
-    return result;
+    return split_rhat_ess_protocol(sample_dev, c, n, p, nullptr, (cudaStream_t)stream, rhat_host, ess_host);
 }
 
 int mmc_split_rhat_ess(const float *sample_host, int64_t c, int64_t n, int64_t p, float *rhat_host, float *ess_host) {

@@ -136,6 +136,20 @@ class MetropolisHastings:
         host = sample.cpu().numpy()
         return (host.view(np.uint64) if self._np_dtype == np.uint64 else host), stats
 
+    def run_compact(self, n_collect: int, n_discard: int, out=None) -> np.ndarray:
+        """Opt-in compact return type for the integer targets (mmc_mh_run_compact): [chains, n_collect, 1] draws as u8
+        (or u16 for tables of more than 256 states) instead of the reference API's `usize`.  `out` may be a pinned
+        host array of that dtype."""
+        eb = self.d2h_bytes_per_draw()
+        dt = np.uint8 if eb == 1 else np.uint16
+        if out is None:
+            out = np.empty((self.n_chains, n_collect, 1), dtype=dt)
+        assert out.dtype == dt and out.shape == (self.n_chains, n_collect, 1)
+        got = C.c_int32()
+        L.check(L.lib.mmc_mh_run_compact(self._h, C.c_int64(n_collect), C.c_int64(n_discard), L.vp(out), C.byref(got)))
+        assert got.value == eb
+        return out
+
     def d2h_bytes_per_draw(self) -> int:
         return int(L.lib.mmc_mh_d2h_bytes_per_draw(self._h))
 

@@ -41,33 +41,84 @@ def _as_device_f32(sample):
     return sample.to(device="cuda", dtype=torch.float32).contiguous()
 
 
-def split_rhat_mean_ess(sample, group=None):
+class Communicator:
+    """The library's own NCCL communicator (mmc_comm, include/minimcmc.h): rank 0 draws the 128-byte NCCL id, the bytes
+    travel through torch.distributed's existing process group (any out-of-band channel would do), and every rank calls
+    ncclCommInitRank inside libminimcmc.  Only the diagnostics all-reduce uses it."""
+
+    _cache = {}
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.nranks, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L.check(L.lib.mmc_comm_unique_id(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        dev = torch.device("cuda") if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        uid = uid.to(dev)
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        self._h = C.c_void_p()
+        L.check(L.lib.mmc_comm_create(C.byref(self._h), raw, C.c_int32(self.nranks), C.c_int32(self.rank)))
+
+    @classmethod
+    def for_group(cls, group=None):
+        key = id(group) if group is not None else None
+        if key not in cls._cache:
+            cls._cache[key] = cls(group)
+        return cls._cache[key]
+
+    @classmethod
+    def shutdown(cls):
+        """Destroy the cached communicators (call before torch.distributed.destroy_process_group)."""
+        for c in cls._cache.values():
+            c.close()
+        cls._cache.clear()
+
+    def info(self):
+        n, r, v = C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(L.lib.mmc_comm_info(self._h, C.byref(n), C.byref(r), C.byref(v)))
+        return dict(nranks=n.value, rank=r.value, nccl_version=v.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib.mmc_comm_destroy(self._h)
+            self._h = None
+
+
+def split_rhat_mean_ess(sample, group=None, comm=None):
     """split_rhat_mean_ess(sample [c, n, p]) -> (rhat[p], ess[p]) as numpy f32 (src/stats.rs:416-423).
 
     `sample` may be a host array or a CUDA tensor (kept in HBM).  If torch.distributed is initialised and
-    `group` is not False, `sample` is this rank's shard of the chains and the per-parameter moment sums and
-    summed autocovariances are all-reduced (NCCL over NVLink) before every rank finalises."""
-    import torch
+    `group` is not False (or a Communicator is passed), `sample` is this rank's shard of the chains and ONE library
+    call (mmc_split_rhat_ess_sharded) all-reduces the per-parameter moment sums and summed autocovariances with NCCL
+    over NVLink, checks the Geyer truncation on the device and returns the same rhat / ess on every rank."""
     import torch.distributed as dist
 
     x = _as_device_f32(sample)
     c, n, p = x.shape
-    sharded = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    sharded = comm is not None or (group is not False and dist.is_available() and dist.is_initialized()
+                                   and dist.get_world_size(group) > 1)
     rhat = np.empty(p, dtype=np.float32)
     ess = np.empty(p, dtype=np.float32)
     if not sharded:
         L.check(L.lib.mmc_split_rhat_ess_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), L.vp(rhat), L.vp(ess),
                                              L.current_stream_ptr()))
         return rhat, ess
-    def device_partial(partial, lag0, n_lags):
-        L.check(L.lib.mmc_stats_partial_dev(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), C.c_int64(lag0),
-                                            C.c_int64(n_lags), L.vp(partial), L.current_stream_ptr()))
-
-    return sharded_split_rhat_ess(device_partial, c, n, p, group, torch.device("cuda"))
+    if comm is None:
+        comm = Communicator.for_group(group)
+    L.check(L.lib.mmc_split_rhat_ess_sharded(L.vp(x), C.c_int64(c), C.c_int64(n), C.c_int64(p), comm._h,
+                                             L.current_stream_ptr(), L.vp(rhat), L.vp(ess)))
+    return rhat, ess
 
 
 def sharded_split_rhat_ess(partial_fn, c_local, n, p, group, device):
-    """Host side of the sharded diagnostics (one process per GPU).
+    """The lag-window protocol of mmc_split_rhat_ess_sharded restated over torch.distributed, so that the N > 1 logic is
+    testable with the gloo backend on CPU ranks (tests/test_multirank_gloo.py); the GPU path is the library call.
 
     partial_fn(partial, lag0, n_lags) fills rows [2 + lag0, 2 + lag0 + n_lags) (and rows 0-1 when lag0 == 0) of
     the f64 [2 + n/2, p] `partial` tensor with this rank's sums over its LOCAL split chains.  The partials are

@@ -26,6 +26,26 @@ import mini_mcmc_b200 as mm  # noqa: E402
 RANK = int(os.environ.get("RANK", "0"))
 LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def peaks():
+    """Roofline denominators: HBM copy bandwidth and dense bf16 throughput measured by the driver on this pool
+    (MEASURED_PEAKS.json), else the profiling guide's fallbacks; FP32 SIMT peak = 148 SMs x 128 lanes x 2 x SM clock
+    (derived; an FFMA micro-benchmark reaches 72-74 TFLOP/s); the 3xTF32 dense path is held against TF32 / 3 with
+    TF32 = bf16 / 2."""
+    hbm, bf16, mhz, src = 6650.0, 1500.0, 1965.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        hbm, bf16, mhz, src = float(d["hbm_gbs"]), float(d["bf16_tflops"]), float(d.get("sm_max_mhz", 1965.0)), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    fp32 = 148 * 128 * 2 * mhz * 1e6 / 1e12
+    return dict(hbm_gbs=hbm, fp32_tflops=fp32, tf32x3_tflops=bf16 / 2.0 / 3.0, source=src)
+
+
+RESULTS = []
 
 
 def barrier():
@@ -53,8 +73,9 @@ def timed(fn, warm=1, reps=3):
 
 
 def emit(**kw):
-    if RANK == 0:
-        kw["n_gpus"] = WORLD
+    kw["n_gpus"] = WORLD
+    RESULTS.append(kw)
+    if RANK == 0 and __name__ == "__main__":
         print(json.dumps(kw), flush=True)
 
 
@@ -118,9 +139,13 @@ def c3(args):
         import oracle
         _, cess = oracle.split_rhat_mean_ess(cpu_out["x"])
         cpu_ess = float(cess.min()) / (8192 * (nc + nd) / cpu_rate)
-    emit(config="C3 rosenbrock3d_hmc 262144 chains/GPU, L=50, run(400,50) (weak)", kernel_ms=ms,
+    pk = peaks()
+    tf = tr / WORLD * 2442 / ms / 1e9
+    emit(config="C3 rosenbrock3d_hmc 262144 chains/GPU, L=50, run(400,50) (weak)", scaling="weak", ms=ms, kernel_ms=ms,
          transitions_per_s=tr / ms * 1e3, grad_evals_per_s=tr * (L + 1) / ms * 1e3,
-         tflops_per_gpu=tr / WORLD * 2442 / ms / 1e9, fp32_frac_of_74p4=tr / WORLD * 2442 / ms / 1e9 / 74.4,
+         tflops_per_gpu=tf,
+         roofline=dict(bound="fp32", achieved=tf, peak=pk["fp32_tflops"], unit="TFLOP/s", frac=tf / pk["fp32_tflops"],
+                       kernel="hmc_run_pair_kernel", algorithmic_flop_per_transition=2442),
          ess_min=float(ess.min()), ess_per_s=float(ess.min()) / ms * 1e3, cpu_transitions_per_s=cpu_rate, cpu_cores=cores,
          cpu_ess_per_s=cpu_ess, cpu_sample="8192 chains, same run(400,50); ESS/s = min-ESS of those chains / their wall time")
     del out
@@ -136,10 +161,15 @@ def c4(args):
     tgt = mm.DenseGaussian(mean, cov)
     init = mm.init_device(chains, D, 42, chain_offset=RANK * chains).cpu().numpy()
     res = {}
-    for path, name in ((2, "tcgen05_3xTF32_cta_pair"), (1, "tcgen05_3xTF32_1cta"), (0, "fp32_simt")):
-        h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_chain_offset(RANK * chains).set_gemm_path(path)
+    pk = peaks()
+    # "default" = what a caller of mmc_hmc_create + mmc_hmc_run gets (tcgen05 CTA pairs); the others on request
+    paths = [(-1, "default")] + ([(1, "tcgen05_3xTF32_1cta"), (0, "fp32_simt")] if getattr(args, "all_paths", False) else [])
+    for path, name in paths:
+        h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_chain_offset(RANK * chains)
+        if path >= 0:
+            h.set_gemm_path(path)
         out = torch.empty((chains, steps, D), dtype=torch.float32, device="cuda")
-        ms = timed(lambda: h.run_device(steps, 0, out=out), warm=1, reps=2)
+        ms = timed(lambda: h.run_device(steps, 0, out=out), warm=1, reps=3)
         ge = total * steps * (L + 1)
         res[name] = dict(ms=ms, grad_evals_per_s=ge / ms * 1e3, us_per_leapfrog=ms * 1e3 / (steps * (L + 1)),
                          tflops_fp32_equiv_per_gpu=ge / WORLD * (2 * D * D + 4 * D) / ms / 1e9)
@@ -153,8 +183,14 @@ def c4(args):
             o.hmc_run_reference(ot, init[:64], 0.05, L, 2, 0, seed=1, want_out=False)
             return 64 * 2 * (L + 1)
         cpu_rate, cores = cpu(f)
-    emit(config=f"C4 dense Gaussian D=1024 HMC, 32768 chains total ({chains}/GPU, strong), L=50", **res,
-         cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores)
+    d = res["default"]
+    emit(config=f"C4 dense Gaussian D=1024 HMC, 32768 chains total ({chains}/GPU, strong), L=50, {steps} transitions",
+         scaling="strong", ms=d["ms"], grad_evals_per_s=d["grad_evals_per_s"], us_per_leapfrog=d["us_per_leapfrog"],
+         roofline=dict(bound="tensor", achieved=d["tflops_fp32_equiv_per_gpu"], peak=pk["tf32x3_tflops"], unit="TFLOP/s",
+                       frac=d["tflops_fp32_equiv_per_gpu"] / pk["tf32x3_tflops"], kernel="dense_gemm_tc_pair_kernel",
+                       note="fp32-equivalent flops (2 D^2 + 4 D per grad-eval); the 3xTF32 split issues 3 MMAs per product, "
+                            "so the denominator is TF32 / 3 = measured dense bf16 / 6"),
+         paths=res, cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores)
 
 
 def c5(args):
@@ -163,10 +199,12 @@ def c5(args):
     init = mm.init_device(chains, D, 42, chain_offset=RANK * chains).cpu().numpy()
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=10).set_seed(7).set_chain_offset(RANK * chains)
     out = torch.empty((chains, nc, D), dtype=torch.float32, device="cuda")
-    # warm-up on a throw-away sampler: module load, scratch allocation and clocks are not part of the measurement
+    # warm-up on a throw-away sampler: module load, scratch allocation, clocks and (sharded) the NCCL communicator of the
+    # diagnostics are not part of the measurement
     w = mm.NUTS(mm.RosenbrockND(), init[:2048], 0.95, scalar_dtype="f32", max_depth=10).set_seed(8)
-    w.run_device(20, 20, progress=True)
-    del w
+    wo = w.run_device(20, 20, progress=True)
+    mm.split_rhat_mean_ess(wo, group=None if WORLD > 1 else False)
+    del w, wo
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -180,11 +218,18 @@ def c5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(g)
     ms = t.item()
-    barrier()
-    t0 = time.perf_counter()
-    rhat, ess = mm.split_rhat_mean_ess(out, group=None if WORLD > 1 else False)   # NCCL all-reduce of the partials when sharded
-    barrier()
-    stats_ms = (time.perf_counter() - t0) * 1e3
+    # diagnostics: ONE library call per rank (mmc_split_rhat_ess_sharded: local partial sums, NCCL all-reduce, Geyer check
+    # on the device), timed between device-synchronised barriers, best of 3
+    stats_ms = None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        rhat, ess = mm.split_rhat_mean_ess(out, group=None if WORLD > 1 else False)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+        if WORLD > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        stats_ms = dt.item() if stats_ms is None else min(stats_ms, dt.item())
     cpu_rate = cores = cpu_ess = None
     if RANK == 0 and not args.no_cpu:
         cpu_out = {}
@@ -196,14 +241,39 @@ def c5(args):
         import oracle
         _, cess = oracle.split_rhat_mean_ess(cpu_out["x"])
         cpu_ess = float(cess.min()) / (cpu_out["g"] / cpu_rate)
-    emit(config=f"C5 NUTS RosenbrockND D=100, 65536 chains total ({chains}/GPU, strong), run_progress(400,400)", sample_ms=ms,
-         grad_evals_per_s=g[0].item() / ms * 1e3, transitions_per_s=g[1].item() / ms * 1e3,
-         tflops_per_gpu=g[0].item() / WORLD * 2285 / ms / 1e9, stats_ms=stats_ms, ess_min=float(ess.min()),
-         ess_per_s_sampling=float(ess.min()) / ms * 1e3, ess_per_s_incl_stats=float(ess.min()) / (ms + stats_ms) * 1e3,
-         rhat_min=float(rhat.min()), rhat_max=float(rhat.max()), depth_hist=cnt["depth_hist"],
-         lanes_per_chain=s.lanes_per_chain,
+    pk = peaks()
+    tf = g[0].item() / WORLD * 2285 / ms / 1e9
+    # reference convention: rhat = sqrt(W / var+) (src/stats.rs:425-427), i.e. the inverse of the textbook value
+    rmin, rmax = float(rhat.min()), float(rhat.max())
+    emit(config=f"C5 NUTS RosenbrockND D=100, 65536 chains total ({chains}/GPU, strong), run_progress(400,400)", scaling="strong",
+         ms=ms + stats_ms, sample_ms=ms, stats_ms=stats_ms,
+         grad_evals_per_s=g[0].item() / ms * 1e3, transitions_per_s=g[1].item() / ms * 1e3, tflops_per_gpu=tf,
+         roofline=dict(bound="fp32", achieved=tf, peak=pk["fp32_tflops"], unit="TFLOP/s", frac=tf / pk["fp32_tflops"],
+                       kernel="nuts_group_kernel", algorithmic_flop_per_grad_eval=2285),
+         stats=dict(ms=stats_ms, sample_GB=chains * nc * D * 4 / 1e9, collective="ncclAllReduce (libminimcmc communicator)" if WORLD > 1 else None),
+         ess_min=float(ess.min()), ess_per_s_sampling=float(ess.min()) / ms * 1e3,
+         ess_per_s_incl_stats=float(ess.min()) / (ms + stats_ms) * 1e3,
+         rhat_min=rmin, rhat_max=rmax, textbook_rhat_max=1.0 / rmin if rmin > 0 else None,
+         convergence_note="run_progress(400, 400) from N(0,1) starts has NOT converged on the 100-dim Rosenbrock ridge "
+                          "(textbook Rhat >> 1.01), so ESS/s here is a throughput proxy for the diagnostics path, not a "
+                          "usable effective sample size",
+         depth_hist=cnt["depth_hist"], lanes_per_chain=s.lanes_per_chain,
          cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores, cpu_ess_per_s=cpu_ess,
          cpu_sample="2048 chains, same run_progress(400,400); ESS/s = min-ESS of those chains / their wall time")
+
+
+def run_configs(names, no_cpu=True, all_paths=False):
+    """In-process entry for bench.py: measures the named configs on the current process group and returns their result
+    dicts keyed by config id (every rank must call it; the dicts are identical on all ranks up to rank-0-only CPU columns)."""
+    args = argparse.Namespace(no_cpu=no_cpu, c2_chains=1 << 20, all_paths=all_paths)
+    RESULTS.clear()
+    for c in names:
+        try:
+            {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}[c](args)
+        except Exception as e:  # noqa: BLE001  (a side measurement must not take the headline down)
+            RESULTS.append({"config": f"{c.upper()} failed", "error": repr(e)[:300], "n_gpus": WORLD})
+        torch.cuda.empty_cache()
+    return {str(r["config"]).split()[0]: r for r in RESULTS}
 
 
 def main():
@@ -211,6 +281,7 @@ def main():
     ap.add_argument("--configs", default="c1,c2,c3,c4,c5")
     ap.add_argument("--c2-chains", type=int, default=1 << 20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--all-paths", action="store_true", help="C4: also time the 1-CTA tcgen05 and the FP32 SIMT GEMM paths")
     args = ap.parse_args()
     torch.cuda.set_device(LOCAL)
     if WORLD > 1:
@@ -223,6 +294,7 @@ def main():
         {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}[c.strip()](args)
         torch.cuda.empty_cache()
     if WORLD > 1:
+        mm.Communicator.shutdown()
         dist.destroy_process_group()
 
 

@@ -211,3 +211,17 @@ def test_categorical_mh_frequencies_and_guards(mm):
         mm.MetropolisHastings(cat, mm.NonnegativeProposal(), np.full((2, 1), 3, dtype=np.uint64))   # start outside the support
     with pytest.raises(Exception):
         mh.set_accept_mode(0)
+
+
+def test_poisson_compact_output_equals_widened_output(mm):
+    """mmc_mh_run_compact (opt-in u8 return type) returns the very draws mmc_mh_run widens to the reference's u64."""
+    chains = 3000
+    init = np.zeros((chains, 1), dtype=np.uint64)
+    a = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(5)
+    b = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.NonnegativeProposal(), init).seed(5)
+    wide = a.run(120, 30)
+    compact = b.run_compact(120, 30)
+    assert compact.dtype == np.uint8 and compact.shape == wide.shape
+    np.testing.assert_array_equal(compact.astype(np.uint64), wide)
+    # continuation: both handles advanced by the same 150 steps
+    np.testing.assert_array_equal(b.run_compact(10, 0).astype(np.uint64), a.run(10, 0))

@@ -93,3 +93,35 @@ def test_basic_stats_matches_oracle(mm):
     exp = oracle.basic_stats(d)
     for k in ("min", "median", "max", "mean", "std"):
         assert abs(getattr(got, k) - exp[k]) <= 1e-6 * max(1.0, abs(exp[k]))
+
+
+def test_library_communicator_single_rank(mm):
+    """mmc_split_rhat_ess_sharded on a one-rank NCCL communicator created inside the library (mmc_comm_unique_id /
+    mmc_comm_create): the all-reduce path runs on a single GPU and returns what the unsharded call returns."""
+    import ctypes as C
+
+    import torch
+
+    from mini_mcmc_b200 import _lib as L
+
+    rng = np.random.default_rng(12)
+    x = _ar1(rng, 10, 300, 12, 0.9, 2.0)
+    x[3] -= 0.4
+    uid = (C.c_ubyte * 128)()
+    L.check(L.lib.mmc_comm_unique_id(uid))
+    comm = C.c_void_p()
+    L.check(L.lib.mmc_comm_create(C.byref(comm), uid, C.c_int32(1), C.c_int32(0)))
+    n, r, v = C.c_int32(), C.c_int32(), C.c_int32()
+    L.check(L.lib.mmc_comm_info(comm, C.byref(n), C.byref(r), C.byref(v)))
+    assert (n.value, r.value) == (1, 0) and v.value >= 21800
+    xd = torch.from_numpy(x).cuda()
+    rhat, ess = np.empty(12, dtype=np.float32), np.empty(12, dtype=np.float32)
+    L.check(L.lib.mmc_split_rhat_ess_sharded(L.vp(xd), C.c_int64(10), C.c_int64(300), C.c_int64(12), comm,
+                                             L.current_stream_ptr(), L.vp(rhat), L.vp(ess)))
+    L.lib.mmc_comm_destroy(comm)
+    r0, e0 = mm.split_rhat_mean_ess(x, group=False)
+    np.testing.assert_array_equal(rhat, r0)
+    np.testing.assert_array_equal(ess, e0)
+    exp_rhat, exp_ess = oracle.split_rhat_mean_ess(x)
+    np.testing.assert_allclose(rhat, exp_rhat, rtol=1e-4)
+    np.testing.assert_allclose(ess, exp_ess, rtol=2e-3)
