@@ -74,6 +74,7 @@ typedef enum {
     MMC_T_DENSE_GAUSSIAN = 7,  /* D-dim dense Gaussian (config C4)  params = norm_const; vec = mean[D]; mat = precision[D,D] */
     MMC_T_STD_NORMAL = 8,      /* test target          src/nuts.rs:1024-1037                                               */
     MMC_T_CATEGORICAL = 9,     /* Categorical          src/distributions.rs:422-477  (mmc_mh_create_categorical)            */
+    MMC_T_TABULATED = 10,      /* any Target<i32|usize, f64> given as a table of log-probabilities (mmc_mh_create_tabulated) */
     MMC_T_CUSTOM_BASE = 1000
 } mmc_target_kind;
 
@@ -88,7 +89,9 @@ typedef struct {
 /* Proposals for Metropolis-Hastings (trait Proposal, src/distributions.rs:92-101). */
 typedef enum {
     MMC_Q_ISO_GAUSSIAN = 1, /* IsotropicGaussian::sample/logp  src/distributions.rs:360-392  param = std */
-    MMC_Q_NONNEG_RW = 2     /* NonnegativeProposal             examples/poisson_mh.rs:28-77              */
+    MMC_Q_NONNEG_RW = 2,    /* NonnegativeProposal             examples/poisson_mh.rs:28-77              */
+    MMC_Q_REFLECT_RW = 3    /* symmetric +-1 walk clamped to the support (PoissonRandomWalk / BinomialRandomWalk,
+                               tests/metrohast_poisson_test.rs:52-84,184-214); mmc_mh_create_tabulated only */
 } mmc_proposal_kind;
 
 typedef struct {
@@ -114,7 +117,10 @@ int mmc_init_positions_dev(float *out_dev, int64_t n, int64_t d, uint64_t seed, 
 /* ------------------------------------------------------------------ Metropolis-Hastings
  * Replaces MetropolisHastings::new / .seed / ChainRunner::run for the built-in target+proposal pairs
  * (src/metropolis_hastings.rs:149-193,303-315; src/core.rs:55-73,176-186).
- * state dtype: MMC_F64 (continuous targets) or MMC_U64 (`usize` state of the Poisson example). */
+ * state dtype: MMC_F64 or MMC_F32 (continuous targets; MetropolisHastings<S, T, ..> is generic over the float type,
+ * src/metropolis_hastings.rs:87 - with MMC_F32 every operation runs in f32, in/out arrays are f32, replay tapes stay f64
+ * arrays holding f32 values) or MMC_U64 (`usize` state of the Poisson example).  IsotropicGaussian targets run for any
+ * dim <= 256; custom targets / proposals come from mmc_register_mh_target. */
 typedef struct mmc_mh mmc_mh;
 
 typedef struct {
@@ -132,6 +138,12 @@ int mmc_mh_create(mmc_mh **h, const mmc_target_desc *target, const mmc_proposal_
  * for k < n, -inf beyond) with the +-1 NonnegativeProposal of examples/poisson_mh.rs:28-77; u64 state [chains], dim 1.
  * Runs through the same table-driven integer kernel as the Poisson target (threshold accept mode). */
 int mmc_mh_create_categorical(mmc_mh **out, const double *probs, int32_t n_categories, const void *init_host, int64_t chains);
+/* MetropolisHastings over any integer-state target tabulated on [0, n_states): logp[k] = Target::unnorm_logp(&[k]) as the
+ * caller's host code evaluates it, -inf beyond the table.  proposal_kind = MMC_Q_NONNEG_RW or MMC_Q_REFLECT_RW.  This is
+ * how the `i32` Poisson / Binomial variants of tests/metrohast_poisson_test.rs:18-85,157-214 run (state is carried as u64).
+ * The accept thresholds are bisected on the host from (lp' + q_b) - (lp + q_f) > ln(u), like the Poisson target. */
+int mmc_mh_create_tabulated(mmc_mh **out, const double *logp, int32_t n_states, int32_t proposal_kind, const void *init_host,
+                            int64_t chains);
 int mmc_mh_seed(mmc_mh *h, uint64_t seed);                  /* .seed(s): also resets the step counter */
 int mmc_mh_set_chain_offset(mmc_mh *h, int64_t offset);     /* first global chain id held by this handle */
 /* Poisson accept test: 0 = evaluate (lp'+qb)-(lp+qf) > ln(u) in f64 on the device,
@@ -200,6 +212,17 @@ void mmc_hmc_destroy(mmc_hmc *h);
  * Replaces the role of the BatchedGradientTarget trait bound of HMC (src/distributions.rs:65-76, src/hmc.rs:36-57). */
 typedef int (*mmc_hmc_launch_fn)(const void *hmc_params, int replay, int exact, const double *target_params, void *stream);
 int mmc_register_hmc_target(const char *name, int32_t dim, mmc_hmc_launch_fn fn);
+/* The same for NUTS (any GradientTarget in NUTS::new, src/nuts.rs:123-129, trait src/distributions.rs:78-88) and for
+ * Metropolis-Hastings (any Target, optionally with its own Proposal, in MetropolisHastings::new,
+ * src/metropolis_hastings.rs:149-159, traits src/distributions.rs:92-108).  A name registered for several samplers keeps
+ * ONE kind id; MMC_REGISTER_NUTS_TARGET / MMC_REGISTER_MH_TARGET / MMC_REGISTER_MH_PAIR in minimcmc_target.cuh generate
+ * the launchers.  query_only != 0: only report the persistent grid and the scratch floats the launch needs. */
+typedef int (*mmc_nuts_launch_fn)(const void *nuts_params, int scalar_f64, int replay, int exact, const double *target_params,
+                                  int sm_count, int64_t *grid, size_t *scratch_floats, int query_only, void *stream);
+int mmc_register_nuts_target(const char *name, int32_t dim, mmc_nuts_launch_fn fn);
+typedef int (*mmc_mh_launch_fn)(const void *mh_params, int replay, const double *target_params, double proposal_param,
+                                void *stream);
+int mmc_register_mh_target(const char *name, int32_t dim, mmc_mh_launch_fn fn);
 int mmc_lookup_target(const char *name); /* kind id, or MMC_ERR_INVALID when unknown */
 
 /* ------------------------------------------------------------------ NUTS

@@ -34,8 +34,36 @@
 //     MMC_REGISTER_GIBBS_CONDITIONAL(my_conditional, MyConditional)
 //
 // `my_conditional_register()` returns the kind (>= MMC_G_CUSTOM_BASE) for mmc_conditional_desc.kind.
+//
+// NUTS takes the same thread-form functor (the reference's `GradientTarget`, src/distributions.rs:78-88, in NUTS::new,
+// src/nuts.rs:123-129): MMC_REGISTER_NUTS_TARGET(my_target, MyTarget) instantiates the one-chain-per-warp tree kernel
+// (nuts_run_kernel; every lane evaluates the functor on the gathered vector, kDim <= 128) for both arithmetic policies,
+// both scalar types and native / replay draws, and defines `my_target_register_nuts()`.  A name registered for several
+// samplers keeps one kind id.
+//
+// Metropolis-Hastings (the reference's `Target<T, F>` / `Proposal<T, F>`, src/distributions.rs:92-108, in
+// MetropolisHastings::new, src/metropolis_hastings.rs:149-159) takes f64 functors:
+//
+//     struct MyMhTarget {
+//         static constexpr int kDim = 2;
+//         __host__ explicit MyMhTarget(const double *p);
+//         __device__ double unnorm_logp(const double (&x)[kDim]) const;
+//     };
+//     MMC_REGISTER_MH_TARGET(my_mh_target, MyMhTarget)       // with the built-in IsotropicGaussian proposal
+//
+//     struct MyProposal {                                    // optional: a custom proposal
+//         __host__ explicit MyProposal(double param);
+//         // z: kDim standard normals of this step (Philox / replay tape); the reference's `sample(&mut self, current)`
+//         template <int D> __device__ void sample(const double (&cur)[D], const double (&z)[D], double (&out)[D]) const;
+//         template <int D> __device__ double logp(const double (&from)[D], const double (&to)[D]) const;
+//     };
+//     MMC_REGISTER_MH_PAIR(my_pair, MyMhTarget, MyProposal)
+//
+// Both define `<name>_register_mh()`.
 #include "../mini_mcmc_b200/csrc/mmc_gibbs.cuh"
 #include "../mini_mcmc_b200/csrc/mmc_hmc.cuh"
+#include "../mini_mcmc_b200/csrc/mmc_mh.cuh"
+#include "../mini_mcmc_b200/csrc/mmc_nuts_inst.cuh"
 #include "../mini_mcmc_b200/csrc/mmc_targets.cuh"
 
 #define MMC_REGISTER_HMC_TARGET(NAME, FUNCTOR)                                                                      \
@@ -59,3 +87,40 @@
     extern "C" int NAME##_register(void) {                                                                          \
         return mmc_register_gibbs_conditional(#NAME, FUNCTOR::kDim, NAME##_mmc_gibbs_launch);                       \
     }
+
+#define MMC_REGISTER_NUTS_TARGET(NAME, FUNCTOR)                                                                     \
+    template <class A, class ST, bool kReplay>                                                                      \
+    static int NAME##_mmc_nuts_one(const mmc::NutsParams &p, const double *tp, int sms, int64_t *grid, size_t *scratch, \
+                                   bool query, cudaStream_t stream) {                                               \
+        constexpr int E = (FUNCTOR<A>::kDim + 31) / 32;                                                             \
+        mmc::WSmall<FUNCTOR<A>, E> w{FUNCTOR<A>(tp)};                                                               \
+        return mmc::nuts_launch_one<mmc::WSmall<FUNCTOR<A>, E>, A, ST, E, kReplay>(w, p, sms, grid, scratch, query, stream); \
+    }                                                                                                                \
+    template <class A>                                                                                               \
+    static int NAME##_mmc_nuts_policy(const mmc::NutsParams &p, int f64, int replay, const double *tp, int sms,     \
+                                      int64_t *grid, size_t *scratch, bool query, cudaStream_t s) {                 \
+        if (f64) return replay ? NAME##_mmc_nuts_one<A, double, true>(p, tp, sms, grid, scratch, query, s)          \
+                               : NAME##_mmc_nuts_one<A, double, false>(p, tp, sms, grid, scratch, query, s);        \
+        return replay ? NAME##_mmc_nuts_one<A, float, true>(p, tp, sms, grid, scratch, query, s)                    \
+                      : NAME##_mmc_nuts_one<A, float, false>(p, tp, sms, grid, scratch, query, s);                  \
+    }                                                                                                                \
+    static int NAME##_mmc_nuts_launch(const void *pv, int f64, int replay, int exact, const double *tp, int sms,    \
+                                      int64_t *grid, size_t *scratch, int query, void *stream) {                    \
+        const mmc::NutsParams &p = *static_cast<const mmc::NutsParams *>(pv);                                       \
+        cudaStream_t s = static_cast<cudaStream_t>(stream);                                                          \
+        return exact ? NAME##_mmc_nuts_policy<mmc::Exact>(p, f64, replay, tp, sms, grid, scratch, query != 0, s)    \
+                     : NAME##_mmc_nuts_policy<mmc::Fast>(p, f64, replay, tp, sms, grid, scratch, query != 0, s);    \
+    }                                                                                                                \
+    extern "C" int NAME##_register_nuts(void) {                                                                     \
+        return mmc_register_nuts_target(#NAME, FUNCTOR<mmc::Fast>::kDim, NAME##_mmc_nuts_launch);                   \
+    }
+
+#define MMC_REGISTER_MH_PAIR(NAME, TARGET, PROPOSAL)                                                                \
+    static int NAME##_mmc_mh_launch(const void *pv, int replay, const double *tp, double qparam, void *stream) {     \
+        const mmc::MhContParams &p = *static_cast<const mmc::MhContParams *>(pv);                                   \
+        return mmc::launch_mh_functor<TARGET, PROPOSAL, double, TARGET::kDim>(TARGET(tp), PROPOSAL(qparam), p, replay != 0, \
+                                                                              static_cast<cudaStream_t>(stream));   \
+    }                                                                                                                \
+    extern "C" int NAME##_register_mh(void) { return mmc_register_mh_target(#NAME, TARGET::kDim, NAME##_mmc_mh_launch); }
+
+#define MMC_REGISTER_MH_TARGET(NAME, TARGET) MMC_REGISTER_MH_PAIR(NAME, TARGET, mmc::IsoProposalF<double>)

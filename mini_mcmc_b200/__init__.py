@@ -7,7 +7,7 @@ kernels inside libminimcmc.so; there is no CPU fallback.
 from . import _lib
 from . import io
 from .core import init, init_det, init_device, init_with_seed
-from .distributions import (Categorical, ConstantConditional, CustomConditional, CustomTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, IsotropicGaussian, MixtureConditional,
+from .distributions import (Categorical, ConstantConditional, CustomConditional, CustomProposal, CustomTarget, ReflectingRandomWalk, TabulatedTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, IsotropicGaussian, MixtureConditional,
                             NonnegativeProposal,
                             PoissonTarget, Rosenbrock2D, RosenbrockND, StandardNormalTarget)
 from .gibbs import GibbsSampler
@@ -20,4 +20,4 @@ from .stats import BasicStats, Communicator, RunStats, basic_stats, split_rhat_m
 __all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "NUTS", "Gaussian2D",
            "IsotropicGaussian", "PoissonTarget", "NonnegativeProposal", "RosenbrockND", "Rosenbrock2D",
            "DiffableGaussian2D", "DenseGaussian", "CustomTarget", "StandardNormalTarget", "RunStats", "BasicStats", "basic_stats",
-           "split_rhat_mean_ess", "Communicator", "GibbsSampler", "Categorical", "ConstantConditional", "CustomConditional", "MixtureConditional", "MultiChainTracker", "ChainTrackers", "io"]
+           "split_rhat_mean_ess", "Communicator", "GibbsSampler", "Categorical", "TabulatedTarget", "ReflectingRandomWalk", "CustomProposal", "ConstantConditional", "CustomConditional", "MixtureConditional", "MultiChainTracker", "ChainTrackers", "io"]

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MMC_LIB_PATH", os.path.join(_HERE, "libminimcmc.so"))
 MMC_F32, MMC_F64, MMC_U64 = 0, 1, 2
 (T_GAUSSIAN2D, T_ISO_GAUSSIAN, T_POISSON, T_ROSENBROCK_ND, T_ROSENBROCK_2D, T_DIFF_GAUSSIAN2D, T_DENSE_GAUSSIAN,
  T_STD_NORMAL) = range(1, 9)
-Q_ISO_GAUSSIAN, Q_NONNEG_RW = 1, 2
+Q_ISO_GAUSSIAN, Q_NONNEG_RW, Q_REFLECT_RW, Q_CUSTOM = 1, 2, 3, 100
 G_CONSTANT, G_MIXTURE2 = 1, 2
 
 ERR_NAMES = {0: "MMC_OK", -1: "MMC_ERR_INVALID", -2: "MMC_ERR_NO_DEVICE", -3: "MMC_ERR_CUDA",

@@ -31,6 +31,17 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int ensure_device();
 int sm_count();
 
+// registry of custom device targets (include/minimcmc_target.cuh): one entry per name, one launcher per sampler
+struct CustomTargetEntry {
+    int dim = 0;
+    mmc_hmc_launch_fn hmc = nullptr;
+    mmc_nuts_launch_fn nuts = nullptr;
+    mmc_mh_launch_fn mh = nullptr;
+};
+int custom_target_register(const char *name, int dim, mmc_hmc_launch_fn hmc, mmc_nuts_launch_fn nuts, mmc_mh_launch_fn mh);
+bool custom_target_get(int kind, CustomTargetEntry *out, const char **name = nullptr);
+int custom_target_lookup(const char *name);
+
 // ---------------------------------------------------------------- arithmetic policies
 // Fast : plain operators, nvcc contracts a*b+c into FFMA (throughput build).
 // Exact: round-to-nearest intrinsics that are never contracted, so a replayed trajectory reproduces

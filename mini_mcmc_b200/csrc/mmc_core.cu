@@ -6,10 +6,62 @@
 
 #include <cmath>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "mmc_common.cuh"
 
 namespace mmc {
+
+namespace {
+struct NamedTarget { std::string name; CustomTargetEntry e; };
+std::mutex g_custom_mutex;
+std::vector<NamedTarget> &custom_targets() {
+    static std::vector<NamedTarget> r;
+    return r;
+}
+}  // namespace
+
+int custom_target_register(const char *name, int dim, mmc_hmc_launch_fn hmc, mmc_nuts_launch_fn nuts, mmc_mh_launch_fn mh) {
+    if (!name || dim <= 0 || (!hmc && !nuts && !mh)) {
+        set_error("custom target registration: bad arguments");
+        return MMC_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(g_custom_mutex);
+    auto &r = custom_targets();
+    size_t i = 0;
+    for (; i < r.size(); ++i)
+        if (r[i].name == name) break;
+    if (i == r.size()) r.push_back({name, {}});
+    if (r[i].e.dim != 0 && r[i].e.dim != dim) {
+        set_error("custom target '%s' is already registered with dim %d (got %d)", name, r[i].e.dim, dim);
+        return MMC_ERR_INVALID;
+    }
+    r[i].e.dim = dim;
+    if (hmc) r[i].e.hmc = hmc;
+    if (nuts) r[i].e.nuts = nuts;
+    if (mh) r[i].e.mh = mh;
+    return MMC_T_CUSTOM_BASE + (int)i;
+}
+
+bool custom_target_get(int kind, CustomTargetEntry *out, const char **name) {
+    std::lock_guard<std::mutex> lock(g_custom_mutex);
+    auto &r = custom_targets();
+    const size_t idx = (size_t)(kind - MMC_T_CUSTOM_BASE);
+    if (kind < MMC_T_CUSTOM_BASE || idx >= r.size()) return false;
+    if (out) *out = r[idx].e;
+    if (name) *name = r[idx].name.c_str();
+    return true;
+}
+
+int custom_target_lookup(const char *name) {
+    if (!name) return MMC_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_custom_mutex);
+    auto &r = custom_targets();
+    for (size_t i = 0; i < r.size(); ++i)
+        if (r[i].name == name) return MMC_T_CUSTOM_BASE + (int)i;
+    return MMC_ERR_INVALID;
+}
 
 static thread_local char g_err[512] = "";
 

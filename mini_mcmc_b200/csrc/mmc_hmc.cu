@@ -40,17 +40,6 @@ struct mmc_hmc {
 
 namespace {
 
-struct CustomTarget {
-    std::string name;
-    int dim;
-    mmc_hmc_launch_fn fn;
-};
-std::mutex g_registry_mutex;
-std::vector<CustomTarget> &registry() {
-    static std::vector<CustomTarget> r;
-    return r;
-}
-
 int grow(float **ptr, size_t *cap, size_t need) {
     if (*cap >= need) return MMC_OK;
     if (*ptr) MMC_CUDA(cudaFree(*ptr));
@@ -167,11 +156,10 @@ int mmc_hmc_create(mmc_hmc **out, const mmc_target_desc *target, const float *in
                 "mmc_hmc_create: bad arguments");
     MMC_REQUIRE(target->dim == dim, "target dim %d != dim %d", target->dim, dim);
     if (target->kind >= MMC_T_CUSTOM_BASE) {
-        std::lock_guard<std::mutex> lock(g_registry_mutex);
-        const size_t idx = (size_t)(target->kind - MMC_T_CUSTOM_BASE);
-        MMC_REQUIRE(idx < registry().size(), "custom target kind %d is not registered", target->kind);
-        MMC_REQUIRE(registry()[idx].dim == dim, "custom target '%s' has dim %d, got %d", registry()[idx].name.c_str(),
-                    registry()[idx].dim, dim);
+        CustomTargetEntry e;
+        const char *nm = "";
+        MMC_REQUIRE(custom_target_get(target->kind, &e, &nm) && e.hmc, "custom target kind %d is not registered for HMC", target->kind);
+        MMC_REQUIRE(e.dim == dim, "custom target '%s' has dim %d, got %d", nm, e.dim, dim);
     }
     mmc_hmc *h = new mmc_hmc();
     h->target = *target;
@@ -203,26 +191,10 @@ int mmc_hmc_create(mmc_hmc **out, const mmc_target_desc *target, const float *in
 
 int mmc_register_hmc_target(const char *name, int32_t dim, mmc_hmc_launch_fn fn) {
     MMC_REQUIRE(name && fn && dim > 0, "mmc_register_hmc_target: bad arguments");
-    std::lock_guard<std::mutex> lock(g_registry_mutex);
-    auto &r = registry();
-    for (size_t i = 0; i < r.size(); ++i)
-        if (r[i].name == name) {
-            r[i].dim = dim;
-            r[i].fn = fn;
-            return MMC_T_CUSTOM_BASE + (int)i;
-        }
-    r.push_back({name, dim, fn});
-    return MMC_T_CUSTOM_BASE + (int)r.size() - 1;
+    return custom_target_register(name, dim, fn, nullptr, nullptr);
 }
 
-int mmc_lookup_target(const char *name) {
-    if (!name) return MMC_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_registry_mutex);
-    auto &r = registry();
-    for (size_t i = 0; i < r.size(); ++i)
-        if (r[i].name == name) return MMC_T_CUSTOM_BASE + (int)i;
-    return MMC_ERR_INVALID;
-}
+int mmc_lookup_target(const char *name) { return custom_target_lookup(name); }
 
 int mmc_hmc_set_seed(mmc_hmc *h, uint64_t seed) {
     MMC_REQUIRE(h, "null handle");
@@ -305,12 +277,8 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
     p.key = seed_key(h->seed);
     int rc;
     if (h->target.kind >= MMC_T_CUSTOM_BASE) {
-        mmc_hmc_launch_fn fn = nullptr;
-        {
-            std::lock_guard<std::mutex> lock(g_registry_mutex);
-            const size_t idx = (size_t)(h->target.kind - MMC_T_CUSTOM_BASE);
-            if (idx < registry().size()) fn = registry()[idx].fn;
-        }
+        CustomTargetEntry e;
+        mmc_hmc_launch_fn fn = custom_target_get(h->target.kind, &e) ? e.hmc : nullptr;
         MMC_REQUIRE(fn, "custom target kind %d is not registered", h->target.kind);
         rc = fn(&p, replay ? 1 : 0, h->exact, h->target.params, stream);
     } else {

@@ -53,10 +53,12 @@ void widen_to_u64(const void *src, int elem_bytes, uint64_t *dst, size_t n);
 
 namespace {
 
-size_t elem_size(int32_t dtype) { return 8; }
+size_t elem_size(int32_t dtype) { return dtype == MMC_F32 ? 4 : 8; }
 
-// integer-state targets driven by the threshold tables: Poisson and Categorical
-bool is_int_target(const mmc_mh *h) { return h->target.kind == MMC_T_POISSON || h->target.kind == MMC_T_CATEGORICAL; }
+// integer-state targets driven by the threshold tables: Poisson, Categorical and tabulated log-probabilities
+bool is_int_target(const mmc_mh *h) {
+    return h->target.kind == MMC_T_POISSON || h->target.kind == MMC_T_CATEGORICAL || h->target.kind == MMC_T_TABULATED;
+}
 
 int grow(void **ptr, size_t *cap, size_t need) {
     if (*cap >= need) return MMC_OK;
@@ -130,7 +132,15 @@ int upload_int_tables(mmc_mh *h, const std::vector<double> &lp, const std::vecto
         const uint64_t lo = thr & ((1ULL << 38) - 1);
         return make_uint4((uint32_t)(thr >> 38), (uint32_t)lo, (uint32_t)(lo >> 32), 0u);
     };
+    const bool reflect = h->proposal.kind == MMC_Q_REFLECT_RW;
     for (int64_t k = 0; k + 1 < len; ++k) {
+        if (reflect) {
+            // symmetric +-1 walk clamped to the support (tests/metrohast_poisson_test.rs:63-80,193-207): q_f = q_b = ln 1/2.
+            // A clamped move proposes the current state, so leaving its threshold at 0 ("never accept") gives the same chain.
+            lim[2 * k + 1] = encode(accept_threshold((lp[k + 1] + h->ln_half) - (lp[k] + h->ln_half)));
+            if (k >= 1) lim[2 * k] = encode(accept_threshold((lp[k - 1] + h->ln_half) - (lp[k] + h->ln_half)));
+            continue;
+        }
         // x = k -> y = k + 1 : q_f = (k == 0 ? 0 : ln 1/2), q_b = ln 1/2
         const double qf = k == 0 ? 0.0 : h->ln_half, qb = h->ln_half;
         lim[2 * k + 1] = encode(accept_threshold((lp[k + 1] + qb) - (lp[k] + qf)));
@@ -161,6 +171,37 @@ int launch_cont(const MhContParams &p, bool replay, cudaStream_t stream) {
     return MMC_OK;
 }
 
+// IsotropicGaussian target of any dimension (<= kMhDynMax), f64 or f32 state: vectors in local memory, sums in the
+// reference's sequential order
+template <class T>
+int launch_iso_dyn(const mmc_mh *h, const MhContParams &p, bool replay, cudaStream_t stream) {
+    MMC_REQUIRE(h->target.kind == MMC_T_ISO_GAUSSIAN && h->dim <= kMhDynMax, "continuous MH: dim %d unsupported for this target (IsotropicGaussian runs up to %d)",
+                h->dim, kMhDynMax);
+    const T tstd = (T)h->target.params[0], pstd = (T)h->proposal.param;
+    const IsoProposalF<T> q(h->proposal.param);
+    const int block = 128;
+    const unsigned grid = (unsigned)((p.chains + block - 1) / block);
+    if (replay) mh_iso_dyn_kernel<T, true><<<grid, block, 0, stream>>>(p, tstd, pstd, q.ln_term);
+    else mh_iso_dyn_kernel<T, false><<<grid, block, 0, stream>>>(p, tstd, pstd, q.ln_term);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+// MetropolisHastings<f32, f32, ..> (src/metropolis_hastings.rs:87): every operation in f32
+int run_cont_f32(const mmc_mh *h, const MhContParams &p, bool replay, cudaStream_t stream) {
+    const IsoProposalF<float> q(h->proposal.param);
+    if (h->target.kind == MMC_T_GAUSSIAN2D)
+        return launch_mh_functor<Gauss2DTargetF<float>, IsoProposalF<float>, float, 2>(Gauss2DTargetF<float>(h->target.params), q, p, replay, stream);
+    switch (h->dim) {
+    case 1: return launch_mh_functor<IsoTargetF<float, 1>, IsoProposalF<float>, float, 1>(IsoTargetF<float, 1>(h->target.params), q, p, replay, stream);
+    case 2: return launch_mh_functor<IsoTargetF<float, 2>, IsoProposalF<float>, float, 2>(IsoTargetF<float, 2>(h->target.params), q, p, replay, stream);
+    case 3: return launch_mh_functor<IsoTargetF<float, 3>, IsoProposalF<float>, float, 3>(IsoTargetF<float, 3>(h->target.params), q, p, replay, stream);
+    case 4: return launch_mh_functor<IsoTargetF<float, 4>, IsoProposalF<float>, float, 4>(IsoTargetF<float, 4>(h->target.params), q, p, replay, stream);
+    case 8: return launch_mh_functor<IsoTargetF<float, 8>, IsoProposalF<float>, float, 8>(IsoTargetF<float, 8>(h->target.params), q, p, replay, stream);
+    default: return launch_iso_dyn<float>(h, p, replay, stream);
+    }
+}
+
 int run_cont(mmc_mh *h, int64_t n_collect, int64_t n_discard, double *out_dev, const mmc_replay_mh *rp,
              cudaStream_t stream) {
     MhContParams p{};
@@ -184,15 +225,20 @@ int run_cont(mmc_mh *h, int64_t n_collect, int64_t n_discard, double *out_dev, c
     p.prop_norm_term = -(double)h->dim * 0.5 * std::log(var * M_PI * std_ * std_);
     const bool replay = rp && rp->noise && rp->u;
     MMC_REQUIRE(!rp || replay, "MH replay needs both noise and u tapes");
+    p.dim = h->dim;
+    if (h->target.kind >= MMC_T_CUSTOM_BASE) {
+        CustomTargetEntry e;
+        MMC_REQUIRE(custom_target_get(h->target.kind, &e) && e.mh, "custom target kind %d is not registered for MH", h->target.kind);
+        return e.mh(&p, replay ? 1 : 0, h->target.params, h->proposal.param, stream);
+    }
+    if (h->dtype == MMC_F32) return run_cont_f32(h, p, replay, stream);
     switch (h->dim) {
     case 1: return launch_cont<1>(p, replay, stream);
     case 2: return launch_cont<2>(p, replay, stream);
     case 3: return launch_cont<3>(p, replay, stream);
     case 4: return launch_cont<4>(p, replay, stream);
     case 8: return launch_cont<8>(p, replay, stream);
-    default:
-        set_error("continuous MH is compiled for dim in {1,2,3,4,8}, got %d", h->dim);
-        return MMC_ERR_UNSUPPORTED;
+    default: return launch_iso_dyn<double>(h, p, replay, stream);
     }
 }
 
@@ -227,6 +273,7 @@ int run_poisson(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_dev, 
         }
     }
     p.error_flag = h->d_error;
+    p.force_up_at = h->proposal.kind == MMC_Q_REFLECT_RW ? 0xffffffffu : 0u;
     const bool replay = rp && rp->flip && rp->u;
     MMC_REQUIRE(!rp || replay, "Poisson MH replay needs both flip and u tapes");
     const int block = kPoisWarps * 32;
@@ -289,12 +336,19 @@ int mmc_mh_create(mmc_mh **out, const mmc_target_desc *target, const mmc_proposa
     if (poisson) {
         MMC_REQUIRE(proposal->kind == MMC_Q_NONNEG_RW && state_dtype == MMC_U64 && dim == 1,
                     "Poisson target needs the nonnegative random-walk proposal, u64 state and dim 1");
+    } else if (target->kind >= MMC_T_CUSTOM_BASE) {
+        CustomTargetEntry e;
+        const char *nm = "";
+        MMC_REQUIRE(custom_target_get(target->kind, &e, &nm) && e.mh, "custom target kind %d is not registered for MH", target->kind);
+        MMC_REQUIRE(e.dim == dim, "custom target '%s' has dim %d, got %d", nm, e.dim, dim);
+        MMC_REQUIRE(state_dtype == MMC_F64, "custom MH targets run on f64 state");
     } else {
         MMC_REQUIRE(target->kind == MMC_T_GAUSSIAN2D || target->kind == MMC_T_ISO_GAUSSIAN,
                     "MH target kind %d is not a built-in MH target", target->kind);
-        MMC_REQUIRE(proposal->kind == MMC_Q_ISO_GAUSSIAN && state_dtype == MMC_F64,
-                    "continuous MH needs the IsotropicGaussian proposal and f64 state");
+        MMC_REQUIRE(proposal->kind == MMC_Q_ISO_GAUSSIAN && (state_dtype == MMC_F64 || state_dtype == MMC_F32),
+                    "continuous MH needs the IsotropicGaussian proposal and f64 or f32 state");
         MMC_REQUIRE(target->kind != MMC_T_GAUSSIAN2D || dim == 2, "Gaussian2D needs dim 2");
+        MMC_REQUIRE(dim <= kMhDynMax, "continuous MH runs up to dim %d, got %d", kMhDynMax, dim);
         MMC_REQUIRE(proposal->param > 0.0, "proposal std must be > 0");
     }
     mmc_mh *h = new mmc_mh();
@@ -347,6 +401,49 @@ int mmc_mh_create_categorical(mmc_mh **out, const double *probs, int32_t n_categ
     return MMC_OK;
 }
 
+// Any Target<i32 / usize, f64> tabulated on [0, n_states) (-inf beyond) with one of the two +-1 random walks the
+// reference's tests and examples use: NonnegativeProposal (examples/poisson_mh.rs:28-77) or the symmetric walk clamped to
+// the support (PoissonRandomWalk / BinomialRandomWalk, tests/metrohast_poisson_test.rs:52-84,184-214).
+int mmc_mh_create_tabulated(mmc_mh **out, const double *logp, int32_t n_states, int32_t proposal_kind, const void *init_host,
+                            int64_t chains) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    MMC_REQUIRE(out && logp && init_host && chains > 0 && n_states > 0 && n_states <= 4000,
+                "mmc_mh_create_tabulated: bad arguments (1..4000 states)");
+    MMC_REQUIRE(proposal_kind == MMC_Q_NONNEG_RW || proposal_kind == MMC_Q_REFLECT_RW,
+                "mmc_mh_create_tabulated: proposal must be MMC_Q_NONNEG_RW or MMC_Q_REFLECT_RW");
+    const uint64_t *init = static_cast<const uint64_t *>(init_host);
+    for (int64_t c = 0; c < chains; ++c)
+        MMC_REQUIRE(init[c] < (uint64_t)n_states, "chain %lld starts at state %llu >= %d", (long long)c,
+                    (unsigned long long)init[c], n_states);
+    mmc_mh *h = new mmc_mh();
+    h->target.kind = MMC_T_TABULATED;
+    h->target.dim = 1;
+    h->proposal.kind = proposal_kind;
+    h->chains = chains;
+    h->dim = 1;
+    h->dtype = MMC_U64;
+    auto fail = [&](int code) { mmc_mh_destroy(h); return code; };
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    e = cudaMalloc(&h->d_state, (size_t)chains * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_state, init_host, (size_t)chains * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "mmc_mh_create_tabulated", __FILE__, __LINE__));
+    const int64_t len = (int64_t)n_states + 16;   // 16 unreachable states past the support (see build_categorical_tables)
+    h->table_len = (int32_t)len;
+    std::vector<double> lnfact(len, 0.0), lp(len, -INFINITY);
+    for (int32_t k = 0; k < n_states; ++k) lp[k] = logp[k];
+    rc = upload_int_tables(h, lp, lnfact);
+    if (rc) return fail(rc);
+    *out = h;
+    return MMC_OK;
+}
+
+int mmc_register_mh_target(const char *name, int32_t dim, mmc_mh_launch_fn fn) {
+    MMC_REQUIRE(name && fn && dim > 0, "mmc_register_mh_target: bad arguments");
+    return custom_target_register(name, dim, nullptr, nullptr, fn);
+}
+
 int mmc_mh_seed(mmc_mh *h, uint64_t seed) {
     MMC_REQUIRE(h, "null handle");
     h->seed = seed;
@@ -368,7 +465,7 @@ int mmc_mh_set_out_pitch(mmc_mh *h, int64_t pitch_steps) {
 
 int mmc_mh_set_accept_mode(mmc_mh *h, int32_t mode) {
     MMC_REQUIRE(h && (mode == 0 || mode == 1), "accept mode must be 0 or 1");
-    MMC_REQUIRE(mode == 1 || h->target.kind != MMC_T_CATEGORICAL, "the Categorical target only has the threshold accept mode");
+    MMC_REQUIRE(mode == 1 || h->target.kind == MMC_T_POISSON, "only the Poisson target has the device-evaluated accept mode");
     h->accept_mode = mode;
     return MMC_OK;
 }
@@ -485,10 +582,11 @@ int mmc_mh_run_compact(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *ou
 int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, const mmc_replay_mh *replay) {
     MMC_REQUIRE(h && n_collect >= 0 && n_discard >= 0 && (out_host || n_collect == 0), "mmc_mh_run: bad arguments");
     MMC_REQUIRE(h->out_pitch == 0, "mmc_mh_run: an output pitch only applies to mmc_mh_run_dev");
+    MMC_CUDA(cudaDeviceSynchronize());  // earlier *_run_dev work on a caller stream may still be updating the chain state
     if (is_int_target(h) && !replay && h->accept_mode == 1 && n_collect > 0 && !getenv("MMC_NO_COMPACT"))
         return mh_run_poisson_compact(h, n_collect, n_discard, (uint64_t *)out_host);
     const int64_t steps = n_collect + n_discard;
-    const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * 8;
+    const size_t out_bytes = (size_t)h->chains * n_collect * h->dim * elem_size(h->dtype);
     int rc = grow(&h->d_out, &h->d_out_bytes, out_bytes ? out_bytes : 8);
     if (rc) return rc;
     mmc_replay_mh dev_rp{};
@@ -530,7 +628,7 @@ int mmc_mh_run(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, 
 int mmc_mh_d2h_bytes_per_draw(mmc_mh *h) {
     if (!h) return MMC_ERR_INVALID;
     if (is_int_target(h) && h->accept_mode == 1 && !getenv("MMC_NO_COMPACT")) return h->table_len <= 256 ? 1 : 2;
-    return 8 * h->dim;
+    return (int)elem_size(h->dtype) * h->dim;
 }
 
 int mmc_mh_run_progress(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *out_host, int64_t block, mmc_progress_fn cb,
@@ -550,13 +648,15 @@ int mmc_mh_run_progress(mmc_mh *h, int64_t n_collect, int64_t n_discard, void *o
 
 int mmc_mh_get_state(mmc_mh *h, void *state_host) {
     MMC_REQUIRE(h && state_host, "mmc_mh_get_state: bad arguments");
-    MMC_CUDA(cudaMemcpy(state_host, h->d_state, (size_t)h->chains * h->dim * 8, cudaMemcpyDeviceToHost));
+    MMC_CUDA(cudaDeviceSynchronize());  // orders the copy after *_run_dev work on any caller stream
+    MMC_CUDA(cudaMemcpy(state_host, h->d_state, (size_t)h->chains * h->dim * elem_size(h->dtype), cudaMemcpyDeviceToHost));
     return check_error_flag(h, h->stream);
 }
 
 int mmc_mh_set_state(mmc_mh *h, const void *state_host) {
     MMC_REQUIRE(h && state_host, "mmc_mh_set_state: bad arguments");
-    MMC_CUDA(cudaMemcpy(h->d_state, state_host, (size_t)h->chains * h->dim * 8, cudaMemcpyHostToDevice));
+    MMC_CUDA(cudaDeviceSynchronize());
+    MMC_CUDA(cudaMemcpy(h->d_state, state_host, (size_t)h->chains * h->dim * elem_size(h->dtype), cudaMemcpyHostToDevice));
     if (h->d_error) MMC_CUDA(cudaMemset(h->d_error, 0, sizeof(int32_t)));
     return MMC_OK;
 }

@@ -26,6 +26,7 @@ struct MhContParams {
     double tp[6];          // Gaussian2D: mean0, mean1, a, b, c, d ; Iso: std
     double prop_std;
     double prop_norm_term; // -D * 0.5 * ln(var * pi * std * std), evaluated by the host libm
+    int32_t dim;           // state dimension (the any-dimension kernel reads it; the register kernels are templated on it)
 };
 
 // Gaussian2D::unnorm_logp, src/distributions.rs:193-205 (inverse re-derived per call in the reference;
@@ -154,6 +155,218 @@ __global__ void mh_cont_export_tape_kernel(uint2 key, int64_t chains, int64_t ch
     }
 }
 
+// ------------------------------------------------------------------ functor form (any Target / Proposal, f64 or f32 state)
+// MetropolisHastings<S, T, D, Q> is generic over the state / float type and over the Target and Proposal traits
+// (src/metropolis_hastings.rs:87,149-159; src/distributions.rs:92-108).  On the device a target is a functor with
+//     static constexpr int kDim;  __device__ T unnorm_logp(const T (&x)[kDim]) const;
+// and a proposal a functor with
+//     template <int D> __device__ void sample(const T (&cur)[D], const T (&z)[D], T (&out)[D]) const;   // z: D standard normals
+//     template <int D> __device__ T logp(const T (&from)[D], const T (&to)[D]) const;
+// The step is MHMarkovChain::step (:303-315) verbatim; the built-in f64 pairs keep their dedicated kernel above, this one
+// runs f32 state (every operation in f32 like MetropolisHastings<f32, f32, ..>) and the registered custom pairs
+// (include/minimcmc_target.cuh).  Replay tapes are f64 arrays holding T-typed values; traces are written as f64.
+template <class T> struct MhReal;
+template <> struct MhReal<double> {
+    static __device__ __forceinline__ double ln(double u) { return log(u); }
+    static __device__ __forceinline__ double uniform(const uint4 &w) { return u53_half_open(w.x, w.y); }
+    static constexpr int kPerBlock = 2;
+    static __device__ __forceinline__ void normals(const uint4 &w, double (&n)[4]) { box_muller_f64(w, n[0], n[1]); n[2] = n[3] = 0.0; }
+};
+template <> struct MhReal<float> {
+    static __device__ __forceinline__ float ln(float u) { return logf(u); }
+    static __device__ __forceinline__ float uniform(const uint4 &w) { return u24_half_open(w.x); }
+    static constexpr int kPerBlock = 4;
+    static __device__ __forceinline__ void normals(const uint4 &w, float (&n)[4]) {
+        box_muller_f32(w.x, w.y, n[0], n[1]);
+        box_muller_f32(w.z, w.w, n[2], n[3]);
+    }
+};
+
+// Gaussian2D<T>::unnorm_logp, src/distributions.rs:193-205, in T arithmetic
+template <class T>
+struct Gauss2DTargetF {
+    static constexpr int kDim = 2;
+    T m0, m1, i00, i01, i10, i11;
+    __host__ explicit Gauss2DTargetF(const double *tp) {
+        const T a = (T)tp[2], b = (T)tp[3], c = (T)tp[4], d = (T)tp[5];
+        const T det = a * d - b * c;
+        m0 = (T)tp[0]; m1 = (T)tp[1];
+        i00 = d / det; i01 = -b / det; i10 = -c / det; i11 = a / det;
+    }
+    __device__ __forceinline__ T unnorm_logp(const T (&x)[2]) const {
+        const T d0 = x[0] - m0, d1 = x[1] - m1;
+        const T r0 = d0 * i00 + d1 * i10;
+        const T r1 = d0 * i01 + d1 * i11;
+        return (T)-0.5 * (r0 * d0 + r1 * d1);
+    }
+};
+// IsotropicGaussian<T> as Target, src/distributions.rs:394-402
+template <class T, int D>
+struct IsoTargetF {
+    static constexpr int kDim = D;
+    T std;
+    __host__ explicit IsoTargetF(const double *tp) : std((T)tp[0]) {}
+    __device__ __forceinline__ T unnorm_logp(const T (&x)[D]) const {
+        T sum = (T)0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) sum = sum + x[i] * x[i];
+        return (T)-0.5 * sum / (std * std);
+    }
+};
+// IsotropicGaussian<T> as Proposal, src/distributions.rs:364-386 (the ln(var pi std std) normaliser kept verbatim; the
+// logarithm is evaluated by the host libm)
+template <class T>
+struct IsoProposalF {
+    T std, ln_term;
+    __host__ explicit IsoProposalF(double s) : std((T)s) {
+        const T var = std * std;
+        ln_term = sizeof(T) == 8 ? (T)::log((double)(var * (T)M_PI * std * std)) : (T)::logf((float)(var * (T)M_PI * std * std));
+    }
+    template <int D>
+    __device__ __forceinline__ void sample(const T (&cur)[D], const T (&z)[D], T (&out)[D]) const {
+#pragma unroll
+        for (int i = 0; i < D; ++i) out[i] = ((T)0 + std * z[i]) + cur[i];
+    }
+    template <int D>
+    __device__ __forceinline__ T logp(const T (&from)[D], const T (&to)[D]) const {
+        T lp = (T)0;
+        const T var = std * std;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const T diff = to[i] - from[i];
+            lp += -(diff * diff) / ((T)2 * var);
+        }
+        lp += -(T)D * (T)0.5 * ln_term;
+        return lp;
+    }
+};
+
+template <class TGT, class PROP, class T, int D, bool kReplay>
+__global__ void __launch_bounds__(128) mh_functor_kernel(const TGT tgt, const PROP prop, const MhContParams p) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.chains) return;
+    T *state = reinterpret_cast<T *>(p.state), *out = reinterpret_cast<T *>(p.out);
+    T x[D], y[D], z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = state[c * D + i];
+    const int64_t steps = p.n_collect + p.n_discard;
+    const uint64_t gchain = (uint64_t)(c + p.chain_offset);
+    for (int64_t s = 0; s < steps; ++s) {
+        T u;
+        if (kReplay) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) z[i] = (T)p.noise[(c * steps + s) * D + i];
+            u = (T)p.u[c * steps + s];
+        } else {
+            const uint32_t gstep = (uint32_t)(p.step_base + s);
+            u = MhReal<T>::uniform(philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), gstep, 0u)));
+            constexpr int K = MhReal<T>::kPerBlock;
+#pragma unroll
+            for (int j = 0; j < (D + K - 1) / K; ++j) {
+                T n[4];
+                MhReal<T>::normals(philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), gstep, (uint32_t)(1 + j))), n);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (K * j + k < D) z[K * j + k] = n[k];
+            }
+        }
+        prop.sample(x, z, y);
+        const T cur_lp = tgt.unnorm_logp(x);
+        const T prop_lp = tgt.unnorm_logp(y);
+        const T qf = prop.logp(x, y);
+        const T qb = prop.logp(y, x);
+        const T r = (prop_lp + qb) - (cur_lp + qf);
+        const bool acc = r > MhReal<T>::ln(u);
+        if (acc) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] = y[i];
+        }
+        if (p.trace) {
+            double *t = p.trace + (c * steps + s) * 4;
+            t[0] = (double)cur_lp; t[1] = (double)prop_lp; t[2] = (double)r; t[3] = acc ? 1.0 : 0.0;
+        }
+        if (s >= p.n_discard && out) {
+            T *o = out + (c * p.out_pitch + (s - p.n_discard)) * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) o[i] = x[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) state[c * D + i] = x[i];
+}
+
+template <class TGT, class PROP, class T, int D>
+int launch_mh_functor(const TGT &tgt, const PROP &prop, const MhContParams &p, bool replay, cudaStream_t stream) {
+    const int block = 128;
+    const unsigned grid = (unsigned)((p.chains + block - 1) / block);
+    if (replay) mh_functor_kernel<TGT, PROP, T, D, true><<<grid, block, 0, stream>>>(tgt, prop, p);
+    else mh_functor_kernel<TGT, PROP, T, D, false><<<grid, block, 0, stream>>>(tgt, prop, p);
+    MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+// IsotropicGaussian target + proposal for ANY dimension (<= kMhDynMax): the vectors live in local memory and the loops
+// run to p.dim in the reference's (sequential) order, so the sums round exactly like the CPU code.
+constexpr int kMhDynMax = 256;
+template <class T, bool kReplay>
+__global__ void __launch_bounds__(128) mh_iso_dyn_kernel(const MhContParams p, const T tstd, const T pstd, const T ln_term) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.chains) return;
+    const int D = p.dim;
+    T *state = reinterpret_cast<T *>(p.state), *out = reinterpret_cast<T *>(p.out);
+    T x[kMhDynMax], y[kMhDynMax];
+    for (int i = 0; i < D; ++i) x[i] = state[c * D + i];
+    const int64_t steps = p.n_collect + p.n_discard;
+    const uint64_t gchain = (uint64_t)(c + p.chain_offset);
+    auto tlogp = [&](const T *v) {
+        T sum = (T)0;
+        for (int i = 0; i < D; ++i) sum = sum + v[i] * v[i];
+        return (T)-0.5 * sum / (tstd * tstd);
+    };
+    auto qlogp = [&](const T *from, const T *to) {
+        T lp = (T)0;
+        const T var = pstd * pstd;
+        for (int i = 0; i < D; ++i) {
+            const T diff = to[i] - from[i];
+            lp += -(diff * diff) / ((T)2 * var);
+        }
+        lp += -(T)D * (T)0.5 * ln_term;
+        return lp;
+    };
+    for (int64_t s = 0; s < steps; ++s) {
+        T u;
+        if (kReplay) {
+            for (int i = 0; i < D; ++i) y[i] = ((T)0 + pstd * (T)p.noise[(c * steps + s) * D + i]) + x[i];
+            u = (T)p.u[c * steps + s];
+        } else {
+            const uint32_t gstep = (uint32_t)(p.step_base + s);
+            u = MhReal<T>::uniform(philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), gstep, 0u)));
+            constexpr int K = MhReal<T>::kPerBlock;
+            for (int j = 0; j < (D + K - 1) / K; ++j) {
+                T n[4];
+                MhReal<T>::normals(philox4x32_10(p.key, make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), gstep, (uint32_t)(1 + j))), n);
+                for (int k = 0; k < K; ++k)
+                    if (K * j + k < D) y[K * j + k] = ((T)0 + pstd * n[k]) + x[K * j + k];
+            }
+        }
+        const T cur_lp = tlogp(x), prop_lp = tlogp(y);
+        const T qf = qlogp(x, y), qb = qlogp(y, x);
+        const T r = (prop_lp + qb) - (cur_lp + qf);
+        const bool acc = r > MhReal<T>::ln(u);
+        if (acc)
+            for (int i = 0; i < D; ++i) x[i] = y[i];
+        if (p.trace) {
+            double *t = p.trace + (c * steps + s) * 4;
+            t[0] = (double)cur_lp; t[1] = (double)prop_lp; t[2] = (double)r; t[3] = acc ? 1.0 : 0.0;
+        }
+        if (s >= p.n_discard && out) {
+            T *o = out + (c * p.out_pitch + (s - p.n_discard)) * D;
+            for (int i = 0; i < D; ++i) o[i] = x[i];
+        }
+    }
+    for (int i = 0; i < D; ++i) state[c * D + i] = x[i];
+}
+
 // ------------------------------------------------------------------ Poisson / integer state (config C2)
 // PoissonTarget + NonnegativeProposal, examples/poisson_mh.rs:10-89.
 //
@@ -184,6 +397,7 @@ struct MhPoissonParams {
     int64_t out_pitch;     // draws per chain row of `out` (>= n_collect; the caller may fill a window of a longer tensor)
     uint32_t rk[20];        // Philox round keys (key + r * Weyl), host-expanded: they depend on the seed only
     int32_t *error_flag;    // set to 1 when a chain reaches the end of the table
+    uint32_t force_up_at;   // 0: NonnegativeProposal (a chain at 0 always proposes 1); 0xffffffff: reflecting +-1 walk
 };
 
 constexpr int kPoisWarps = 8;
@@ -257,7 +471,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     // One transition from the 16-bit field h; `low38()` yields the lazily evaluated low bits of u53.
     auto transition = [&](uint32_t h, auto low38) {
         // NonnegativeProposal::sample, examples/poisson_mh.rs:34-47: 0 -> 1, else +-1 by the flip
-        const uint32_t up = (h >> 15) | (uint32_t)(x == 0);
+        const uint32_t up = (h >> 15) | (uint32_t)(x == p.force_up_at);
         const uint32_t y = min(x + 2u * up - 1u, kmax);
         const uint32_t u15 = h & 0x7fffu;
         bool acc;
@@ -286,7 +500,7 @@ __global__ void __launch_bounds__(kPoisWarps * 32, 6) mh_poisson_kernel(const __
     // Branch-free fast transition (threshold mode): decides on the top 15 bits and records whether a tie
     // occurred; the caller replays the whole octet through `transition` in that case.
     auto fast = [&](uint32_t h, bool &tie) {
-        const uint32_t up = (h >> 15) | (uint32_t)(x == 0);
+        const uint32_t up = (h >> 15) | (uint32_t)(x == p.force_up_at);
         const uint32_t y = min(x + 2u * up - 1u, kmax);
         const uint32_t u15 = h & 0x7fffu;
         const uint32_t hi = s_hi[2u * x + up];

@@ -57,6 +57,20 @@ int grow(T **ptr, size_t *cap, size_t need) {
     return MMC_OK;
 }
 
+// one launch (or grid / scratch query) of the tree kernel the handle's settings select: a built-in target on the group
+// or warp layout, or the launcher a custom target registered (mmc_register_nuts_target; warp layout)
+int nuts_launch(const NutsLaunch &L, int exact, bool group, const NutsParams &p, int64_t *grid, size_t *scratch, bool query,
+                cudaStream_t s) {
+    if (L.target.kind >= MMC_T_CUSTOM_BASE) {
+        CustomTargetEntry e;
+        MMC_REQUIRE(custom_target_get(L.target.kind, &e) && e.nuts, "custom target kind %d is not registered for NUTS", L.target.kind);
+        return e.nuts(&p, L.scalar_f64 ? 1 : 0, L.replay ? 1 : 0, exact, L.target.params, L.sm_count, grid, scratch, query ? 1 : 0, s);
+    }
+    auto dispatch = group ? (exact ? nuts_group_dispatch_exact : nuts_group_dispatch_fast)
+                          : (exact ? nuts_dispatch_exact : nuts_dispatch_fast);
+    return dispatch(L, p, grid, scratch, query, s);
+}
+
 // ---- regrouping of the group kernel's warps (lock-step efficiency)
 // The chains of a warp advance in lock step, so a warp is as slow as its deepest tree; tree depth is governed by the
 // chain's adapted step size (oracle study in DESIGN.md: corr(log eps, leapfrogs per chain) = -0.92; lock-step efficiency
@@ -142,6 +156,12 @@ int mmc_nuts_create(mmc_nuts **out, const mmc_target_desc *target, const float *
     MMC_REQUIRE(out && target && init_host && chains > 0 && dim > 0, "mmc_nuts_create: bad arguments");
     MMC_REQUIRE(target->dim == dim, "target dim %d != dim %d", target->dim, dim);
     MMC_REQUIRE(scalar_dtype == MMC_F32 || scalar_dtype == MMC_F64, "scalar dtype must be MMC_F32 or MMC_F64");
+    if (target->kind >= MMC_T_CUSTOM_BASE) {
+        CustomTargetEntry e;
+        const char *nm = "";
+        MMC_REQUIRE(custom_target_get(target->kind, &e, &nm) && e.nuts, "custom target kind %d is not registered for NUTS", target->kind);
+        MMC_REQUIRE(e.dim == dim, "custom target '%s' has dim %d, got %d", nm, e.dim, dim);
+    }
     if (max_depth <= 0) max_depth = 10;
     MMC_REQUIRE(max_depth <= 16, "max_depth %d > 16", max_depth);
     mmc_nuts *h = new mmc_nuts();
@@ -172,6 +192,11 @@ int mmc_nuts_create(mmc_nuts **out, const mmc_target_desc *target, const float *
     if ((e = cudaMemset(h->d_counters, 0, kCounters * 8)) != cudaSuccess) return fail(e, "memset");
     *out = h;
     return MMC_OK;
+}
+
+int mmc_register_nuts_target(const char *name, int32_t dim, mmc_nuts_launch_fn fn) {
+    MMC_REQUIRE(name && fn && dim > 0 && dim <= 128, "mmc_register_nuts_target: bad arguments (dim <= 128)");
+    return custom_target_register(name, dim, nullptr, fn, nullptr);
 }
 
 int mmc_nuts_set_seed(mmc_nuts *h, uint64_t seed) {
@@ -273,8 +298,10 @@ int mmc_nuts_run_dev(mmc_nuts *h, int64_t n_collect, int64_t n_discard, int32_t 
     const int group_lanes = nuts_group_lanes(h->target);
     const bool group = h->layout == kNutsLayoutAuto ? group_lanes != 0 : h->layout != kNutsLayoutWarp;
     h->lanes_used = group ? group_lanes : 32;
-    auto dispatch = group ? (h->exact ? nuts_group_dispatch_exact : nuts_group_dispatch_fast)
-                          : (h->exact ? nuts_dispatch_exact : nuts_dispatch_fast);
+    const int exact = h->exact;
+    auto dispatch = [&](const NutsLaunch &LL, const NutsParams &pp, int64_t *g, size_t *sc, bool query, cudaStream_t st) {
+        return nuts_launch(LL, exact, group, pp, g, sc, query, st);
+    };
     int64_t grid = 0;
     size_t scratch_floats = 0;
     int rc = dispatch(L, p, &grid, &scratch_floats, true, s);
@@ -450,8 +477,10 @@ int mmc_nuts_build_tree(mmc_nuts *h, const float *mom_host, const float *grad_ho
     const int group_lanes = nuts_group_lanes(h->target);
     const bool group = h->layout == kNutsLayoutAuto ? group_lanes != 0 : h->layout != kNutsLayoutWarp;
     h->lanes_used = group ? group_lanes : 32;
-    auto dispatch = group ? (h->exact ? nuts_group_dispatch_exact : nuts_group_dispatch_fast)
-                          : (h->exact ? nuts_dispatch_exact : nuts_dispatch_fast);
+    const int exact = h->exact;
+    auto dispatch = [&](const NutsLaunch &LL, const NutsParams &pp, int64_t *g, size_t *sc, bool query, cudaStream_t st) {
+        return nuts_launch(LL, exact, group, pp, g, sc, query, st);
+    };
     int64_t grid = 0;
     size_t scratch_floats = 0;
     if ((rc = dispatch(L, p, &grid, &scratch_floats, true, s))) return done(rc);

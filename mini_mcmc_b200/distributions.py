@@ -107,6 +107,74 @@ class Categorical:
     def unnorm_logp(self, position) -> float:
         return self.logp(int(position[0]))
 
+    def set_seed(self, seed: int):
+        """Categorical::set_seed; the host-side sampler below draws from numpy's PCG64 keyed by `seed`."""
+        self._rng = np.random.default_rng(int(seed))
+        return self
+
+    def sample(self) -> int:
+        """Discrete::sample, src/distributions.rs:447-459: the first index whose running sum reaches r (`r <= cum`), the
+        last index when rounding leaves the total below r."""
+        if getattr(self, "_rng", None) is None:
+            self._rng = np.random.default_rng()
+        r = self._rng.random()
+        cum = 0.0
+        for i, p in enumerate(self.probs):
+            cum += float(p)
+            if r <= cum:
+                return i
+        return self.probs.size - 1
+
+
+class TabulatedTarget:
+    """Any integer-state target (`Target<i32, f64>` / `Target<usize, f64>`) given as its log-probabilities on
+    [0, len(logp)), -inf beyond: how user-defined discrete targets such as the PoissonDist / BinomialDist of
+    tests/metrohast_poisson_test.rs:18-46,157-173 reach the device (mmc_mh_create_tabulated)."""
+    dim = 1
+
+    def __init__(self, logp):
+        self.table = np.ascontiguousarray(logp, dtype=np.float64)
+        if self.table.ndim != 1 or self.table.size == 0:
+            raise ValueError("logp must be a non-empty vector")
+
+    @staticmethod
+    def ln_factorial(k: int) -> float:
+        """ln_factorial of the reference's tests / example: 0 for k < 2, else sum_{i=1..k} ln(i) in that order."""
+        if k < 2:
+            return 0.0
+        acc = 0.0
+        for i in range(1, k + 1):
+            acc += float(np.log(float(i)))
+        return acc
+
+    @classmethod
+    def poisson(cls, lam: float, n_states: int = 256):
+        """PoissonDist { lambda }, tests/metrohast_poisson_test.rs:18-36: k ln(lambda) - lambda - ln k! (that order)."""
+        ln_lam = float(np.log(lam))
+        return cls([float(k) * ln_lam - lam - cls.ln_factorial(k) for k in range(n_states)])
+
+    @classmethod
+    def binomial(cls, n: int, p: float):
+        """BinomialDist { n, p }, tests/metrohast_poisson_test.rs:157-178."""
+        lf = cls.ln_factorial
+        ln_p, ln_q = float(np.log(p)), float(np.log(1.0 - p))
+        return cls([(lf(n) - lf(k) - lf(n - k)) + float(k) * ln_p + (float(n) - float(k)) * ln_q for k in range(n + 1)])
+
+    def unnorm_logp(self, position) -> float:
+        k = int(position[0])
+        return float(self.table[k]) if 0 <= k < self.table.size else float("-inf")
+
+
+class ReflectingRandomWalk:
+    """The symmetric +-1 walk of tests/metrohast_poisson_test.rs:52-84,184-214 (PoissonRandomWalk / BinomialRandomWalk):
+    moves that would leave the support are clamped back, logp is ln(0.5) both ways."""
+
+    def set_seed(self, seed):
+        return self
+
+    def proposal_desc(self) -> L.ProposalDesc:
+        return L.ProposalDesc(L.Q_REFLECT_RW, 0.0)
+
 
 class NonnegativeProposal:
     """NonnegativeProposal, examples/poisson_mh.rs:28-77."""
@@ -194,22 +262,43 @@ class DenseGaussian(_Target):
 
 
 class CustomTarget(_Target):
-    """A user-compiled device target registered through include/minimcmc_target.cuh (HMC only).
+    """A user-compiled device target registered through include/minimcmc_target.cuh.
 
     `library` is the path of the shared object built from the user's .cu file, `name` the identifier given to
-    MMC_REGISTER_HMC_TARGET; `params` fill mmc_target_desc.params (up to 8 doubles)."""
+    MMC_REGISTER_HMC_TARGET / MMC_REGISTER_NUTS_TARGET / MMC_REGISTER_MH_TARGET / MMC_REGISTER_MH_PAIR; `samplers` names
+    the registrations to run ("hmc", "nuts", "mh" - one name keeps one kind id across them); `params` fill
+    mmc_target_desc.params (up to 8 doubles)."""
+    _ENTRY = {"hmc": "_register", "nuts": "_register_nuts", "mh": "_register_mh"}
 
-    def __init__(self, library: str, name: str, dim: int, params=()):
+    def __init__(self, library: str, name: str, dim: int, params=(), samplers=("hmc",)):
         import ctypes
 
         self._user_lib = ctypes.CDLL(library, mode=ctypes.RTLD_GLOBAL)
-        kind = getattr(self._user_lib, f"{name}_register")()
-        if kind < 1000:
-            raise RuntimeError(f"registering custom target {name!r} failed with code {kind}")
+        kind = None
+        for smp in samplers:
+            k = getattr(self._user_lib, name + self._ENTRY[smp])()
+            if k < 1000:
+                raise RuntimeError(f"registering custom target {name!r} for {smp} failed with code {k}")
+            if kind is not None and k != kind:
+                raise RuntimeError(f"custom target {name!r} got two kind ids ({kind}, {k})")
+            kind = k
         self.kind, self.dim, self._p = int(kind), int(dim), tuple(float(v) for v in params)
 
     def _params(self):
         return self._p
+
+
+class CustomProposal:
+    """The proposal half of MMC_REGISTER_MH_PAIR: `param` is handed to the device functor's constructor."""
+
+    def __init__(self, param: float = 0.0):
+        self.param = float(param)
+
+    def set_seed(self, seed):
+        return self
+
+    def proposal_desc(self) -> L.ProposalDesc:
+        return L.ProposalDesc(L.Q_CUSTOM, self.param)
 
 
 class ConstantConditional:

@@ -7,18 +7,27 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .distributions import Categorical, NonnegativeProposal, PoissonTarget
+from .distributions import Categorical, NonnegativeProposal, PoissonTarget, ReflectingRandomWalk, TabulatedTarget
 
 
 class MetropolisHastings:
     """MetropolisHastings::new(target, proposal, initial_states) — one chain per initial state
     (src/metropolis_hastings.rs:149-159).  `.seed(s)` (…:187-193) keys the device Philox streams."""
 
-    def __init__(self, target, proposal, initial_states):
+    def __init__(self, target, proposal, initial_states, dtype=None):
+        """`dtype=np.float32` runs MetropolisHastings<f32, f32, ..> (the struct is generic over the float type,
+        src/metropolis_hastings.rs:87): f32 state and arithmetic; initial states that already are f32 select it too."""
         self.target, self.proposal = target, proposal
         categorical = isinstance(target, Categorical)
-        poisson = isinstance(target, PoissonTarget) or categorical
-        self._np_dtype = np.uint64 if poisson else np.float64
+        tabulated = isinstance(target, TabulatedTarget)
+        if isinstance(target, PoissonTarget) and isinstance(proposal, ReflectingRandomWalk):
+            target, tabulated = TabulatedTarget.poisson(target.lam), True
+        poisson = isinstance(target, PoissonTarget) or categorical or tabulated
+        if dtype is None:
+            dtype = np.float32 if (not poisson and getattr(initial_states, "dtype", None) == np.float32) else np.float64
+        self._np_dtype = np.uint64 if poisson else np.dtype(dtype).type
+        if self._np_dtype not in (np.uint64, np.float64, np.float32):
+            raise ValueError("state dtype must be float64 or float32")
         init = np.ascontiguousarray(initial_states, dtype=self._np_dtype)
         if init.ndim != 2:
             raise ValueError("initial_states must be [chains, dim]")
@@ -33,12 +42,23 @@ class MetropolisHastings:
             L.check(L.lib.mmc_mh_create_categorical(C.byref(self._h), L.vp(probs), C.c_int32(probs.shape[0]), L.vp(init),
                                                     C.c_int64(self.n_chains)))
             return
+        if tabulated:
+            if not isinstance(proposal, (NonnegativeProposal, ReflectingRandomWalk)) or self.dim != 1:
+                raise ValueError("a tabulated target runs with NonnegativeProposal or ReflectingRandomWalk and a 1-d integer state")
+            L.check(L.lib.mmc_mh_create_tabulated(C.byref(self._h), L.vp(target.table), C.c_int32(target.table.shape[0]),
+                                                  C.c_int32(proposal.proposal_desc().kind), L.vp(init), C.c_int64(self.n_chains)))
+            return
         tdesc, qdesc = target.desc(), proposal.proposal_desc()
+        sdt = L.MMC_U64 if poisson else (L.MMC_F32 if self._np_dtype == np.float32 else L.MMC_F64)
         L.check(L.lib.mmc_mh_create(C.byref(self._h), C.byref(tdesc), C.byref(qdesc), L.vp(init),
-                                    C.c_int64(self.n_chains), C.c_int32(self.dim),
-                                    C.c_int32(L.MMC_U64 if poisson else L.MMC_F64)))
+                                    C.c_int64(self.n_chains), C.c_int32(self.dim), C.c_int32(sdt)))
 
     new = classmethod(lambda cls, target, proposal, initial_states: cls(target, proposal, initial_states))
+
+    def _torch_dtype(self):
+        import torch
+
+        return {np.uint64: torch.int64, np.float64: torch.float64, np.float32: torch.float32}[self._np_dtype]
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -76,7 +96,7 @@ class MetropolisHastings:
         """Same as run() but the sample stays in HBM: returns a torch tensor on the current CUDA device."""
         import torch
 
-        tdt = torch.int64 if self._np_dtype == np.uint64 else torch.float64
+        tdt = self._torch_dtype()
         if out is None:
             out = torch.empty((self.n_chains, n_collect, self.dim), dtype=tdt, device="cuda")
         rp = None
@@ -102,8 +122,8 @@ class MetropolisHastings:
 
         total = n_collect + n_discard
         report = resolve_reporter(progress, "MH", total)
-        esize = 8
-        tdt = torch.int64 if self._np_dtype == np.uint64 else torch.float64
+        esize = np.dtype(self._np_dtype).itemsize
+        tdt = self._torch_dtype()
         tracker = ChainTrackers(self.dim, self.current_state())
         sample = torch.empty((self.n_chains, n_collect, self.dim), dtype=tdt, device="cuda")
 

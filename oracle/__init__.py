@@ -222,6 +222,25 @@ def mh_cont_run_replay(kind, tparams, prop_std, state, n_collect, n_discard, noi
     return out, state, trace
 
 
+def mh_cont_run_replay_f32(kind, tparams, prop_std, state, n_collect, n_discard, noise, u, want_trace=False):
+    """MetropolisHastings<f32, f32, ..>: state [chains, D] f32; tapes hold f32 values.  Returns (out, state, trace)."""
+    state = _f32(state).copy()
+    chains, D = state.shape
+    steps = n_collect + n_discard
+    noise, u = _f64(noise), _f64(u)
+    assert noise.shape == (chains, steps, D) and u.shape == (chains, steps)
+    tp = np.zeros(6, dtype=np.float64)
+    tp[: len(tparams)] = tparams
+    out = np.empty((chains, n_collect, D), dtype=np.float32)
+    trace = np.empty((chains, steps, 4), dtype=np.float32) if want_trace else None
+    rc = lib().orc_mh_cont_run_replay_f32(kind, _p(tp, C.c_double), C.c_double(prop_std), _p(state, C.c_float),
+                                          C.c_int64(chains), D, C.c_int64(n_collect), C.c_int64(n_discard),
+                                          _p(noise, C.c_double), _p(u, C.c_double), _p(out, C.c_float),
+                                          _p(trace, C.c_float))
+    assert rc == 0
+    return out, state, trace
+
+
 def mh_cont_reference_tape(chain_seed, prop_seed, chains, steps, D):
     noise = np.empty((chains, steps, D), dtype=np.float64)
     u = np.empty((chains, steps), dtype=np.float64)
@@ -627,4 +646,30 @@ def mh_categorical_run_philox(probs, state, n_collect, n_discard, seed, chain_of
     lib().orc_mh_categorical_run_philox(_p(probs, C.c_double), C.c_int64(probs.shape[0]), _p(state, C.c_uint64), C.c_int64(chains),
                                         C.c_int64(chain_offset), C.c_int64(step_base), C.c_int64(n_collect), C.c_int64(n_discard),
                                         C.c_uint64(seed), _p(out, C.c_uint64))
+    return out, state
+
+
+def mh_tabulated_run_replay(logp, state, n_collect, n_discard, flip, u, reflect=True, upper=-1):
+    """MH over a Target<i32, f64> tabulated as logp[0..K) with the reflecting (tests/metrohast_poisson_test.rs) or the
+    nonnegative (examples/poisson_mh.rs) +-1 walk; literal `r > ln(u)` accept test."""
+    logp = _f64(logp)
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy().reshape(-1)
+    chains = state.shape[0]
+    flip = np.ascontiguousarray(flip, dtype=np.uint8)
+    u = _f64(u)
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_tabulated_run_replay(_p(logp, C.c_double), C.c_int64(logp.shape[0]), int(bool(reflect)), C.c_int64(upper),
+                                      _p(state, C.c_uint64), C.c_int64(chains), C.c_int64(n_collect), C.c_int64(n_discard),
+                                      _p(flip, C.c_uint8), _p(u, C.c_double), _p(out, C.c_uint64))
+    return out, state
+
+
+def mh_tabulated_run_philox(logp, state, n_collect, n_discard, seed, reflect=True, upper=-1, chain_offset=0, step_base=0):
+    logp = _f64(logp)
+    state = np.ascontiguousarray(state, dtype=np.uint64).copy().reshape(-1)
+    chains = state.shape[0]
+    out = np.empty((chains, n_collect, 1), dtype=np.uint64)
+    lib().orc_mh_tabulated_run_philox(_p(logp, C.c_double), C.c_int64(logp.shape[0]), int(bool(reflect)), C.c_int64(upper),
+                                      _p(state, C.c_uint64), C.c_int64(chains), C.c_int64(chain_offset), C.c_int64(step_base),
+                                      C.c_int64(n_collect), C.c_int64(n_discard), C.c_uint64(seed), _p(out, C.c_uint64))
     return out, state

@@ -127,7 +127,7 @@ ORC_API float orc_target_logp_grad(int kind, int dim, const double *params, int 
  * Normal::sample (mean + std*z) followed by `x + *eps` (src/distributions.rs:364-372). */
 static inline int orc_mh_cont_step(int kind, const double *tp, double prop_std, double *x, int D, const double *noise,
                                    double u, double *lp_out) {
-    double prop[64];
+    double prop[256];
     for (int i = 0; i < D; ++i) prop[i] = (0.0 + prop_std * noise[i]) + x[i];
     double cur_lp, prop_lp;
     if (kind == ORC_T_GAUSSIAN2D) {
@@ -152,7 +152,7 @@ static inline int orc_mh_cont_step(int kind, const double *tp, double prop_std, 
 ORC_API int orc_mh_cont_run_replay(int kind, const double *tp, double prop_std, double *state, int64_t chains, int D,
                                    int64_t n_collect, int64_t n_discard, const double *noise, const double *u,
                                    double *out, double *trace) {
-    if (D > 64) return -1;
+    if (D > 256) return -1;
     const int64_t steps = n_collect + n_discard;
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < chains; ++c) {
@@ -165,6 +165,75 @@ ORC_API int orc_mh_cont_run_replay(int kind, const double *tp, double prop_std, 
                 tr[0] = lp[0]; tr[1] = lp[1]; tr[2] = lp[2]; tr[3] = (double)acc;
             }
             if (i >= n_discard) memcpy(out + (c * n_collect + (i - n_discard)) * D, x, sizeof(double) * D);
+        }
+    }
+    return 0;
+}
+
+/* MetropolisHastings<f32, f32, ..> (the struct is generic over the state / float type, src/metropolis_hastings.rs:87):
+ * the same step with every operation in f32 - Gaussian2D<f32> / IsotropicGaussian<f32> arithmetic
+ * (src/distributions.rs:193-205,364-402), `u: f32 = rng.random()` and `u.ln()` in f32 (:309-311).  Tapes are f64 arrays
+ * holding f32 values. */
+static inline float orc_gaussian2d_unnorm_logp_f32(const float *p, const float *x) {
+    float a = p[2], b = p[3], c = p[4], d = p[5];
+    float det = a * d - b * c;
+    float i00 = d / det, i01 = -b / det, i10 = -c / det, i11 = a / det;
+    float d0 = x[0] - p[0], d1 = x[1] - p[1];
+    float r0 = d0 * i00 + d1 * i10;
+    float r1 = d0 * i01 + d1 * i11;
+    return -0.5f * (r0 * d0 + r1 * d1);
+}
+static inline float orc_iso_unnorm_logp_f32(float std, const float *x, int D) {
+    float sum = 0.0f;
+    for (int i = 0; i < D; ++i) sum = sum + x[i] * x[i];
+    return -0.5f * sum / (std * std);
+}
+static inline float orc_iso_proposal_logp_f32(float std, const float *from, const float *to, int D) {
+    float lp = 0.0f;
+    float d = (float)D;
+    float two = 2.0f;
+    float var = std * std;
+    for (int i = 0; i < D; ++i) {
+        float diff = to[i] - from[i];
+        float exponent = -(diff * diff) / (two * var);
+        lp += exponent;
+    }
+    lp += -d * 0.5f * logf(var * (float)M_PI * std * std);
+    return lp;
+}
+ORC_API int orc_mh_cont_run_replay_f32(int kind, const double *tp, double prop_std, float *state, int64_t chains, int D,
+                                       int64_t n_collect, int64_t n_discard, const double *noise, const double *u,
+                                       float *out, float *trace) {
+    if (D > 256) return -1;
+    const int64_t steps = n_collect + n_discard;
+    float tpf[6];
+    for (int i = 0; i < 6; ++i) tpf[i] = (float)tp[i];
+    const float std = (float)prop_std;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        float *x = state + c * D;
+        float prop[256];
+        for (int64_t i = 0; i < steps; ++i) {
+            const double *z = noise + (c * steps + i) * D;
+            for (int k = 0; k < D; ++k) prop[k] = (0.0f + std * (float)z[k]) + x[k];
+            float cur_lp, prop_lp;
+            if (kind == ORC_T_GAUSSIAN2D) {
+                cur_lp = orc_gaussian2d_unnorm_logp_f32(tpf, x);
+                prop_lp = orc_gaussian2d_unnorm_logp_f32(tpf, prop);
+            } else {
+                cur_lp = orc_iso_unnorm_logp_f32(tpf[0], x, D);
+                prop_lp = orc_iso_unnorm_logp_f32(tpf[0], prop, D);
+            }
+            float qf = orc_iso_proposal_logp_f32(std, x, prop, D);
+            float qb = orc_iso_proposal_logp_f32(std, prop, x, D);
+            float r = (prop_lp + qb) - (cur_lp + qf);
+            int acc = r > logf((float)u[c * steps + i]);
+            if (acc) memcpy(x, prop, sizeof(float) * D);
+            if (trace) {
+                float *tr = trace + (c * steps + i) * 4;
+                tr[0] = cur_lp; tr[1] = prop_lp; tr[2] = r; tr[3] = (float)acc;
+            }
+            if (i >= n_discard) memcpy(out + (c * n_collect + (i - n_discard)) * D, x, sizeof(float) * D);
         }
     }
     return 0;
@@ -902,6 +971,73 @@ ORC_API int orc_mh_categorical_run_philox(const double *probs, int64_t K, uint64
             if (s >= n_discard) out[c * n_collect + (s - n_discard)] = x;
         }
         state[c] = x;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ MH over a tabulated integer target
+ * Any Target<i32, f64> given as logp[0..K) (-inf outside), with either NonnegativeProposal (examples/poisson_mh.rs:28-77)
+ * or the symmetric +-1 walk clamped to [0, upper] whose logp is ln(0.5) both ways (PoissonRandomWalk: `new_state < 0 ->
+ * 0`, BinomialRandomWalk: `.max(0).min(n)`, tests/metrohast_poisson_test.rs:63-80,193-207).  Transition =
+ * MHMarkovChain::step (src/metropolis_hastings.rs:303-315).  upper < 0: no upper clamp. */
+static inline double orc_tab_logp(const double *lp, int64_t K, int64_t k) { return (k >= 0 && k < K) ? lp[k] : -INFINITY; }
+static inline int64_t orc_mh_tab_step(const double *lp, int64_t K, int reflect, int64_t upper, int64_t x, int flip, double u) {
+    int64_t y;
+    double qf, qb;
+    if (reflect) {
+        y = x + (flip ? 1 : -1);
+        if (y < 0) y = 0;
+        if (upper >= 0 && y > upper) y = upper;
+        qf = qb = log(0.5);
+    } else {
+        y = (x == 0) ? 1 : (flip ? x + 1 : x - 1);
+        qf = orc_nonneg_logq((uint64_t)x, (uint64_t)y);
+        qb = orc_nonneg_logq((uint64_t)y, (uint64_t)x);
+    }
+    double r = (orc_tab_logp(lp, K, y) + qb) - (orc_tab_logp(lp, K, x) + qf);
+    return (r > log(u)) ? y : x;
+}
+ORC_API int orc_mh_tabulated_run_replay(const double *lp, int64_t K, int reflect, int64_t upper, uint64_t *state, int64_t chains,
+                                        int64_t n_collect, int64_t n_discard, const uint8_t *flip, const double *u, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        int64_t x = (int64_t)state[c];
+        for (int64_t i = 0; i < steps; ++i) {
+            x = orc_mh_tab_step(lp, K, reflect, upper, x, flip[c * steps + i], u[c * steps + i]);
+            if (i >= n_discard) out[c * n_collect + (i - n_discard)] = (uint64_t)x;
+        }
+        state[c] = (uint64_t)x;
+    }
+    return 0;
+}
+/* native Philox keying: the octet contract of the integer MH kernel (see orc_mh_poisson_run_philox) */
+ORC_API int orc_mh_tabulated_run_philox(const double *lp, int64_t K, int reflect, int64_t upper, uint64_t *state, int64_t chains,
+                                        int64_t chain_offset, int64_t step_base, int64_t n_collect, int64_t n_discard,
+                                        uint64_t seed, uint64_t *out) {
+    const int64_t steps = n_collect + n_discard;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chains; ++c) {
+        int64_t x = (int64_t)state[c];
+        const uint64_t gc = (uint64_t)(c + chain_offset);
+        for (int64_t s = 0; s < steps; ++s) {
+            const uint64_t gs = (uint64_t)(step_base + s);
+            const uint32_t i = (uint32_t)(gs & 7);
+            uint32_t ctr[4] = {(uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)(gs >> 3), 0u};
+            uint32_t w[4], v[4];
+            orc_philox4x32_10(key, ctr, w);
+            ctr[3] = 1u + (i >> 1);
+            orc_philox4x32_10(key, ctr, v);
+            const uint32_t h = (w[i >> 1] >> (16u * (i & 1u))) & 0xffffu;
+            const int flip = (int)(h >> 15);
+            const uint64_t bits = (i & 1u) ? (((uint64_t)v[3] << 32) | v[2]) : (((uint64_t)v[1] << 32) | v[0]);
+            const uint64_t u53 = ((uint64_t)(h & 0x7fffu) << 38) | (bits >> 26);
+            const double u = (double)u53 * (1.0 / 9007199254740992.0);
+            x = orc_mh_tab_step(lp, K, reflect, upper, x, flip, u);
+            if (s >= n_discard) out[c * n_collect + (s - n_discard)] = (uint64_t)x;
+        }
+        state[c] = (uint64_t)x;
     }
     return 0;
 }

@@ -75,5 +75,10 @@ if "nuts" in what:
             for layout in (32, 0):
                 for exact in (True, False):
                     got = st.nuts_device(mm, case, layout, exact)
-                    report(f"NUTS D={D} {'f32' if f32 else 'f64'} layout={layout}(G={got['lanes']}) {'exact' if exact else 'fast'}",
-                           st.nuts_compare(exp, got))
+                    cmp = st.nuts_compare(exp, got)
+                    report(f"NUTS D={D} {'f32' if f32 else 'f64'} layout={layout}(G={got['lanes']}) {'exact' if exact else 'fast'}", cmp)
+                    if not exact:   # contracted arithmetic: the error against the tree depth (trajectory length)
+                        for d in sorted(set(cmp["depth"].tolist())):
+                            m = cmp["depth"] == d
+                            print(f"      depth {d}: {m.sum():4d} chains, alpha max {cmp['alpha'][m].max():.1e} inside 1e-5: {(cmp['alpha'][m] <= 1e-5).mean():.3f}; "
+                                  f"state max {cmp['state'][m].max():.1e} inside 1e-5: {(cmp['state'][m] <= 1e-5).mean():.3f}")

@@ -225,3 +225,126 @@ def test_poisson_compact_output_equals_widened_output(mm):
     np.testing.assert_array_equal(compact.astype(np.uint64), wide)
     # continuation: both handles advanced by the same 150 steps
     np.testing.assert_array_equal(b.run_compact(10, 0).astype(np.uint64), a.run(10, 0))
+
+
+# ---------------------------------------------------------------- MetropolisHastings<f32, f32, ..> and any-dimension targets
+def _f32_tapes(rng, chains, steps, D):
+    """Tapes of f32-representable values (the reference draws `u: f32`, `z: f32` for MetropolisHastings<f32, ..>)."""
+    noise = rng.normal(size=(chains, steps, D)).astype(np.float32).astype(np.float64)
+    u = rng.random((chains, steps)).astype(np.float32).astype(np.float64)
+    u[u >= 1.0] = 0.5
+    return noise, u
+
+
+@pytest.mark.parametrize("kind,D", [("gauss", 2), ("iso", 1), ("iso", 3), ("iso", 8), ("iso", 5), ("iso", 20)])
+def test_mh_f32_state_replay(mm, kind, D):
+    """f32 state (src/metropolis_hastings.rs:87): proposal, log-probabilities and the log-ratio reproduce the oracle's f32
+    restatement operation by operation; accept decisions are identical away from ties of r with ln(u) (the device logf
+    is not the host's), and chains whose decisions agree have bit-identical states."""
+    rng = np.random.default_rng(11 + D)
+    chains, steps = 300, 1
+    noise, u = _f32_tapes(rng, chains, steps, D)
+    u[0, 0] = 0.0
+    init = rng.normal(size=(chains, D)).astype(np.float32)
+    if kind == "gauss":
+        tgt, tp, okind = mm.Gaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]]), [0.0, 1.0, 4.0, 2.0, 2.0, 3.0], oracle.T_GAUSSIAN2D
+    else:
+        tgt, tp, okind = mm.IsotropicGaussian(1.7, dim=D), [1.7], oracle.T_ISO_GAUSSIAN
+    exp, exp_state, exp_trace = oracle.mh_cont_run_replay_f32(okind, tp, 0.8, init, 1, 0, noise, u, want_trace=True)
+    mh = mm.MetropolisHastings(tgt, mm.IsotropicGaussian(0.8), init)
+    assert mh._np_dtype == np.float32
+    trace = np.zeros((chains, steps, 4))
+    got = mh.run(1, 0, replay=dict(noise=noise, u=u), trace=trace)
+    assert got.dtype == np.float32
+    # single transition: log-probabilities and the ratio are the same f32 operations -> equal to the last bit
+    np.testing.assert_array_equal(trace[..., :3].astype(np.float32), exp_trace[..., :3])
+    lnu = np.log(np.maximum(u, 1e-300))
+    tie = np.abs(exp_trace[..., 2].astype(np.float64) - lnu) < 1e-5 * np.maximum(1.0, np.abs(lnu))
+    same = trace[..., 3] == exp_trace[..., 3]
+    assert (same | tie).all() and tie.mean() < 0.01
+    ok = same[:, 0]
+    np.testing.assert_array_equal(got[ok], exp[ok])
+    np.testing.assert_array_equal(mh.current_state()[ok], exp_state[ok])
+
+
+@pytest.mark.parametrize("D", [5, 16, 100, 256])
+def test_mh_iso_any_dimension_f64(mm, D):
+    """IsotropicGaussian target + proposal beyond the register-resident dimensions: sequential sums like the CPU code."""
+    rng = np.random.default_rng(D)
+    chains, n_collect, n_discard = 130, 12, 5
+    steps = n_collect + n_discard
+    noise = rng.normal(size=(chains, steps, D))
+    u = rng.random((chains, steps))
+    init = rng.normal(size=(chains, D))
+    exp, exp_state, _ = oracle.mh_cont_run_replay(oracle.T_ISO_GAUSSIAN, [1.3], 0.3, init, n_collect, n_discard, noise, u)
+    mh = mm.MetropolisHastings(mm.IsotropicGaussian(1.3, dim=D), mm.IsotropicGaussian(0.3), init)
+    got = mh.run(n_collect, n_discard, replay=dict(noise=noise, u=u))
+    np.testing.assert_allclose(got, exp, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(mh.current_state(), exp_state, rtol=1e-12, atol=0)
+    with pytest.raises(Exception):
+        mm.MetropolisHastings(mm.IsotropicGaussian(1.0, dim=257), mm.IsotropicGaussian(0.3), np.zeros((2, 257)))
+
+
+def test_mh_f32_native_distribution_and_progress(mm):
+    """Native Philox path on f32 state: the Gaussian2D moments of src/metropolis_hastings.rs:338-401, sharding invariance
+    and run_progress == run."""
+    init = mm.init_det(64, 2).astype(np.float32)
+    tgt = mm.Gaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
+    s = mm.MetropolisHastings(tgt, mm.IsotropicGaussian(1.0), init).seed(42).run(2000, 500)
+    assert s.dtype == np.float32
+    flat = s.reshape(-1, 2).astype(np.float64)
+    assert np.abs(flat.mean(axis=0) - [0.0, 1.0]).max() < 0.3
+    assert np.abs(np.cov(flat.T) - [[4.0, 2.0], [2.0, 3.0]]).max() < 0.5
+    part = mm.MetropolisHastings(tgt, mm.IsotropicGaussian(1.0), init[40:]).seed(42).set_chain_offset(40).run(2000, 500)
+    np.testing.assert_array_equal(part, s[40:])
+    sample, stats = mm.MetropolisHastings(tgt, mm.IsotropicGaussian(1.0), init).seed(42).run_progress(2000, 500, progress=False, block=300)
+    np.testing.assert_array_equal(sample, s)
+
+
+# ---------------------------------------------------------------- i32 variants of tests/metrohast_poisson_test.rs
+@pytest.mark.parametrize("case", ["poisson", "binomial"])
+def test_tabulated_reflecting_walk_bit_exact(mm, case):
+    """PoissonDist + PoissonRandomWalk and BinomialDist + BinomialRandomWalk (tests/metrohast_poisson_test.rs:18-85,
+    157-214): the device's table-driven kernel against the oracle's literal `r > ln(u)` step, native Philox stream and
+    replayed flips / uniforms."""
+    rng = np.random.default_rng(3)
+    if case == "poisson":
+        tgt, upper, start = mm.TabulatedTarget.poisson(4.0, 64), -1, 0
+    else:
+        tgt, upper, start = mm.TabulatedTarget.binomial(10, 0.3), 10, 5
+    chains, nc, nd = 333, 210, 45
+    init = np.full((chains, 1), start, dtype=np.uint64)
+    mh = mm.MetropolisHastings(tgt, mm.ReflectingRandomWalk(), init).seed(42).set_chain_offset(9)
+    out = mh.run(nc, nd)
+    exp, exp_state = oracle.mh_tabulated_run_philox(tgt.table, init, nc, nd, seed=42, reflect=True, upper=upper, chain_offset=9)
+    np.testing.assert_array_equal(out, exp)
+    np.testing.assert_array_equal(mh.current_state().reshape(-1), exp_state)
+    out2 = mh.run(30, 0)
+    exp2, _ = oracle.mh_tabulated_run_philox(tgt.table, exp_state, 30, 0, seed=42, reflect=True, upper=upper, chain_offset=9,
+                                             step_base=nc + nd)
+    np.testing.assert_array_equal(out2, exp2)
+    flip = rng.integers(0, 2, size=(chains, nc + nd)).astype(np.uint8)
+    u = rng.random((chains, nc + nd))
+    out3 = mm.MetropolisHastings(tgt, mm.ReflectingRandomWalk(), init).run(nc, nd, replay=dict(flip=flip, u=u))
+    exp3, _ = oracle.mh_tabulated_run_replay(tgt.table, init, nc, nd, flip, u, reflect=True, upper=upper)
+    np.testing.assert_array_equal(out3, exp3)
+    # the same table under NonnegativeProposal follows examples/poisson_mh.rs' asymmetric walk
+    out4 = mm.MetropolisHastings(tgt, mm.NonnegativeProposal(), init).run(nc, nd, replay=dict(flip=flip, u=u))
+    exp4, _ = oracle.mh_tabulated_run_replay(tgt.table, init, nc, nd, flip, u, reflect=False)
+    np.testing.assert_array_equal(out4, exp4)
+
+
+def test_tabulated_pmf_pins(mm):
+    """test_poisson_mh / test_binomial_mh (tests/metrohast_poisson_test.rs:90-130,220-249): frequencies of k = 0..10
+    within 0.05 of the pmf (0.01 here: many chains)."""
+    init = np.zeros((2048, 1), dtype=np.uint64)
+    s = mm.MetropolisHastings(mm.PoissonTarget(4.0), mm.ReflectingRandomWalk(), init).seed(42).run(1000, 2000).reshape(-1)
+    for k in range(11):
+        pmf = math.exp(-4.0 + k * math.log(4.0) - math.lgamma(k + 1))
+        assert abs((s == k).mean() - pmf) < 0.01
+    init = np.full((2048, 1), 5, dtype=np.uint64)
+    s = mm.MetropolisHastings(mm.TabulatedTarget.binomial(10, 0.3), mm.ReflectingRandomWalk(), init).seed(42).run(1000, 2000).reshape(-1)
+    assert s.max() <= 10
+    for k in range(11):
+        pmf = math.comb(10, k) * 0.3 ** k * 0.7 ** (10 - k)
+        assert abs((s == k).mean() - pmf) < 0.01

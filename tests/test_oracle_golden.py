@@ -255,3 +255,28 @@ def test_gibbs_constant_and_replay_roundtrip():
     rec = oracle.gibbs_run(oracle.G_MIXTURE2, (-2.0, 1.0, 3.0, 1.5, 0.25), init, 50, 10, cond_seed=7, record=True)
     rep = oracle.gibbs_run(oracle.G_MIXTURE2, (-2.0, 1.0, 3.0, 1.5, 0.25), init, 50, 10, tapes=rec["tapes"])
     np.testing.assert_array_equal(rec["out"], rep["out"])
+
+
+def test_tabulated_reflecting_walk_pmf_pins():
+    """test_poisson_mh / test_binomial_mh (tests/metrohast_poisson_test.rs:90-130,220-249): one chain, 20,000 + 2,000
+    transitions from 0 (Poisson) / 5 (Binomial), frequencies of k = 0..10 within 0.05 of the pmf - on the oracle's
+    restatement of the i32 targets with the reflecting +-1 walk."""
+    import math
+
+    import mini_mcmc_b200.distributions as dist
+
+    for table, start, upper, pmf in (
+        (dist.TabulatedTarget.poisson(4.0, 64).table, 0, -1, lambda k: math.exp(-4.0 + k * math.log(4.0) - math.lgamma(k + 1))),
+        (dist.TabulatedTarget.binomial(10, 0.3).table, 5, 10, lambda k: math.comb(10, k) * 0.3 ** k * 0.7 ** (10 - k)),
+    ):
+        flips = oracle.SmallRng(42).bool_half(22_000)[None]
+        u = oracle.SmallRng(43).f64(22_000)[None]
+        out, _ = oracle.mh_tabulated_run_replay(table, np.array([start], dtype=np.uint64), 20_000, 2_000, flips, u,
+                                                reflect=True, upper=upper)
+        s = out.reshape(-1)
+        assert s.max() <= (upper if upper >= 0 else 63)
+        for k in range(11):
+            assert abs((s == k).mean() - pmf(k)) < 0.05
+    # BinomialDist's table is ln C(n, k) + k ln p + (n - k) ln(1 - p)
+    t = dist.TabulatedTarget.binomial(10, 0.3).table
+    np.testing.assert_allclose(np.exp(t), [math.comb(10, k) * 0.3 ** k * 0.7 ** (10 - k) for k in range(11)], rtol=1e-12)
