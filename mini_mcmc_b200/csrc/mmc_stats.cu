@@ -295,8 +295,14 @@ __device__ __forceinline__ SF2 sf2_sub(SF2 a, SF2 b) { SF2 r; asm("sub.rn.f32x2 
 __device__ __forceinline__ SF2 sf2_mul(SF2 a, SF2 b) { SF2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ SF2 sf2_ld(const float *p) { SF2 r; r.v = *reinterpret_cast<const unsigned long long *>(p); return r; }
 
-template <bool kFirst>
-__global__ void __launch_bounds__(256, 1)
+// Thread (k, q2, r): staged chain k, parameter pair q2, replica r = (lag group h of LB lags, time segment g).  A lag group
+// with base lag l only has partners for t >= l, so its G segments split [l, N) (not [0, N)): every replica of a group does
+// the same number of steps.  LB = 8 for the first window (lags 0..7: 8 FFMA2 per draw keep the pass under the HBM time of
+// its 80 KB block), 16 afterwards.  Main loop: unmasked blocks of LB steps; one masked block at the end of the segment.
+// kThreads x kBlocks: 512 x 1 (one CTA per SM, double-buffered staging) or 256 x 2 (two CTAs per SM, one staging buffer
+// each: while one CTA waits for its bulk copy the other one computes, and their barriers do not line up)
+template <int LB, bool kFirst, int kThreads, int kBlocks>
+__global__ void __launch_bounds__(kThreads, kBlocks)
 stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int p, int64_t lag0, int H, int G, int K, int nbuf,
                     double *__restrict__ partial) {
     extern __shared__ __align__(128) float st_smem[];
@@ -313,8 +319,12 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
     const int q2 = v % p2, k = v / p2;              // this thread's parameters are 2 q2 and 2 q2 + 1
     const int h = r % H, g = r / H;
     const bool active = r < R;
-    const int seg = (((N + G - 1) / G) + kLagBlock - 1) / kLagBlock * kLagBlock;
-    const int t_lo = g * seg, t_hi = (t_lo + seg < N) ? t_lo + seg : N;
+    const int lag_base = (int)lag0 + h * LB;
+    // this replica's steps: segment g of [lag_base, N)
+    const int span = N > lag_base ? N - lag_base : 0;
+    const int seg = (span + G - 1) / G;
+    const int t_lo = lag_base + g * seg;
+    const int t_hi = (t_lo + seg < N) ? t_lo + seg : N;
     const float inv_n = 1.0f / (float)N;
     const SF2 inv_n2 = sf2_pack(inv_n, inv_n), zero2 = sf2_pack(0.f, 0.f);
     const uint32_t bytes = (uint32_t)blk * 4u;
@@ -335,11 +345,11 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
         for (int kk = 0; kk < nk; ++kk)
             st_bulk_load(st_smem_u32(bufs + ((size_t)b * K + kk) * blk), block_src(j + kk), bytes, st_smem_u32(&bars[b]));
     };
-    SF2 acc[kLagBlock];
+    SF2 acc[LB];
 #pragma unroll
-    for (int i = 0; i < kLagBlock; ++i) acc[i] = zero2;
+    for (int i = 0; i < LB; ++i) acc[i] = zero2;
     double acc_m0 = 0.0, acc_m1 = 0.0, acc_q0 = 0.0, acc_q1 = 0.0;
-    const int lag_base = (int)lag0 + h * kLagBlock;
+    const bool lag_zero = lag_base == 0;            // lag 0 shares its operand with the ring: one load per step
 
     int64_t j = (int64_t)blockIdx.x * K;
     const int64_t stride = (int64_t)gridDim.x * K;
@@ -352,54 +362,60 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
         st_mbar_wait(st_smem_u32(&bars[b]), ph);
         const bool have = active && (j + k < C);
         const float *x = bufs + ((size_t)b * K + k) * blk + 2 * q2;   // 8-byte aligned: blk and p are even
-        if (have) {
-            SF2 s0 = zero2;
-            for (int t = r; t < N; t += R) s0 = sf2_add(s0, sf2_ld(x + (size_t)t * p));
-            *reinterpret_cast<unsigned long long *>(mean_part + (size_t)r * 2 * PK + 2 * v) = s0.v;
+        if (have) {   // mean: replica r sums t = r, r + R, ...; the R partials are combined through shared memory
+            SF2 s0 = zero2, s1 = zero2;
+            int t = r;
+            for (; t + R < N; t += 2 * R) {
+                s0 = sf2_add(s0, sf2_ld(x + (size_t)t * p));
+                s1 = sf2_add(s1, sf2_ld(x + (size_t)(t + R) * p));
+            }
+            if (t < N) s0 = sf2_add(s0, sf2_ld(x + (size_t)t * p));
+            *reinterpret_cast<unsigned long long *>(mean_part + (size_t)r * 2 * PK + 2 * v) = sf2_add(s0, s1).v;
         }
         __syncthreads();
-        if (have && t_lo < N) {
+        if (have) {
             SF2 m = zero2;
             for (int rr = 0; rr < R; ++rr) m = sf2_add(m, sf2_ld(mean_part + (size_t)rr * 2 * PK + 2 * v));
             m = sf2_mul(m, inv_n2);
-            SF2 P[kLagBlock], ring[kLagBlock];
+            if (t_lo < t_hi) {
+                SF2 P[LB], ring[LB];
 #pragma unroll
-            for (int i = 0; i < kLagBlock; ++i) P[i] = zero2;
+                for (int i = 0; i < LB; ++i) P[i] = zero2;
+                // ring slot u before the first block holds the partner of step t_lo - LB + u, i.e. draw t_lo - LB + u - lag_base
 #pragma unroll
-            for (int u = 0; u < kLagBlock; ++u) {
-                const int tb = t_lo - kLagBlock + u - lag_base;
-                const SF2 vb = sf2_ld(x + (size_t)(tb > 0 ? tb : 0) * p);
-                ring[u] = (t_lo > 0 && tb >= 0) ? sf2_sub(vb, m) : zero2;
-            }
-            int t0 = t_lo;
-            const bool lag_zero = kFirst && h == 0;
-            for (; t0 + kLagBlock <= t_hi && (lag_zero || t0 >= lag_base); t0 += kLagBlock) {
-                const float *xa = x + (size_t)t0 * p;
-                const float *xb = x + (size_t)(t0 - lag_base) * p;
-#pragma unroll
-                for (int u = 0; u < kLagBlock; ++u) {
-                    const SF2 a = sf2_sub(sf2_ld(xa + (size_t)u * p), m);
-                    ring[u] = lag_zero ? a : sf2_sub(sf2_ld(xb + (size_t)u * p), m);
-#pragma unroll
-                    for (int i = 0; i < kLagBlock; ++i) P[i] = sf2_fma(a, ring[(u - i) & (kLagBlock - 1)], P[i]);
-                }
-            }
-            for (; t0 < t_hi; t0 += kLagBlock) {
-#pragma unroll
-                for (int u = 0; u < kLagBlock; ++u) {
-                    const int t = t0 + u;
-                    const int tc = t < N ? t : N - 1;
-                    const int tb = tc - lag_base;
-                    const SF2 va = sf2_ld(x + (size_t)tc * p);
+                for (int u = 0; u < LB; ++u) {
+                    const int tb = t_lo - LB + u - lag_base;
                     const SF2 vb = sf2_ld(x + (size_t)(tb > 0 ? tb : 0) * p);
-                    const SF2 a = t < N ? sf2_sub(va, m) : zero2;
-                    ring[u] = (t < N && tb >= 0) ? sf2_sub(vb, m) : zero2;
-#pragma unroll
-                    for (int i = 0; i < kLagBlock; ++i) P[i] = sf2_fma(a, ring[(u - i) & (kLagBlock - 1)], P[i]);
+                    ring[u] = tb >= 0 ? sf2_sub(vb, m) : zero2;
                 }
-            }
+                int t0 = t_lo;
+                for (; t0 + LB <= t_hi; t0 += LB) {
+                    const float *xa = x + (size_t)t0 * p;
+                    const float *xb = x + (size_t)(t0 - lag_base) * p;
 #pragma unroll
-            for (int i = 0; i < kLagBlock; ++i) acc[i] = sf2_fma(P[i], inv_n2, acc[i]);
+                    for (int u = 0; u < LB; ++u) {
+                        const SF2 a = sf2_sub(sf2_ld(xa + (size_t)u * p), m);
+                        ring[u] = lag_zero ? a : sf2_sub(sf2_ld(xb + (size_t)u * p), m);
+#pragma unroll
+                        for (int i = 0; i < LB; ++i) P[i] = sf2_fma(a, ring[(u - i) & (LB - 1)], P[i]);
+                    }
+                }
+                if (t0 < t_hi) {   // last, partial block of the segment
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) {
+                        const int t = t0 + u;
+                        const int tc = t < t_hi ? t : t_hi - 1;
+                        const SF2 va = sf2_ld(x + (size_t)tc * p);
+                        const SF2 vb = sf2_ld(x + (size_t)(tc - lag_base) * p);
+                        const SF2 a = t < t_hi ? sf2_sub(va, m) : zero2;
+                        ring[u] = sf2_sub(vb, m);
+#pragma unroll
+                        for (int i = 0; i < LB; ++i) P[i] = sf2_fma(a, ring[(u - i) & (LB - 1)], P[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < LB; ++i) acc[i] = sf2_fma(P[i], inv_n2, acc[i]);
+            }
             if (kFirst && r == 0) {
                 float m0, m1;
                 sf2_unpack(m, m0, m1);
@@ -419,7 +435,7 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
             atomicAdd(partial + p + q + 1, acc_q1);
         }
 #pragma unroll
-        for (int i = 0; i < kLagBlock; ++i)
+        for (int i = 0; i < LB; ++i)
             if (lag_base + i < N) {
                 float a0, a1;
                 sf2_unpack(acc[i], a0, a1);
@@ -440,30 +456,44 @@ int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p
         getenv("MMC_STATS_NO_SMEM"))
         return MMC_OK;
     if ((reinterpret_cast<uintptr_t>(sample) & 15) != 0) return MMC_OK;
-    if (p % 2 == 0 && lag0 == 0 && !getenv("MMC_STATS_NO_PACKED")) {
-        // packed kernel (first pass, where lag 0 shares its operand with the ring: 3.8 vs 4.3 ms on the C5 sample; later
-        // passes read two operands per step and measured slower packed): a thread owns two adjacent parameters, 256 threads
+    if (p % 2 == 0 && p <= 512 && !getenv("MMC_STATS_NO_PACKED")) {
+        // packed kernel: a thread owns two adjacent parameters; up to 512 threads = (p / 2) x K staged chains x R replicas,
+        // R = H lag groups x G time segments.  The first window uses groups of 8 lags, later ones 16.
         const int64_t p2 = p / 2;
-        int H = (int)std::min<int64_t>((n_lags + kLagBlock - 1) / kLagBlock, 256 / p2);
+        const bool first = lag0 == 0;
+        const int LB = (first && n_lags <= 8) ? 8 : kLagBlock;
+        // two CTAs of 256 threads per SM when two single staging buffers fit (C5: 2 x 80 KB), else one CTA of 512 threads
+        // (16-lag groups keep 96 packed accumulator / ring registers: they run as one CTA of 384 threads with 168 registers)
+        const bool twin = LB == 8 && 2 * (blk_bytes + 2 * (size_t)std::max<int64_t>(1, 256 / p2) * p * 4 + 512) <= 224 * 1024 &&
+                          p2 <= 256 && !getenv("MMC_STATS_ONE_CTA");
+        const int64_t tmax = twin ? 256 : (LB == 8 ? 512 : 384);
+        const int64_t rmax = std::max<int64_t>(1, tmax / p2);           // replicas per (chain, pair) with one staged chain
+        int H = (int)std::min<int64_t>((n_lags + LB - 1) / LB, rmax);
         if (H < 1) H = 1;
-        int G = (int)(256 / (p2 * H));
+        int G = (int)(rmax / H);
         if (G < 1) G = 1;
-        if (G > (int)((N + kLagBlock - 1) / kLagBlock)) G = (int)((N + kLagBlock - 1) / kLagBlock);
-        int K = (int)std::min<int64_t>(16, 256 / (p2 * H * G));
+        const int64_t steps = std::max<int64_t>(1, N - lag0);
+        if (G > (int)((steps + LB - 1) / LB)) G = (int)((steps + LB - 1) / LB);   // a segment is at least one block of LB steps
+        int K = (int)std::min<int64_t>(16, tmax / (p2 * H * G));
         if (K < 1) K = 1;
-        while (K > 1 && 2 * (size_t)K * blk_bytes + (size_t)H * G * K * p * 4 + 256 > 200 * 1024) --K;
+        const size_t budget = twin ? 112 * 1024 : 200 * 1024;
+        while (K > 1 && (twin ? 1 : 2) * (size_t)K * blk_bytes + (size_t)H * G * K * p * 4 + 256 > budget) --K;
         if ((int64_t)K > 2 * c_local) K = (int)(2 * c_local);
         const size_t extra = (size_t)H * G * K * p * 4 + 256;
-        const int nbuf = (2 * K * blk_bytes + extra <= 220 * 1024) ? 2 : 1;
+        const int nbuf = twin ? 1 : ((2 * K * blk_bytes + extra <= 220 * 1024) ? 2 : 1);
         const size_t smem = nbuf * K * blk_bytes + extra;
         const int threads = (int)((p2 * H * G * K + 31) / 32 * 32);
-        int64_t grid = sm_count();
+        MMC_REQUIRE(threads <= tmax, "stats: %d threads > %d", threads, (int)tmax);
+        int64_t grid = (int64_t)sm_count() * (twin ? 2 : 1);
         if (grid > (2 * c_local + K - 1) / K) grid = (2 * c_local + K - 1) / K;
-        auto kern = stats_block2_kernel<true>;
+        void (*kern)(const float *, int64_t, int64_t, int, int64_t, int, int, int, int, double *);
+        if (twin) kern = stats_block2_kernel<8, true, 256, 2>;
+        else kern = LB == 8 ? stats_block2_kernel<8, true, 512, 1>
+                            : (first ? stats_block2_kernel<kLagBlock, true, 384, 1> : stats_block2_kernel<kLagBlock, false, 384, 1>);
         MMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, threads, smem, stream>>>(sample, c_local, n, (int)p, lag0, H, G, K, nbuf, partial);
         MMC_CUDA(cudaGetLastError());
-        *covered = std::min<int64_t>((int64_t)H * kLagBlock, N - lag0);
+        *covered = std::min<int64_t>((int64_t)H * LB, N - lag0);
         return MMC_OK;
     }
     int H = (int)std::min<int64_t>((n_lags + kLagBlock - 1) / kLagBlock, 512 / p);
@@ -650,7 +680,8 @@ int split_rhat_ess_protocol(const float *sample_dev, int64_t c_local, int64_t n,
     }
     double *d_partial = W.ws + 1;
     int *d_flag = reinterpret_cast<int *>(W.out + 2 * p);
-    int64_t have = 0, block = kLagBlock;
+    // lag windows: 8 (well-mixed chains terminate there and the pass stays HBM bound), then 64 more, then everything
+    int64_t have = 0, block = 8;
     while (have < N) {
         const int64_t want = std::min<int64_t>(block, N - have);
         if (have == 0) stats_set_count_kernel<<<1, 1, 0, s>>>(W.ws, (double)c_local, d_flag);
@@ -672,7 +703,7 @@ int split_rhat_ess_protocol(const float *sample_dev, int64_t c_local, int64_t n,
         int flag;
         memcpy(&flag, W.h_out + 2 * p, sizeof(int));
         if (!flag) break;
-        block *= 2;  // geometric growth keeps the number of rounds logarithmic
+        block = have <= 8 ? 64 : N;  // at most three rounds
     }
     if (rhat_host) memcpy(rhat_host, W.h_out, sizeof(float) * (size_t)p);
     if (ess_host) memcpy(ess_host, W.h_out + p, sizeof(float) * (size_t)p);

@@ -135,7 +135,7 @@ def sharded_split_rhat_ess(partial_fn, c_local, n, p, group, device):
     partial = torch.zeros(plen, dtype=torch.float64, device=device)
     rhat = np.empty(p, dtype=np.float32)
     ess = np.empty(p, dtype=np.float32)
-    have, block = 0, 16
+    have, block = 0, 8       # the windows of split_rhat_ess_protocol (csrc/mmc_stats.cu): 8, 64 more, everything
     while have < N:
         want = min(block, N - have)
         partial_fn(partial, have, want)
@@ -150,7 +150,7 @@ def sharded_split_rhat_ess(partial_fn, c_local, n, p, group, device):
             L.check(rc)
         if rc == 0:
             break
-        block *= 2
+        block = 64 if have <= 8 else N
     return rhat, ess
 
 

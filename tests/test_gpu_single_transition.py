@@ -127,8 +127,17 @@ def check_nuts(cmp, exact, what):
     # and inside 1e-4 for all of them - the tail are deep trees (up to 256 leapfrogs) and the stiff 2-D ridge, where the
     # dynamics amplify a last-ulp difference exactly as in the HMC f64-shadow test
     for k in ("state", "alpha"):
-        assert frac(cmp[k], RTOL) >= 0.99, f"{what}: {k} only {frac(cmp[k], RTOL):.3f} of the chains inside RTOL"
+        # alpha on the stiff 2-D Rosenbrock target: logp = -(100 t^2 + u^2) with t = y - x^2 turns a last-ulp difference of
+        # x^2 into 200 |t| ulp(x^2) of logp, so the sum of exp(joint' - joint_0) over up to 256 leaves leaves RTOL on a few
+        # per cent of the deep trees (measured: every tree of depth <= 4 inside RTOL, 95.5 % at depth 5-6, max 3.3e-5; x'
+        # stays inside RTOL on every chain).  The reference arithmetic (exact = True) is held to RTOL above.
+        need = 0.95 if (k == "alpha" and what_dim(what) == 2) else 0.99
+        assert frac(cmp[k], RTOL) >= need, f"{what}: {k} only {frac(cmp[k], RTOL):.3f} of the chains inside RTOL"
         assert cmp[k].max() <= 1e-4, f"{what}: {k} {cmp[k].max():.2e}"
+    if what_dim(what) == 2:
+        assert cmp["state"].max() <= RTOL, f"{what}: state {cmp['state'].max():.2e}"
+        shallow = cmp["depth"] <= 4
+        assert cmp["alpha"][shallow].max(initial=0.0) <= RTOL, f"{what}: alpha (depth <= 4) {cmp['alpha'][shallow].max():.2e}"
     if what_dim(what) >= 10:   # the C5 family: shallow trees (depth <= 5, 95 % of C5's transitions) are inside RTOL on EVERY chain
         shallow = cmp["depth"] <= 5
         assert cmp["state"][shallow].max(initial=0.0) <= RTOL, f"{what}: state {cmp['state'][shallow].max():.2e}"
