@@ -298,10 +298,13 @@ __device__ __forceinline__ SF2 sf2_ld(const float *p) { SF2 r; r.v = *reinterpre
 // Thread (k, q2, r): staged chain k, parameter pair q2, replica r = (lag group h of LB lags, time segment g).  A lag group
 // with base lag l only has partners for t >= l, so its G segments split [l, N) (not [0, N)): every replica of a group does
 // the same number of steps.  LB = 8 for the first window (lags 0..7: 8 FFMA2 per draw keep the pass under the HBM time of
-// its 80 KB block), 16 afterwards.  Main loop: unmasked blocks of LB steps; one masked block at the end of the segment.
-// kThreads x kBlocks: 512 x 1 (one CTA per SM, double-buffered staging) or 256 x 2 (two CTAs per SM, one staging buffer
-// each: while one CTA waits for its bulk copy the other one computes, and their barriers do not line up)
-template <int LB, bool kFirst, int kThreads, int kBlocks>
+// its 80 KB block), 16 afterwards.  kZero: every replica works on lag base 0 (first window), so a step's value is its own
+// partner and one shared-memory read feeds the step.  Everything a thread needs per round is computed once before the round
+// loop (offsets, trip counts, the warm-up mask); a round is: mean (strided partial sums + one barrier), ring warm-up,
+// unmasked blocks of LB steps, one masked block.
+// kThreads x kBlocks: 512 x 1 / 384 x 1 (one CTA per SM, double-buffered staging) or 256 x 2 (two CTAs per SM, one staging
+// buffer each: while one CTA waits for its bulk copy the other one computes, and their barriers do not line up).
+template <int LB, bool kFirst, bool kZero, int kThreads, int kBlocks>
 __global__ void __launch_bounds__(kThreads, kBlocks)
 stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n, int p, int64_t lag0, int H, int G, int K, int nbuf,
                     double *__restrict__ partial) {
@@ -319,12 +322,25 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
     const int q2 = v % p2, k = v / p2;              // this thread's parameters are 2 q2 and 2 q2 + 1
     const int h = r % H, g = r / H;
     const bool active = r < R;
-    const int lag_base = (int)lag0 + h * LB;
+    const int lag_base = kZero ? 0 : (int)lag0 + h * LB;
     // this replica's steps: segment g of [lag_base, N)
     const int span = N > lag_base ? N - lag_base : 0;
     const int seg = (span + G - 1) / G;
     const int t_lo = lag_base + g * seg;
     const int t_hi = (t_lo + seg < N) ? t_lo + seg : N;
+    const int n_steps = (active && t_hi > t_lo) ? t_hi - t_lo : 0;
+    const int n_full = n_steps / LB, n_rem = n_steps % LB;
+    const int off_a = k * blk + t_lo * p + 2 * q2;              // this thread's first draw (floats from the buffer base)
+    const int off_b = off_a - lag_base * p;                     // and its partner at the group's base lag
+    // ring slot u before the first block holds the partner of step t_lo - LB + u, i.e. draw t_lo - LB + u - lag_base (if any)
+    uint32_t warm_mask = 0;
+#pragma unroll
+    for (int u = 0; u < LB; ++u)
+        if (t_lo - LB + u - lag_base >= 0) warm_mask |= 1u << u;
+    const int off_w = off_b - LB * p;
+    // mean: replica r sums t = r, r + R, ...
+    const int mean_cnt = active ? (N - r + R - 1) / R : 0;
+    const int off_m = k * blk + r * p + 2 * q2, stride_m = R * p;
     const float inv_n = 1.0f / (float)N;
     const SF2 inv_n2 = sf2_pack(inv_n, inv_n), zero2 = sf2_pack(0.f, 0.f);
     const uint32_t bytes = (uint32_t)blk * 4u;
@@ -349,7 +365,6 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
 #pragma unroll
     for (int i = 0; i < LB; ++i) acc[i] = zero2;
     double acc_m0 = 0.0, acc_m1 = 0.0, acc_q0 = 0.0, acc_q1 = 0.0;
-    const bool lag_zero = lag_base == 0;            // lag 0 shares its operand with the ring: one load per step
 
     int64_t j = (int64_t)blockIdx.x * K;
     const int64_t stride = (int64_t)gridDim.x * K;
@@ -361,15 +376,16 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
         if (nbuf == 2 && tid == 0 && j + stride < C) issue(j + stride, b ^ 1);
         st_mbar_wait(st_smem_u32(&bars[b]), ph);
         const bool have = active && (j + k < C);
-        const float *x = bufs + ((size_t)b * K + k) * blk + 2 * q2;   // 8-byte aligned: blk and p are even
-        if (have) {   // mean: replica r sums t = r, r + R, ...; the R partials are combined through shared memory
+        const float *xbuf = bufs + (size_t)b * K * blk;   // 8-byte aligned offsets: blk and p are even
+        if (have) {
             SF2 s0 = zero2, s1 = zero2;
-            int t = r;
-            for (; t + R < N; t += 2 * R) {
-                s0 = sf2_add(s0, sf2_ld(x + (size_t)t * p));
-                s1 = sf2_add(s1, sf2_ld(x + (size_t)(t + R) * p));
+            const float *pm = xbuf + off_m;
+            int c2 = mean_cnt;
+            for (; c2 >= 2; c2 -= 2, pm += 2 * stride_m) {
+                s0 = sf2_add(s0, sf2_ld(pm));
+                s1 = sf2_add(s1, sf2_ld(pm + stride_m));
             }
-            if (t < N) s0 = sf2_add(s0, sf2_ld(x + (size_t)t * p));
+            if (c2) s0 = sf2_add(s0, sf2_ld(pm));
             *reinterpret_cast<unsigned long long *>(mean_part + (size_t)r * 2 * PK + 2 * v) = sf2_add(s0, s1).v;
         }
         __syncthreads();
@@ -377,38 +393,48 @@ stats_block2_kernel(const float *__restrict__ sample, int64_t c_local, int64_t n
             SF2 m = zero2;
             for (int rr = 0; rr < R; ++rr) m = sf2_add(m, sf2_ld(mean_part + (size_t)rr * 2 * PK + 2 * v));
             m = sf2_mul(m, inv_n2);
-            if (t_lo < t_hi) {
+            if (n_steps > 0) {
                 SF2 P[LB], ring[LB];
 #pragma unroll
                 for (int i = 0; i < LB; ++i) P[i] = zero2;
-                // ring slot u before the first block holds the partner of step t_lo - LB + u, i.e. draw t_lo - LB + u - lag_base
+                if (warm_mask == 0) {
 #pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const int tb = t_lo - LB + u - lag_base;
-                    const SF2 vb = sf2_ld(x + (size_t)(tb > 0 ? tb : 0) * p);
-                    ring[u] = tb >= 0 ? sf2_sub(vb, m) : zero2;
+                    for (int u = 0; u < LB; ++u) ring[u] = zero2;
+                } else {
+                    const float *pw = xbuf + off_w;
+#pragma unroll
+                    for (int u = 0; u < LB; ++u)
+                        ring[u] = ((warm_mask >> u) & 1u) ? sf2_sub(sf2_ld(pw + u * p), m) : zero2;
                 }
-                int t0 = t_lo;
-                for (; t0 + LB <= t_hi; t0 += LB) {
-                    const float *xa = x + (size_t)t0 * p;
-                    const float *xb = x + (size_t)(t0 - lag_base) * p;
+                const float *pa = xbuf + off_a, *pb = xbuf + off_b;
+                for (int bi = 0; bi < n_full; ++bi) {
 #pragma unroll
                     for (int u = 0; u < LB; ++u) {
-                        const SF2 a = sf2_sub(sf2_ld(xa + (size_t)u * p), m);
-                        ring[u] = lag_zero ? a : sf2_sub(sf2_ld(xb + (size_t)u * p), m);
+                        const SF2 a = sf2_sub(sf2_ld(pa), m);
+                        pa += p;
+                        if (kZero) {
+                            ring[u] = a;
+                        } else {
+                            ring[u] = sf2_sub(sf2_ld(pb), m);
+                            pb += p;
+                        }
 #pragma unroll
                         for (int i = 0; i < LB; ++i) P[i] = sf2_fma(a, ring[(u - i) & (LB - 1)], P[i]);
                     }
                 }
-                if (t0 < t_hi) {   // last, partial block of the segment
+                if (n_rem) {   // last, partial block of the segment (clamped reads, masked products)
 #pragma unroll
                     for (int u = 0; u < LB; ++u) {
-                        const int t = t0 + u;
-                        const int tc = t < t_hi ? t : t_hi - 1;
-                        const SF2 va = sf2_ld(x + (size_t)tc * p);
-                        const SF2 vb = sf2_ld(x + (size_t)(tc - lag_base) * p);
-                        const SF2 a = t < t_hi ? sf2_sub(va, m) : zero2;
-                        ring[u] = sf2_sub(vb, m);
+                        const bool ok = u < n_rem;
+                        const SF2 va = sf2_sub(sf2_ld(pa), m);
+                        const SF2 a = ok ? va : zero2;
+                        if (kZero) {
+                            ring[u] = a;
+                        } else {
+                            ring[u] = sf2_sub(sf2_ld(pb), m);
+                            if (u + 1 < n_rem) pb += p;
+                        }
+                        if (u + 1 < n_rem) pa += p;
 #pragma unroll
                         for (int i = 0; i < LB; ++i) P[i] = sf2_fma(a, ring[(u - i) & (LB - 1)], P[i]);
                     }
@@ -487,9 +513,11 @@ int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p
         int64_t grid = (int64_t)sm_count() * (twin ? 2 : 1);
         if (grid > (2 * c_local + K - 1) / K) grid = (2 * c_local + K - 1) / K;
         void (*kern)(const float *, int64_t, int64_t, int, int64_t, int, int, int, int, double *);
-        if (twin) kern = stats_block2_kernel<8, true, 256, 2>;
-        else kern = LB == 8 ? stats_block2_kernel<8, true, 512, 1>
-                            : (first ? stats_block2_kernel<kLagBlock, true, 384, 1> : stats_block2_kernel<kLagBlock, false, 384, 1>);
+        // kZero needs every replica on lag base 0: one lag group (H == 1) starting at lag 0
+        if (twin) kern = stats_block2_kernel<8, true, true, 256, 2>;
+        else if (LB == 8) kern = stats_block2_kernel<8, true, true, 512, 1>;
+        else if (first) kern = H == 1 ? stats_block2_kernel<kLagBlock, true, true, 384, 1> : stats_block2_kernel<kLagBlock, true, false, 384, 1>;
+        else kern = stats_block2_kernel<kLagBlock, false, false, 384, 1>;
         MMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, threads, smem, stream>>>(sample, c_local, n, (int)p, lag0, H, G, K, nbuf, partial);
         MMC_CUDA(cudaGetLastError());

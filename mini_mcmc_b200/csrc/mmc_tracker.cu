@@ -171,29 +171,35 @@ __global__ void __launch_bounds__(kWideWarps * 32) tracker_wide_kernel(const Tra
                 last[j] = ok[j] ? p.last[c * dim + d] : 0.0f;
             }
             const InT *src = row + tr * dim + d0 + lane;
-#pragma unroll 2
+            const uint64_t step0 = p.n_before + (uint64_t)tr + 1;   // step count of s = 0
+            const bool small = step0 + 32 < (1ull << 32);            // (always, in practice): 32-bit int -> float conversions
+            const uint32_t step0_lo = (uint32_t)step0;
+            uint32_t ne_bits = 0, ne0_bits = 0;                     // per lane: bit s = this lane's element changed at step s
+#pragma unroll 4
             for (int s = 0; s < ns; ++s) {
-                const uint64_t step = p.n_before + (uint64_t)(tr + s) + 1;
-                const float n = (float)step;
+                const float n = small ? (float)(step0_lo + (uint32_t)s) : (float)(step0 + (uint64_t)s);
                 const StepDiv dv(n);
                 const float nm1 = __fsub_rn(n, 1.0f);
+                const bool first = step0 + (uint64_t)s == 1;
                 float x[NC];
 #pragma unroll
-                for (int j = 0; j < NC; ++j) x[j] = ok[j] ? to_f32(__ldcs(src + (int64_t)s * dim + 32 * j)) : 0.0f;
-                bool ne = false, ne0 = false;
+                for (int j = 0; j < NC; ++j) x[j] = ok[j] ? to_f32(__ldcs(src + 32 * j)) : 0.0f;
+                src += dim;
+                bool ne = false;
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
                     if (ok[j]) {
-                        fold_moments(mean[j], msq[j], x[j], dv, nm1, step == 1);
+                        fold_moments(mean[j], msq[j], x[j], dv, nm1, first);
                         const bool d = x[j] != last[j];
                         ne |= d;
-                        if (j == 0) ne0 = d;
+                        if (j == 0) ne0_bits |= (uint32_t)d << s;
                         last[j] = x[j];
                     }
                 }
-                if (__ballot_sync(0xffffffffu, ne)) changed_mask |= 1u << s;
-                if (d0 == 0 && (__ballot_sync(0xffffffffu, ne0) & 1u)) changed0_mask |= 1u << s;
+                ne_bits |= (uint32_t)ne << s;
             }
+            changed_mask |= __reduce_or_sync(0xffffffffu, ne_bits);
+            if (d0 == 0) changed0_mask |= __shfl_sync(0xffffffffu, ne0_bits, 0);
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 if (ok[j]) {

@@ -60,6 +60,16 @@ def stats(c=65536, n=400, p=100):
     print(json.dumps(dict(k="stats", c=c, n=n, p=p, ms=ms, all=ts, read_GBs=c * n * p * 4 / ms / 1e6)))
 
 
+def stats_slow(c=65536, n=400, p=100):
+    """slowly mixing chains (random walks): the Geyer sum never terminates, so every lag window is computed (C5's case)"""
+    x = torch.randn((c, n, p), device="cuda").cumsum(dim=1)
+    ms, ts = ev_time(lambda: mm.split_rhat_mean_ess(x))
+    print(json.dumps(dict(k="stats_all_lags", c=c, n=n, p=p, ms=ms, all=ts)))
+    x = x[: c // 8].contiguous()
+    ms, ts = ev_time(lambda: mm.split_rhat_mean_ess(x))
+    print(json.dumps(dict(k="stats_all_lags", c=c // 8, n=n, p=p, ms=ms, all=ts)))
+
+
 def tracker():
     """one streaming pass of the progress tracker over a block of draws (HBM read bound)"""
     for name, shape, dt, flavor in (("c2_poisson", (1 << 20, 512, 1), torch.int64, 1), ("c3_hmc", (262144, 400, 3), torch.float32, 0),
@@ -227,6 +237,8 @@ if __name__ == "__main__":
         hmc()
     if "stats" in which:
         stats()
+    if "stats_slow" in which:
+        stats_slow()
     if "dense" in which:
         dense(path=0)
         dense(chains=32768, steps=2, path=0)
