@@ -334,8 +334,15 @@ def main():
         if distributed:
             dist.all_reduce(host_peak)   # the ranks measured concurrently: the sum is what the host sustains
         host_write = full_bytes * world / (dt / e2e_steps) / 1e9
+        # everything the host DRAM moves per step: the u64 result (written), the compact draws DMA-written into the pinned
+        # staging buffers and read back by the widening threads
+        d2h_step = e2e["d2h_bytes_per_step"]
+        host_traffic = (full_bytes + 2 * d2h_step) * world / (dt / e2e_steps) / 1e9
         e2e["roofline"] = {"bound": "host_dram_write", "achieved": host_write, "peak": float(host_peak.item()), "unit": "GB/s",
                            "frac": host_write / max(float(host_peak.item()), 1e-9), "threads_per_rank": nthreads.value,
+                           "dram_traffic": {"achieved": host_traffic, "frac": host_traffic / max(float(host_peak.item()), 1e-9),
+                                            "note": "result written + compact draws written by the copy engine and read by the "
+                                                    "widening threads"},
                            "numa_nodes": len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
                            if os.path.isdir("/sys/devices/system/node") else None,
                            "note": "8 B of u64 result per draw written by the host cores (75.5 GB per GPU and step); "

@@ -185,15 +185,30 @@ __global__ void __launch_bounds__(kWideWarps * 32) tracker_wide_kernel(const Tra
 #pragma unroll
                 for (int j = 0; j < NC; ++j) x[j] = ok[j] ? to_f32(__ldcs(src + 32 * j)) : 0.0f;
                 src += dim;
-                bool ne = false;
+                // the 2 NC numerators of this step (the recurrences of fold_moments); one range test and ONE branch for all
+                float am[NC], aq[NC];
+                bool ne = false, all_in = dv.fast;
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
-                    if (ok[j]) {
-                        fold_moments(mean[j], msq[j], x[j], dv, nm1, first);
-                        const bool d = x[j] != last[j];
-                        ne |= d;
-                        if (j == 0) ne0_bits |= (uint32_t)d << s;
-                        last[j] = x[j];
+                    am[j] = __fadd_rn(__fmul_rn(mean[j], nm1), x[j]);
+                    aq[j] = __fadd_rn(__fmul_rn(msq[j], nm1), __fmul_rn(x[j], x[j]));
+                    if (ok[j]) all_in = all_in && StepDiv::in_range(am[j]) && (first || StepDiv::in_range(aq[j]));
+                    const bool d = ok[j] && x[j] != last[j];
+                    ne |= d;
+                    if (j == 0) ne0_bits |= (uint32_t)d << s;
+                    last[j] = x[j];
+                }
+                if (all_in) {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        mean[j] = dv.quotient_in_range(am[j]);
+                        msq[j] = first ? __fmul_rn(x[j], x[j]) : dv.quotient_in_range(aq[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        mean[j] = __fdiv_rn(am[j], n);
+                        msq[j] = first ? __fmul_rn(x[j], x[j]) : __fdiv_rn(aq[j], n);
                     }
                 }
                 ne_bits |= (uint32_t)ne << s;

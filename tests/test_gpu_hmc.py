@@ -186,3 +186,30 @@ def test_hmc_packed_throughput_kernel_matches_oracle(mm, monkeypatch, D):
     np.testing.assert_array_equal(z.run(2, 0), np.repeat(init[:, None, :], 2, axis=1))
     acc, tot = z.accept_counts()
     assert acc == tot == 2 * chains
+
+
+@pytest.mark.parametrize("D,chains,n_collect", [(3, 1000, 37), (2, 129, 8), (5, 64, 19), (8, 333, 10), (16, 70, 9)])
+def test_pair_kernel_tiled_stores_equal_direct_stores(mm, D, chains, n_collect):
+    """The production HMC kernel stages kT steps of a warp's 64 chains in shared memory and flushes whole row segments
+    (128-bit stores when 16-byte aligned, coalesced 32-bit stores otherwise - the misaligned tensor below); the scalar
+    kernel (exact arithmetic aside, same Philox streams) stores directly.  Same draws on both store paths, including
+    ragged chain counts, run lengths that are not multiples of the tile and continued runs."""
+    import torch
+
+    init = mm.init_with_seed(chains, D, 7, dtype=np.float32) * 0.3
+    a = mm.HMC(mm.RosenbrockND(), init, 0.01, 7).set_seed(11)
+    b = mm.HMC(mm.RosenbrockND(), init, 0.01, 7).set_seed(11)
+    out_a = a.run_device(n_collect, 5)
+    flat = torch.empty(chains * n_collect * D + 1, dtype=torch.float32, device="cuda")
+    out_b = flat[1:].view(chains, n_collect, D)
+    assert out_b.data_ptr() % 16 != 0
+    b.run_device(n_collect, 5, out=out_b)
+    assert torch.equal(out_a, out_b)
+    assert torch.isfinite(out_a).all()
+    out_a2 = a.run_device(n_collect + 3, 0)          # continuation
+    flat2 = torch.empty(chains * (n_collect + 3) * D + 1, dtype=torch.float32, device="cuda")
+    out_b2 = flat2[1:].view(chains, n_collect + 3, D)
+    b.run_device(n_collect + 3, 0, out=out_b2)
+    assert torch.equal(out_a2, out_b2)
+    np.testing.assert_array_equal(a.positions, b.positions)
+    np.testing.assert_array_equal(a.positions, out_a2[:, -1].cpu().numpy())
