@@ -222,7 +222,10 @@ def main():
         # the run stays observable while stdout carries the single JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (a per-process file that is copied to stderr at the end: opening /dev/stderr from inside NCCL loses the lines when
+        # stderr is a redirected regular file)
+        nccl_log = f"/tmp/mmc_bench_nccl_{os.getpid()}.log"
+        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -406,6 +409,11 @@ def main():
     if distributed:
         mm.Communicator.shutdown()
         dist.destroy_process_group()
+        if os.environ.get("NCCL_DEBUG_FILE") == nccl_log and os.path.exists(nccl_log):
+            with open(nccl_log) as f:
+                sys.stderr.write(f.read())
+            sys.stderr.flush()
+            os.remove(nccl_log)
 
 
 if __name__ == "__main__":

@@ -15,9 +15,9 @@ from .hmc import HMC
 from .metropolis_hastings import MetropolisHastings
 from .nuts import NUTS
 from .progress import ChainTrackers, MultiChainTracker
-from .stats import BasicStats, Communicator, RunStats, basic_stats, split_rhat_mean_ess
+from .stats import BasicStats, Communicator, RunStats, basic_stats, rank_normalized_split_rhat, split_rhat_mean_ess
 
 __all__ = ["init", "init_det", "init_with_seed", "init_device", "MetropolisHastings", "HMC", "NUTS", "Gaussian2D",
            "IsotropicGaussian", "PoissonTarget", "NonnegativeProposal", "RosenbrockND", "Rosenbrock2D",
            "DiffableGaussian2D", "DenseGaussian", "CustomTarget", "StandardNormalTarget", "RunStats", "BasicStats", "basic_stats",
-           "split_rhat_mean_ess", "Communicator", "GibbsSampler", "Categorical", "TabulatedTarget", "ReflectingRandomWalk", "CustomProposal", "ConstantConditional", "CustomConditional", "MixtureConditional", "MultiChainTracker", "ChainTrackers", "io"]
+           "split_rhat_mean_ess", "rank_normalized_split_rhat", "Communicator", "GibbsSampler", "Categorical", "TabulatedTarget", "ReflectingRandomWalk", "CustomProposal", "ConstantConditional", "CustomConditional", "MixtureConditional", "MultiChainTracker", "ChainTrackers", "io"]

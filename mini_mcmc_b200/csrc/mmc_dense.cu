@@ -19,16 +19,21 @@ namespace mmc {
 // ---------------------------------------------------------------- begin / accept
 __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *__restrict__ mean, float *__restrict__ delta,
                                    float *__restrict__ mom, float *__restrict__ scal, const float *__restrict__ rp_mom,
-                                   const float *__restrict__ rp_u, int64_t chains, int D, int64_t chain_offset,
+                                   const float *__restrict__ rp_u, int64_t chains, int D, int Dp, int64_t chain_offset,
                                    uint32_t gstep, int64_t local_step, uint2 key) {
-    // one warp per chain
+    // one warp per chain; internal rows have pitch Dp >= D, columns >= D are zero
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= chains) return;
     const uint64_t gchain = (uint64_t)(c + chain_offset);
     float ke = 0.f;
-    for (int j = lane; j < D / 4; j += 32) {
+    for (int j = lane; j < Dp / 4; j += 32) {
         const int i = 4 * j;
+        if (i >= D) {
+            *reinterpret_cast<float4 *>(delta + c * Dp + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(mom + c * Dp + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
         const float4 x = *reinterpret_cast<const float4 *>(pos + c * D + i);
         const float4 m = *reinterpret_cast<const float4 *>(mean + i);
         float4 p;
@@ -39,8 +44,8 @@ __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *_
             box_muller_f32(w.x, w.y, p.x, p.y);
             box_muller_f32(w.z, w.w, p.z, p.w);
         }
-        *reinterpret_cast<float4 *>(delta + c * D + i) = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-        *reinterpret_cast<float4 *>(mom + c * D + i) = p;
+        *reinterpret_cast<float4 *>(delta + c * Dp + i) = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+        *reinterpret_cast<float4 *>(mom + c * Dp + i) = p;
         ke += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
     }
 #pragma unroll
@@ -59,7 +64,7 @@ __global__ void dense_begin_kernel(const float *__restrict__ pos, const float *_
 
 __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__restrict__ mean, const float *__restrict__ delta,
                                     const float *__restrict__ delta_lo, const float *__restrict__ scal, float norm_const, float *__restrict__ out,
-                                    float *__restrict__ trace, unsigned long long *accept_count, int64_t chains, int D,
+                                    float *__restrict__ trace, unsigned long long *accept_count, int64_t chains, int D, int Dp,
                                     int64_t out_pitch, int64_t slot, int64_t local_step) {
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -74,9 +79,9 @@ __global__ void dense_accept_kernel(float *__restrict__ pos, const float *__rest
         const int i = 4 * j;
         float4 x = *reinterpret_cast<const float4 *>(pos + c * D + i);
         if (acc) {
-            float4 d = *reinterpret_cast<const float4 *>(delta + c * D + i);
+            float4 d = *reinterpret_cast<const float4 *>(delta + c * Dp + i);
             if (delta_lo) {  // tensor-core path keeps Delta as an exact hi + lo split
-                const float4 l = *reinterpret_cast<const float4 *>(delta_lo + c * D + i);
+                const float4 l = *reinterpret_cast<const float4 *>(delta_lo + c * Dp + i);
                 d = make_float4(d.x + l.x, d.y + l.y, d.z + l.z, d.w + l.w);
             }
             const float4 m = *reinterpret_cast<const float4 *>(mean + i);
@@ -211,26 +216,34 @@ void dense_tc_destroy(DenseState *st);
 // ---------------------------------------------------------------- host driver
 int dense_create(DenseState **out, const mmc_target_desc *t, int64_t chains) {
     MMC_REQUIRE(t->vec && t->mat, "dense Gaussian target needs mean (vec) and precision (mat)");
-    MMC_REQUIRE(t->dim % 16 == 0 && t->dim >= 16, "dense Gaussian: dim must be a multiple of 16, got %d", t->dim);
+    MMC_REQUIRE(t->dim % 4 == 0 && t->dim >= 4, "dense Gaussian: dim must be a multiple of 4, got %d", t->dim);
     DenseState *st = new DenseState();
     st->D = t->dim;
+    // internal pitch: whole 256-column tiles (tcgen05 path; the FP32 SIMT path needs 128), zero padded; D = 128 stays as it is
+    st->Dp = (t->dim % 256 == 0 || t->dim == 128) ? t->dim : (t->dim + 255) / 256 * 256;
     st->chains = chains;
     st->norm_const = (float)t->params[0];
-    const size_t D = (size_t)t->dim, md = (size_t)chains * D * sizeof(float);
+    const size_t D = (size_t)t->dim, Dp = (size_t)st->Dp, md = (size_t)chains * Dp * sizeof(float);
     auto fail = [&](cudaError_t e) { dense_destroy(st); return cuda_fail(e, "dense_create", __FILE__, __LINE__); };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&st->d_mean, D * 4)) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc((void **)&st->d_prec, D * D * 4)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void **)&st->d_mean, Dp * 4)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void **)&st->d_prec, Dp * Dp * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc((void **)&st->d_delta[0], md)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc((void **)&st->d_delta[1], md)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc((void **)&st->d_mom, md)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc((void **)&st->d_scal, 6 * (size_t)chains * 4)) != cudaSuccess) return fail(e);
-    if ((e = cudaMemcpy(st->d_mean, t->vec, D * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+    // both Delta buffers start at zero: the epilogue only ever writes 0 into the padding columns, but it reads them first
+    if ((e = cudaMemset(st->d_delta[0], 0, md)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemset(st->d_delta[1], 0, md)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemset(st->d_mom, 0, md)) != cudaSuccess) return fail(e);
+    std::vector<float> mean(Dp, 0.0f);
+    for (size_t i = 0; i < D; ++i) mean[i] = t->vec[i];
+    if ((e = cudaMemcpy(st->d_mean, mean.data(), Dp * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
     // symmetrise on the host (grad = -Z assumes P = P^T; also lets the tensor path use P as its own transpose)
-    std::vector<float> P(D * D);
+    std::vector<float> P(Dp * Dp, 0.0f);
     for (size_t i = 0; i < D; ++i)
-        for (size_t j = 0; j < D; ++j) P[i * D + j] = 0.5f * (t->mat[i * D + j] + t->mat[j * D + i]);
-    if ((e = cudaMemcpy(st->d_prec, P.data(), D * D * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+        for (size_t j = 0; j < D; ++j) P[i * Dp + j] = 0.5f * (t->mat[i * D + j] + t->mat[j * D + i]);
+    if ((e = cudaMemcpy(st->d_prec, P.data(), Dp * Dp * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
     *out = st;
     return MMC_OK;
 }
@@ -253,13 +266,13 @@ void dense_destroy(DenseState *st) {
 int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
     MMC_REQUIRE(a.n_leapfrog >= 1, "dense Gaussian HMC needs n_leapfrog >= 1");
     MMC_REQUIRE(a.chains == st->chains, "chain count changed");
-    const int D = st->D;
+    const int D = st->D, Dp = st->Dp;
     const int64_t M = a.chains;
     const int64_t steps = a.n_collect + a.n_discard;
     const uint2 key = seed_key(a.seed);
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
-    const dim3 ggrid((unsigned)(D / kBN), (unsigned)((M + kBM - 1) / kBM));
-    MMC_REQUIRE(D % kBN == 0 || a.gemm_path >= 1, "FP32 GEMM path needs dim %% 128 == 0, got %d", D);
+    const dim3 ggrid((unsigned)(Dp / kBN), (unsigned)((M + kBM - 1) / kBM));
+    MMC_REQUIRE(Dp % 256 == 0 || a.gemm_path == 0, "tcgen05 GEMM paths need whole 256-column tiles (dim 128 runs on the FP32 path), got %d", D);
     if (a.gemm_path >= 1) {
         int rc = dense_tc_prepare(st);
         if (rc) return rc;
@@ -267,7 +280,7 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
     }
     for (int64_t s = 0; s < steps; ++s) {
         dense_begin_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, st->d_delta[0], st->d_mom, st->d_scal,
-                                                      a.momenta, a.u, M, D, a.chain_offset, (uint32_t)(a.step_base + s), s, key);
+                                                      a.momenta, a.u, M, D, Dp, a.chain_offset, (uint32_t)(a.step_base + s), s, key);
         if (a.gemm_path >= 1) {
             int rc = dense_tc_split_delta(st, stream);
             if (rc) return rc;
@@ -276,19 +289,19 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
         for (int l = 0; l <= a.n_leapfrog; ++l) {
             const int mode = l == 0 ? kModeFirst : (l == a.n_leapfrog ? kModeLast : kModeMid);
             if (a.gemm_path >= 1) {
-                int rc = dense_gemm_tc(st, cur, M, D, a.eps, mode, stream);
+                int rc = dense_gemm_tc(st, cur, M, Dp, a.eps, mode, stream);
                 if (rc) return rc;
             } else {
                 dense_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(st->d_delta[cur], st->d_prec, st->d_mom,
-                                                                  st->d_delta[cur ^ 1], st->d_scal, M, D, a.eps, mode);
+                                                                  st->d_delta[cur ^ 1], st->d_scal, M, Dp, a.eps, mode);
             }
             if (mode != kModeLast) cur ^= 1;
         }
         const bool collect = s >= a.n_discard && a.out;
         const float *fin = a.gemm_path >= 1 ? st->d_delta_split[cur] : st->d_delta[cur];
-        const float *fin_lo = a.gemm_path >= 1 ? st->d_delta_split[cur] + (size_t)M * D : nullptr;
+        const float *fin_lo = a.gemm_path >= 1 ? st->d_delta_split[cur] + (size_t)M * Dp : nullptr;
         dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, fin, fin_lo, st->d_scal, st->norm_const,
-                                                       collect ? a.out : nullptr, a.trace, a.accept_count, M, D, a.out_pitch,
+                                                       collect ? a.out : nullptr, a.trace, a.accept_count, M, D, Dp, a.out_pitch,
                                                        collect ? s - a.n_discard : 0, s);
     }
     MMC_CUDA(cudaGetLastError());

@@ -10,7 +10,9 @@ namespace mmc {
 
 // device buffers of the dense-Gaussian HMC path
 struct DenseState {
-    int D = 0;
+    int D = 0;                    // the target's dimension (positions, draws, replay tapes)
+    int Dp = 0;                   // internal row pitch: D rounded up to the 256-column tile (zero padding: the extra columns
+                                  // of Delta, the momenta and the precision stay exactly 0 through the trajectory)
     int64_t chains = 0;
     float norm_const = 0.f;
     float *d_mean = nullptr;      // [D]

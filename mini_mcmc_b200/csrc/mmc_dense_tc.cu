@@ -586,7 +586,7 @@ int encode_2d(EncodeTiledFn fn, CUtensorMap *map, float *base, uint64_t rows, ui
 
 int dense_tc_prepare(DenseState *st) {
     if (st->tc) return MMC_OK;
-    const int D = st->D;
+    const int D = st->Dp;   // internal pitch (whole tiles)
     const int64_t M = st->chains;
     MMC_REQUIRE(D % tc::BN == 0, "tcgen05 path needs dim %% 256 == 0, got %d", D);
     void *fn = nullptr;
@@ -620,9 +620,9 @@ int dense_tc_prepare(DenseState *st) {
 
 // splits the full-precision Delta written by dense_begin_kernel into buffer 0 of the hi/lo ping-pong
 int dense_tc_split_delta(DenseState *st, cudaStream_t stream) {
-    const int64_t n4 = st->chains * st->D / 4;
+    const int64_t n4 = st->chains * st->Dp / 4;
     float *hi = st->d_delta_split[0];
-    tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(st->d_delta[0], hi, hi + (size_t)st->chains * st->D, n4);
+    tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(st->d_delta[0], hi, hi + (size_t)st->chains * st->Dp, n4);
     MMC_CUDA(cudaGetLastError());
     return MMC_OK;
 }

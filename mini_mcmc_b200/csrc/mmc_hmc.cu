@@ -252,7 +252,9 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
         a.seed = h->seed;
         // the dense contraction goes through the tensor cores by default (north_star); exact runs and dimensions the
         // 128 x 256 tcgen05 tiles do not divide use the FP32 SIMT tiles
-        a.gemm_path = h->exact ? 0 : (h->gemm_path >= 0 ? h->gemm_path : (h->dim % 256 == 0 ? 2 : 0));
+        // auto: tcgen05 CTA pairs (any dim: the rows are zero padded to whole 256-column tiles); dim 128 and the reference
+        // arithmetic run on the FP32 SIMT tiles
+        a.gemm_path = (h->exact || h->dim == 128) ? 0 : (h->gemm_path >= 0 ? h->gemm_path : 2);
         int rc = dense_run(h->dense, a, (cudaStream_t)stream);
         if (rc) return rc;
         h->step += n_collect + n_discard;

@@ -116,6 +116,61 @@ def split_rhat_mean_ess(sample, group=None, comm=None):
     return rhat, ess
 
 
+def _rank_z(x):
+    """Rank-normalisation of Vehtari et al. (2021, eq. 14): pooled average ranks r of the draws of one parameter (ties share
+    their mean rank) -> z = Phi^-1((r - 3/8) / (S + 1/4)).  x: CUDA tensor [c, n, p]; the ranks pool all c n draws per
+    parameter.  Sorting is torch's device radix sort (library code, like the Arrow encoders of the sinks)."""
+    import torch
+
+    c, n, p = x.shape
+    S = c * n
+    flat = x.reshape(S, p).t().contiguous()                     # [p, S]
+    vals, order = torch.sort(flat, dim=1, stable=True)
+    pos = torch.arange(1, S + 1, device=x.device, dtype=torch.float64).expand(p, S)
+    # tie groups: first / last position of each run of equal values
+    new_run = torch.ones((p, S), dtype=torch.bool, device=x.device)
+    new_run[:, 1:] = vals[:, 1:] != vals[:, :-1]
+    first = torch.where(new_run, pos, torch.zeros_like(pos)).cummax(dim=1).values
+    end_run = torch.ones((p, S), dtype=torch.bool, device=x.device)
+    end_run[:, :-1] = new_run[:, 1:]
+    last = torch.where(end_run, pos, torch.full_like(pos, float(S + 1))).flip(1).cummin(dim=1).values.flip(1)
+    avg_rank = 0.5 * (first + last)
+    ranks = torch.empty_like(avg_rank)
+    ranks.scatter_(1, order, avg_rank)
+    u = (ranks - 0.375) / (S + 0.25)
+    z = torch.special.ndtri(u)
+    return z.t().reshape(c, n, p).to(torch.float32).contiguous()
+
+
+def rank_normalized_split_rhat(sample, group=None):
+    """Rank-normalised split-Rhat (the reference's roadmap item, README.md:393; Vehtari, Gelman, Simpson, Carpenter and
+    Buerkner 2021): the draws of every parameter are replaced by the normal scores of their pooled ranks and split-Rhat is
+    computed on them (bulk), and again on the normal scores of the folded draws |x - median| (tail); returns
+    (bulk[p], folded[p]) in the TEXTBOOK form sqrt(var+ / W) >= ~1 with the unbiased within-chain variance W (what
+    split_rhat_mean_ess returns is the reference's sqrt(W_biased / var+), src/stats.rs:425-427; converted below).  Only the draws the split uses (the first and
+    the last n // 2 of every chain) are ranked.  Single process (the ranks pool every chain)."""
+    import torch
+
+    x = _as_device_f32(sample)
+    c, n, p = x.shape
+    N = n // 2
+    halves = torch.cat([x[:, :N], x[:, n - N:]], dim=1)          # [c, 2 N, p]: what splitcat keeps (src/stats.rs:396-402)
+    out = []
+    for folded in (False, True):
+        y = halves
+        if folded:
+            med = halves.reshape(-1, p).median(dim=0).values
+            y = (halves - med).abs()
+        z = _rank_z(y)
+        rhat, _ = split_rhat_mean_ess(z, group=False)
+        # the kernel returns the reference's sqrt(W_b / var+) with W_b the mean BIASED within-chain variance
+        # (src/stats.rs:425-427, 495-516); the textbook value with the unbiased W = W_b N / (N - 1) is
+        # sqrt(var+ / W) = sqrt((N - 1) / N (1 / rhat_ref^2 + 1 / N))
+        r2 = 1.0 / np.square(rhat.astype(np.float64))
+        out.append(np.sqrt((N - 1.0) / N * (r2 + 1.0 / N)).astype(np.float32))
+    return out[0], out[1]
+
+
 def sharded_split_rhat_ess(partial_fn, c_local, n, p, group, device):
     """The lag-window protocol of mmc_split_rhat_ess_sharded restated over torch.distributed, so that the N > 1 logic is
     testable with the gloo backend on CPU ranks (tests/test_multirank_gloo.py); the GPU path is the library call.

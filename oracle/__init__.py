@@ -673,3 +673,33 @@ def mh_tabulated_run_philox(logp, state, n_collect, n_discard, seed, reflect=Tru
                                       _p(state, C.c_uint64), C.c_int64(chains), C.c_int64(chain_offset), C.c_int64(step_base),
                                       C.c_int64(n_collect), C.c_int64(n_discard), C.c_uint64(seed), _p(out, C.c_uint64))
     return out, state
+
+
+def rank_normalized_split_rhat(sample):
+    """Rank-normalised split-Rhat (README.md:393 roadmap; Vehtari et al. 2021, eqs. 14-15) in plain numpy / scipy, f64:
+    pooled average ranks -> normal scores -> split-Rhat sqrt(var+ / W) of the scores (bulk) and of the scores of the
+    folded draws |x - median| (lower median).  Returns (bulk[p], folded[p])."""
+    from scipy.special import ndtri
+    from scipy.stats import rankdata
+
+    x = np.asarray(sample, dtype=np.float64)
+    c, n, p = x.shape
+    N = n // 2
+    halves = np.concatenate([x[:, :N], x[:, n - N:]], axis=1)      # [c, 2N, p]
+
+    def rhat_of(y):
+        S = y.shape[0] * y.shape[1]
+        z = np.empty_like(y)
+        for q in range(p):
+            r = rankdata(y[:, :, q].reshape(-1), method="average")
+            z[:, :, q] = ndtri((r - 0.375) / (S + 0.25)).reshape(y.shape[0], y.shape[1])
+        split = np.concatenate([z[:, :N], z[:, N:]], axis=0)        # [2c, N, p]
+        m = split.mean(axis=1)
+        W = split.var(axis=1, ddof=1).mean(axis=0)
+        B = N * m.var(axis=0, ddof=1)
+        var_plus = (N - 1) / N * W + B / N
+        return np.sqrt(var_plus / W)
+
+    flat = np.sort(halves.reshape(-1, p), axis=0)
+    med = flat[(flat.shape[0] - 1) // 2]
+    return rhat_of(halves), rhat_of(np.abs(halves - med))

@@ -24,14 +24,14 @@ def make_problem(D, seed=42):
 
 
 def tc_supported(D):
-    return D % 256 == 0   # tcgen05 tile is 128 x 256
+    return D != 128   # tcgen05 tiles are 256 columns wide: other dims are zero padded inside the library, 128 runs on FP32 tiles
 
 
 @pytest.mark.parametrize("path", [0, 1, 2])
-@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3)])
+@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
     if path >= 1 and not tc_supported(D):
-        pytest.skip("tcgen05 path needs dim % 256 == 0")
+        pytest.skip("dim 128 runs on the FP32 tiles")
     mean, cov = make_problem(D)
     tgt = mm.DenseGaussian(mean, cov)
     otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
@@ -100,3 +100,21 @@ def test_dense_hmc_native_tape_and_moments(mm, path, D):
     assert np.abs(flat.var(axis=0) / np.diag(cov) - 1.0).max() < 0.15
     acc, tot = h.accept_counts()
     assert acc / tot > 0.6
+
+
+def test_dense_padded_dims_default_path_and_native_run(mm):
+    """dim % 256 != 0: the library pads its internal rows with zeros to whole 256-column tiles and still takes the tensor-core
+    path by default; draws have the caller's dim, native runs keep the marginal moments, shards reproduce the run."""
+    D, chains = 384, 512
+    mean, cov = make_problem(D, seed=3)
+    tgt = mm.DenseGaussian(mean, cov)
+    rng = np.random.default_rng(0)
+    init = (rng.normal(size=(chains, D)) + mean).astype(np.float32)
+    h = mm.HMC(tgt, init, 0.15, 8).set_seed(4)
+    s = h.run(60, 60)
+    assert s.shape == (chains, 60, D) and np.isfinite(s).all()
+    flat = s.reshape(-1, D).astype(np.float64)
+    assert np.abs(flat.mean(axis=0) - mean).max() < 0.2
+    np.testing.assert_allclose(flat.std(axis=0), np.sqrt(np.diag(cov)), rtol=0.1)
+    part = mm.HMC(tgt, init[200:], 0.15, 8).set_seed(4).set_chain_offset(200).run(60, 60)
+    np.testing.assert_array_equal(part, s[200:])

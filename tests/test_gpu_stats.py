@@ -125,3 +125,28 @@ def test_library_communicator_single_rank(mm):
     exp_rhat, exp_ess = oracle.split_rhat_mean_ess(x)
     np.testing.assert_allclose(rhat, exp_rhat, rtol=1e-4)
     np.testing.assert_allclose(ess, exp_ess, rtol=2e-3)
+
+
+def test_rank_normalized_split_rhat(mm):
+    """README.md:393 roadmap item: rank-normalised (bulk) and folded split-Rhat against a numpy / scipy restatement, on
+    well-mixed chains, on chains with a shifted member, on heavy tails with infinite variance (where the classic Rhat is
+    blind) and on a Metropolis-style sample full of repeated values (ties share their mean rank)."""
+    rng = np.random.default_rng(2)
+    c, n, p = 8, 300, 6
+    good = _ar1(rng, c, n, p, 0.5, 1.0)
+    shifted = good.copy()
+    shifted[2] += 1.5
+    cauchy = rng.standard_cauchy(size=(c, n, p)).astype(np.float32)
+    cauchy[0] *= 6.0                                                 # one chain with a different scale: only the folded Rhat sees it
+    sticky = np.repeat(np.round(rng.normal(size=(c, n // 4 + 1, p)) * 2), 4, axis=1)[:, :n].astype(np.float32)
+    for x in (good, shifted, cauchy, sticky, good[:, :299]):
+        bulk, folded = mm.rank_normalized_split_rhat(x)
+        eb, ef = oracle.rank_normalized_split_rhat(x)
+        # the device pipeline is the reference-convention f32 split-Rhat of csrc/mmc_stats.cu applied to f32 normal scores
+        np.testing.assert_allclose(bulk, eb, rtol=2e-4)
+        np.testing.assert_allclose(folded, ef, rtol=2e-4)
+    bulk, folded = mm.rank_normalized_split_rhat(good)
+    assert bulk.max() < 1.02 and folded.max() < 1.02
+    assert mm.rank_normalized_split_rhat(shifted)[0].min() > 1.05
+    b, f = mm.rank_normalized_split_rhat(cauchy)
+    assert b.max() < 1.05 and f.min() > 1.05
