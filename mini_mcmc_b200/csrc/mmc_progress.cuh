@@ -4,6 +4,7 @@
 // the final [chains, n_collect, dim] tensor in HBM, the device tracker (mmc_tracker.cu) folds each block, and the
 // caller's callback receives p(accept) / max(rhat) once per block.  RunStats comes from the device split-Rhat / ESS.
 #pragma once
+#include <limits>
 
 #include <algorithm>
 #include <vector>
@@ -31,6 +32,11 @@ __global__ void progress_cast_kernel(const InT *__restrict__ src, float *__restr
 template <class RunBlock, class Discard>
 int run_progress_blocks(const ProgressSpec &sp, int64_t n_collect, int64_t n_discard, void *out_host, int64_t block,
                         mmc_progress_fn cb, void *user, mmc_run_stats *stats, cudaStream_t stream, RunBlock run_block, Discard discard) {
+    if (stats) {   // RunStats is always returned; undefined entries (fewer than two collected draws) are NaN like the reference's
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        stats->ess = mmc_basic_stats{nan, nan, nan, nan, nan};
+        stats->rhat = mmc_basic_stats{nan, nan, nan, nan, nan};
+    }
     const size_t esize = sp.dtype == MMC_F32 ? 4 : 8;
     const int64_t total = n_collect + n_discard;
     const int64_t tracked_total = sp.track_burn_in ? total : n_collect;

@@ -80,9 +80,12 @@ def _to_device(data):
     return t.to("cuda").contiguous()
 
 
-def record_batches(data, rows_per_batch: int = 1 << 22, tensor_layout: bool = False):
+def record_batches(data, rows_per_batch: int = 1 << 22, tensor_layout: bool = False, zero_copy: bool = False):
     """Yields pyarrow RecordBatches of the long-format table.  tensor_layout=True is save_parquet_tensor's
-    convention: data is [observations, chains, dims] and the columns start with observation, chain."""
+    convention: data is [observations, chains, dims] and the columns start with observation, chain.
+    zero_copy=True wraps the two reused pinned staging buffers directly: a batch is then only valid until the generator
+    is resumed twice (the writers below consume each batch before asking for the next); the default copies the columns,
+    so batches may be collected (list(record_batches(x)), pa.Table.from_batches)."""
     import pyarrow as pa
     import torch
 
@@ -125,7 +128,8 @@ def record_batches(data, rows_per_batch: int = 1 << 22, tensor_layout: bool = Fa
         host = pin[i & 1].numpy()
         idx_o = np.repeat(np.arange(o0, o0 + cnt, dtype=np.uint32), inner)
         idx_i = np.tile(np.arange(inner, dtype=np.uint32), cnt)
-        cols = [pa.array(idx_o), pa.array(idx_i)] + [pa.array(host[k * rows:(k + 1) * rows]) for k in range(d)]
+        cols = [pa.array(idx_o), pa.array(idx_i)] + \
+               [pa.array(host[k * rows:(k + 1) * rows] if zero_copy else host[k * rows:(k + 1) * rows].copy()) for k in range(d)]
         yield pa.RecordBatch.from_arrays(cols, schema=schema)
 
 
@@ -133,7 +137,7 @@ def save_arrow(data, filename: str, rows_per_batch: int = 1 << 22) -> None:
     """save_arrow(&Array3<T>, filename), src/io/arrow.rs:53-117: Arrow IPC file."""
     import pyarrow as pa
 
-    it = record_batches(data, rows_per_batch)
+    it = record_batches(data, rows_per_batch, zero_copy=True)
     first = next(it)
     with pa.OSFile(filename, "wb") as sink, pa.ipc.new_file(sink, first.schema) as w:
         w.write_batch(first)
@@ -144,7 +148,7 @@ def save_arrow(data, filename: str, rows_per_batch: int = 1 << 22) -> None:
 def _save_parquet(data, filename, rows_per_batch, tensor_layout):
     import pyarrow.parquet as pq
 
-    it = record_batches(data, rows_per_batch, tensor_layout=tensor_layout)
+    it = record_batches(data, rows_per_batch, tensor_layout=tensor_layout, zero_copy=True)
     first = next(it)
     with pq.ParquetWriter(filename, first.schema) as w:
         w.write_batch(first)
