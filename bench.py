@@ -220,12 +220,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's INFO log (communicator set-up: "comm ... rank r nranks N", NVLS / ring choices) goes to STDERR so that
         # the run stays observable while stdout carries the single JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (assigned, not setdefault: an inherited NCCL_DEBUG=WARN would silence the set-up lines)
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
         # (a per-process file that is copied to stderr at the end: opening /dev/stderr from inside NCCL loses the lines when
         # stderr is a redirected regular file)
         nccl_log = f"/tmp/mmc_bench_nccl_{os.getpid()}.log"
-        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
