@@ -68,6 +68,28 @@ inline std::pair<std::vector<float>, std::vector<float>> split_rhat_mean_ess(con
     return {rhat, ess};
 }
 
+// The same over chains that live on several GPUs (one process per GPU): rank 0 obtains the 128-byte id, every rank
+// creates the communicator on its own device and calls split_rhat_mean_ess with its local chains in DEVICE memory.
+class Communicator {
+  public:
+    static std::vector<unsigned char> unique_id() {
+        std::vector<unsigned char> id(128);
+        check(mmc_comm_unique_id(id.data()));
+        return id;
+    }
+    Communicator(const std::vector<unsigned char> &id, int nranks, int rank) { check(mmc_comm_create(&c_, id.data(), nranks, rank)); }
+    ~Communicator() { mmc_comm_destroy(c_); }
+    Communicator(const Communicator &) = delete;
+    std::pair<std::vector<float>, std::vector<float>> split_rhat_mean_ess(const float *sample_dev, int64_t c_local, int64_t n, int64_t p,
+                                                                          void *stream = nullptr) {
+        std::vector<float> rhat((size_t)p), ess((size_t)p);
+        check(mmc_split_rhat_ess_sharded(sample_dev, c_local, n, p, c_, stream, rhat.data(), ess.data()));
+        return {rhat, ess};
+    }
+  private:
+    mmc_comm *c_ = nullptr;
+};
+
 // io::csv::save_csv, src/io/csv.rs:47-77
 template <class T>
 inline void save_csv(const Sample<T> &s, const std::string &filename) {
@@ -100,7 +122,18 @@ class MetropolisHastings {
   public:
     MetropolisHastings(const mmc_target_desc &t, const mmc_proposal_desc &q, const std::vector<S> &init, int64_t chains, int dim)
         : chains_(chains), dim_(dim) {
-        check(mmc_mh_create(&h_, &t, &q, init.data(), chains, dim, sizeof(S) == 8 && std::is_integral<S>::value ? MMC_U64 : MMC_F64));
+        // state type S: f64, f32 (MetropolisHastings<f32, f32, ..>, src/metropolis_hastings.rs:87) or u64 (`usize`)
+        static_assert(std::is_same<S, double>::value || std::is_same<S, float>::value || (std::is_integral<S>::value && sizeof(S) == 8),
+                      "MetropolisHastings state is f64, f32 or u64");
+        check(mmc_mh_create(&h_, &t, &q, init.data(), chains, dim,
+                            std::is_integral<S>::value ? MMC_U64 : (std::is_same<S, float>::value ? MMC_F32 : MMC_F64)));
+    }
+    // Any integer-state target tabulated on [0, logp.size()) with the nonnegative or the reflecting +-1 walk: the `i32`
+    // PoissonDist / BinomialDist variants of tests/metrohast_poisson_test.rs:18-85,157-214 (mmc_mh_create_tabulated)
+    MetropolisHastings(const std::vector<double> &logp, int proposal_kind, const std::vector<S> &init)
+        : chains_((int64_t)init.size()), dim_(1) {
+        static_assert(std::is_integral<S>::value && sizeof(S) == 8, "tabulated targets have a u64 state");
+        check(mmc_mh_create_tabulated(&h_, logp.data(), (int32_t)logp.size(), proposal_kind, init.data(), chains_));
     }
     // MetropolisHastings::new(Categorical::new(probs), NonnegativeProposal, init), src/distributions.rs:422-477
     MetropolisHastings(const std::vector<double> &probs, const std::vector<S> &init) : chains_((int64_t)init.size()), dim_(1) {

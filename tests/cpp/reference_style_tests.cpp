@@ -184,6 +184,46 @@ static void test_errors() {
     EXPECT(threw, "start outside the support must be rejected");
 }
 
+// tests/metrohast_poisson_test.rs:157-249: Binomial(10, 0.3) through the +-1 walk clamped to [0, 10], i32 state there
+static double ln_factorial(int k) {
+    if (k < 2) return 0.0;
+    double acc = 0.0;
+    for (int i = 1; i <= k; ++i) acc += std::log((double)i);
+    return acc;
+}
+static void test_binomial_mh() {
+    const int n = 10;
+    const double p = 0.3;
+    std::vector<double> logp;
+    for (int k = 0; k <= n; ++k)
+        logp.push_back((ln_factorial(n) - ln_factorial(k) - ln_factorial(n - k)) + (double)k * std::log(p) + ((double)n - (double)k) * std::log(1.0 - p));
+    std::vector<uint64_t> init(32, 5);   // start from the middle
+    mmc::MetropolisHastings<uint64_t> mh(logp, MMC_Q_REFLECT_RW, init);
+    auto s = mh.seed(42).run(20000, 2000);
+    std::vector<double> freq(n + 1, 0.0);
+    for (uint64_t k : s.data) {
+        EXPECT(k <= (uint64_t)n, "state %llu outside the support", (unsigned long long)k);
+        if (k <= (uint64_t)n) freq[k] += 1.0 / (double)s.data.size();
+    }
+    for (int k = 0; k <= n; ++k) {
+        double nck = 1.0;
+        for (int i = 1; i <= k; ++i) nck = nck * (double)(n - k + i) / (double)i;
+        const double pmf = nck * std::pow(p, k) * std::pow(1.0 - p, n - k);
+        EXPECT(std::fabs(freq[k] - pmf) < 0.05, "k = %d: frequency %g, pmf %g", k, freq[k], pmf);
+    }
+}
+
+// MetropolisHastings<f32, f32, ..> (src/metropolis_hastings.rs:87): the Gaussian2D moments of :338-401 on f32 state
+static void test_mh_f32_state() {
+    std::vector<float> init(64 * 2, 0.0f);
+    mmc::MetropolisHastings<float> mh(mmc::target(MMC_T_GAUSSIAN2D, 2, {0.0, 1.0, 4.0, 2.0, 2.0, 3.0}), mmc::isotropic_gaussian(1.0), init, 64, 2);
+    auto s = mh.seed(42).run(2000, 500);
+    double m0 = 0, m1 = 0;
+    const double cnt = (double)(s.data.size() / 2);
+    for (size_t i = 0; i < s.data.size(); i += 2) { m0 += s.data[i]; m1 += s.data[i + 1]; }
+    EXPECT(std::fabs(m0 / cnt - 0.0) < 0.3 && std::fabs(m1 / cnt - 1.0) < 0.3, "mean (%g, %g)", m0 / cnt, m1 / cnt);
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && std::string(argv[1]) == "--host-only") {   // CPU boxes: only the pieces that need no device
         test_save_csv();
@@ -197,6 +237,8 @@ int main(int argc, char **argv) {
         {"test_mh_gaussian2d_moments", test_mh_gaussian2d_moments},
         {"test_mh_poisson_mean_and_variance", test_mh_poisson_mean_and_variance},
         {"test_mh_categorical_frequencies", test_mh_categorical_frequencies},
+        {"test_binomial_mh", test_binomial_mh},
+        {"test_mh_f32_state", test_mh_f32_state},
         {"test_hmc_shapes_and_run_progress", test_hmc_shapes_and_run_progress},
         {"test_nuts_run_and_run_progress", test_nuts_run_and_run_progress},
         {"test_split_rhat_mean_ess_iid", test_split_rhat_mean_ess_iid},
