@@ -190,7 +190,9 @@ int mmc_hmc_set_chain_offset(mmc_hmc *h, int64_t offset);
 int mmc_hmc_set_exact(mmc_hmc *h, int32_t exact);
 /* dense Gaussian target only: gradient GEMM on 0 = FP32 SIMT tiles, 1 = tcgen05 tensor cores (3xTF32 split, fp32
  * accumulation in TMEM, one CTA per 128 x 256 tile), 2 = the same on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles,
- * each SM stages half of the B tile).  Paths 1 and 2 give identical results.  exact = 1 always selects the FP32 path. */
+ * each SM stages half of the B tile), 3 = CTA pairs with the mixed split: TF32 hi.hi plus ONE K-concatenated BF16 MMA for
+ * the two cross terms hi.lo + lo.hi (two thirds of the tensor work of the 3xTF32 split, same operand bytes).  Paths 1 and 2
+ * give identical results.  exact = 1 always selects the FP32 path. */
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path);
 int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps); /* see mmc_mh_set_out_pitch */
 int mmc_hmc_step(mmc_hmc *h);

@@ -260,6 +260,9 @@ void dense_destroy(DenseState *st) {
     cudaFree(st->d_prec_split);
     cudaFree(st->d_delta_split[0]);
     cudaFree(st->d_delta_split[1]);
+    cudaFree(st->d_prec_x);
+    cudaFree(st->d_delta_x[0]);
+    cudaFree(st->d_delta_x[1]);
     delete st;
 }
 
@@ -276,7 +279,8 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
     if (a.gemm_path >= 1) {
         int rc = dense_tc_prepare(st);
         if (rc) return rc;
-        st->tc_pair = a.gemm_path == 2;
+        st->tc_pair = a.gemm_path >= 2;
+        st->tc_mixed = a.gemm_path == 3;
     }
     for (int64_t s = 0; s < steps; ++s) {
         dense_begin_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, st->d_delta[0], st->d_mom, st->d_scal,
@@ -298,8 +302,9 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
             if (mode != kModeLast) cur ^= 1;
         }
         const bool collect = s >= a.n_discard && a.out;
-        const float *fin = a.gemm_path >= 1 ? st->d_delta_split[cur] : st->d_delta[cur];
-        const float *fin_lo = a.gemm_path >= 1 ? st->d_delta_split[cur] + (size_t)M * Dp : nullptr;
+        const bool split = a.gemm_path == 1 || a.gemm_path == 2;   // 3xTF32 paths keep Delta as hi + lo; the others in full
+        const float *fin = split ? st->d_delta_split[cur] : st->d_delta[cur];
+        const float *fin_lo = split ? st->d_delta_split[cur] + (size_t)M * Dp : nullptr;
         dense_accept_kernel<<<wgrid, 256, 0, stream>>>(a.positions, st->d_mean, fin, fin_lo, st->d_scal, st->norm_const,
                                                        collect ? a.out : nullptr, a.trace, a.accept_count, M, D, Dp, a.out_pitch,
                                                        collect ? s - a.n_discard : 0, s);

@@ -25,6 +25,12 @@ struct DenseState {
     float *d_delta_split[2] = {nullptr, nullptr};   // ping-pong of [2 (hi, lo), chains, D]
     void *tc = nullptr;                             // tensor maps
     bool tc_pair = false;                           // CTA-pair (cta_group::2) kernel instead of the 1-CTA one
+    // mixed split (gemm_path 3): TF32 hi.hi + one K-concatenated BF16 MMA for hi.lo + lo.hi; the full-precision Delta
+    // stays in d_delta[], the TF32 operand in the hi half of d_delta_split[], the bf16 cross-term operand here
+    uint32_t *d_prec_x = nullptr;                   // [D, 2 D] bf16: per 32-column k-block 32 x lo then 32 x hi
+    uint32_t *d_delta_x[2] = {nullptr, nullptr};    // [chains, 2 D] bf16: per k-block 32 x hi then 32 x lo
+    bool tc_mixed = false;
+    bool tc_hw_trunc = false;                       // MMC_TC_HW_TRUNC=1 experiment (mmc_dense_tc.cu)
 };
 
 enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };
@@ -41,7 +47,7 @@ struct DenseRunArgs {
     float eps;
     int n_leapfrog;
     uint64_t seed;
-    int gemm_path;           // 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tensor-core tiles
+    int gemm_path;           // 0 = FP32 SIMT tiles, 1 / 2 = tcgen05 3xTF32 (1 CTA / CTA pairs), 3 = CTA pairs, TF32 + BF16 mixed split
 };
 
 int dense_create(DenseState **st, const mmc_target_desc *target, int64_t chains);

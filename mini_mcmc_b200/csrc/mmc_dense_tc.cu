@@ -13,8 +13,17 @@
 // stage (TMA -> MMA -> tcgen05.commit) and tmem_full/tmem_empty per accumulator (MMA <-> epilogue); the
 // accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of one tile overlaps the main loop
 // of the next.
+//
+// Mixed split (gemm_path 3, the default; CTA-pair kernel only): the two cross terms hi.lo + lo.hi only need ~9 bits of
+// each factor (lo is already < 2^-10 of its operand), so they run as ONE K-concatenated kind::f16 MMA on bf16 copies,
+// [bf16(a_hi) | bf16(a_lo)] . [bf16(b_lo) | bf16(b_hi)]^T, at twice the TF32 rate: 1 TF32 + 2 BF16 MMAs of cost 1 + 2 x 1/2
+// = 2 TF32-equivalents per product instead of 3.  Operand bytes are unchanged (hi fp32 + one bf16 pair per element), the
+// full-precision Delta lives in the FP32 path's ping-pong buffers and is what the epilogue reads and advances.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "mmc_dense.cuh"
@@ -44,6 +53,8 @@ constexpr uint32_t kTmemCols = 512;          // two 256-column fp32 accumulators
 struct Maps {
     CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
     CUtensorMap b_hi_half, b_lo_half;   // 128-row boxes for the CTA-pair kernel
+    CUtensorMap a_x[2], b_x_half;       // mixed split: bf16 [rows, 2 D] cross-term operands, boxes of 64 x 128
+    CUtensorMap a_full[2];              // MMC_TC_HW_TRUNC experiment: the full-precision Delta as the TF32 operand
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -366,13 +377,40 @@ __device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t 
 __host__ __device__ constexpr uint32_t make_idesc_pair() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 }
+// kind::f16 with BF16 operands (format 1), F32 accumulator; UMMA_K = 16 elements = the same 32 bytes per K step
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_pair_bf16() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_addr, float hi_addr) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo_addr, hi_addr);   // .x (low half) = element at the lower address
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+__device__ __forceinline__ void stg256u(uint32_t *p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 
+// kMixed: map_a_lo / map_b_lo are the bf16 cross-term operands ([rows, 2 D], 64-element boxes), a_hi = the full-precision
+// Delta (read by the epilogue), a_lo unused, n_hi = next TF32 hi (nullptr: not stored, MMC_TC_HW_TRUNC), n_lo = next
+// full-precision Delta, n_x = next bf16 cross-term operand
+template <bool kMixed>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                           const float *__restrict__ a_hi, const float *__restrict__ a_lo, float *__restrict__ n_hi,
-                          float *__restrict__ n_lo, float *__restrict__ mom, float *__restrict__ scal, int64_t M, int D, float eps,
-                          int mode, int n_tiles, int n_nblocks) {
+                          float *__restrict__ n_lo, uint32_t *__restrict__ n_x, float *__restrict__ mom, float *__restrict__ scal,
+                          int64_t M, int D, float eps, int mode, int n_tiles, int n_nblocks) {
+    static_assert(!kMixed || BK == 32, "the mixed split is written for 128-byte swizzle rows");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + kStages2 * kStageBytes2;
@@ -429,10 +467,11 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     const uint32_t st = smem_base + s * kStageBytes2;
                     const uint32_t lbar = mapa_shared(full_bar(s), 0);
                     if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes2);
+                    const int kx = kMixed ? kb * 2 * BK : kb * BK;   // bf16 operands: 2 BK elements (hi | lo) per k-block
                     tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, m0);
-                    tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kb * BK, m0);
+                    tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kx, m0);
                     tma_load_2d_pair(st + 2 * kABytes, &map_b_hi, lbar, kb * BK, n0);
-                    tma_load_2d_pair(st + 2 * kABytes + kBHalfBytes, &map_b_lo, lbar, kb * BK, n0);
+                    tma_load_2d_pair(st + 2 * kABytes + kBHalfBytes, &map_b_lo, lbar, kx, n0);
                 }
             }
         }
@@ -458,8 +497,13 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
                         tcgen05_mma_tf32_pair(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tcgen05_mma_tf32_pair(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
-                        tcgen05_mma_tf32_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                        if constexpr (kMixed) {
+                            // [bf16 a_hi | bf16 a_lo] . [bf16 b_lo | bf16 b_hi]^T: 16 bf16 = the same 32-byte K step
+                            tcgen05_mma_bf16_pair(tmem_d, da_lo + koff, db_lo + koff, make_idesc_pair_bf16(), 1u);
+                        } else {
+                            tcgen05_mma_tf32_pair(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                            tcgen05_mma_tf32_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                        }
                     }
                     tcgen05_commit_pair(empty_bar(s));      // frees the stage in both CTAs
                 }
@@ -489,7 +533,7 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     h8[j] = ldg256(a_hi + off + 8 * j);
-                    l8[j] = ldg256(a_lo + off + 8 * j);
+                    if constexpr (!kMixed) l8[j] = ldg256(a_lo + off + 8 * j);
                     p8[j] = ldg256(mom + off + 8 * j);
                 }
                 if (!waited) {
@@ -508,13 +552,14 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     }
                 }
                 if (row_ok) {
+                    uint32_t xh[16], xl[16];   // mixed split: this chunk's 32 bf16(hi) and 32 bf16(lo), packed in pairs
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float pp[8], hi[8], lo[8];
+                        float pp[8], hi[8], lo[8], dnx[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const float z = __uint_as_float(r[8 * j + e]);
-                            const float dl = h8[j].v[e] + l8[j].v[e];
+                            const float dl = kMixed ? h8[j].v[e] : h8[j].v[e] + l8[j].v[e];
                             const float gh = -z * eps_half;
                             float dn;
                             if (mode != kModeMid) quad = fmaf(z, dl, quad);
@@ -531,11 +576,41 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                             }
                             hi[e] = tf32_hi(dn);
                             lo[e] = dn - hi[e];
+                            dnx[e] = dn;
                         }
                         stg256(mom + off + 8 * j, pp);
                         if (mode != kModeLast) {
-                            stg256(n_hi + off + 8 * j, hi);
-                            stg256(n_lo + off + 8 * j, lo);
+                            if constexpr (kMixed) {
+                                stg256(n_lo + off + 8 * j, dnx);             // full-precision Delta
+                                if (n_hi) stg256(n_hi + off + 8 * j, hi);   // TF32 operand
+#pragma unroll
+                                for (int e = 0; e < 8; e += 2) {
+                                    xh[4 * j + e / 2] = pack_bf16x2(hi[e], hi[e + 1]);
+                                    xl[4 * j + e / 2] = pack_bf16x2(lo[e], lo[e + 1]);
+                                }
+                            } else {
+                                stg256(n_hi + off + 8 * j, hi);
+                                stg256(n_lo + off + 8 * j, lo);
+                            }
+                        }
+                    }
+                    if constexpr (kMixed) {
+                        if (mode != kModeLast) {
+                            // bf16 row m of [M, 2 D]: k-block (n0 + col) / 32 holds 32 hi then 32 lo = 32 words at word m D + n0 + col
+                            uint32_t *xw = n_x + off;
+                            uint32_t v[8];
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = xh[8 * g + e];
+                                stg256u(xw + 8 * g, v);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = xl[8 * g + e];
+                                stg256u(xw + 16 + 8 * g, v);
+                            }
                         }
                     }
                 }
@@ -564,6 +639,36 @@ __global__ void split_kernel(const float *__restrict__ src, float *__restrict__ 
     reinterpret_cast<float4 *>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
+// mixed split of a [rows, D] matrix: hi (TF32 truncation, fp32, optional) and the bf16 cross-term operand [rows, 2 D] whose
+// k-block kb (32 columns) holds 32 x bf16(hi) then 32 x bf16(lo) (b_order: lo first, so that the K-concatenated product
+// of an A row and a B row is a_hi b_lo + a_lo b_hi).  One thread per 8 consecutive elements.
+__global__ void split_mixed_kernel(const float *__restrict__ src, float *__restrict__ hi, uint32_t *__restrict__ x, int64_t n8,
+                                   int b_order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 v0 = reinterpret_cast<const float4 *>(src)[2 * i], v1 = reinterpret_cast<const float4 *>(src)[2 * i + 1];
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        h[e] = tf32_hi(v[e]);
+        l[e] = v[e] - h[e];
+    }
+    if (hi) {
+        reinterpret_cast<float4 *>(hi)[2 * i] = make_float4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<float4 *>(hi)[2 * i + 1] = make_float4(h[4], h[5], h[6], h[7]);
+    }
+    // element index 8 i = row D + c: word index of the pair (c, c + 1) inside the row's k-block = row D + (c / 32) 32 + (c % 32) / 2
+    const int64_t e0 = 8 * i;
+    const int64_t blk = e0 >> 5;           // (row, k-block) index: D % 32 == 0
+    const int w = (int)(e0 & 31) >> 1;     // first of 4 words inside the 16-word half
+    uint32_t *xb = x + blk * 32;
+    uint4 ph = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    *reinterpret_cast<uint4 *>(xb + (b_order ? 16 : 0) + w) = ph;
+    *reinterpret_cast<uint4 *>(xb + (b_order ? 0 : 16) + w) = pl;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -582,7 +687,80 @@ int encode_2d(EncodeTiledFn fn, CUtensorMap *map, float *base, uint64_t rows, ui
     return MMC_OK;
 }
 
+// bf16 [rows, 2 cols] cross-term operand: boxes of 2 BK = 64 elements (one 128-byte swizzle row) x box_rows
+int encode_2d_bf16(EncodeTiledFn fn, CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {2 * cols, rows};
+    const cuuint64_t strides[1] = {2 * cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * BK), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+        return MMC_ERR_CUDA;
+    }
+    return MMC_OK;
+}
+
 }  // namespace tc
+
+int dense_tc_prepare(DenseState *st);
+
+// One-off self-test per process: the same short mixed-split run with the pre-truncated TF32 copy and with the
+// full-precision Delta as the kind::tf32 operand; 1 = bit-identical (the hardware truncates), 0 = not, cached.
+static int g_hw_trunc = -1;   // -1 unknown, -2 probing
+static bool tc_hw_truncates() {
+    if (g_hw_trunc >= 0) return g_hw_trunc == 1;
+    if (g_hw_trunc == -2) return false;   // the probe's own handles
+    g_hw_trunc = -2;
+    int verdict = 0;
+    const int D = 256;
+    const int64_t M = 256;
+    std::vector<float> mean(D), prec((size_t)D * D), init((size_t)M * D);
+    uint32_t lcg = 12345u;
+    auto rnd = [&]() { lcg = lcg * 1664525u + 1013904223u; return (float)(lcg >> 8) * (1.0f / 16777216.0f) - 0.5f; };
+    for (auto &v : mean) v = rnd();
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j <= i; ++j) prec[(size_t)i * D + j] = prec[(size_t)j * D + i] = (i == j ? 2.0f : 0.0f) + 0.1f * rnd();
+    for (auto &v : init) v = 3.0f * rnd();
+    mmc_target_desc t{};
+    t.dim = D;
+    t.vec = mean.data();
+    t.mat = prec.data();
+    DenseState *ps = nullptr;
+    float *d_pos = nullptr, *d_out = nullptr;
+    unsigned long long *d_acc = nullptr;
+    std::vector<float> out[2];
+    bool ok = dense_create(&ps, &t, M) == MMC_OK && cudaMalloc((void **)&d_pos, init.size() * 4) == cudaSuccess &&
+              cudaMalloc((void **)&d_out, init.size() * 4) == cudaSuccess && cudaMalloc((void **)&d_acc, 8) == cudaSuccess;
+    for (int v = 0; v < 2 && ok; ++v) {
+        ok = cudaMemcpy(d_pos, init.data(), init.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemset(d_acc, 0, 8) == cudaSuccess;
+        DenseRunArgs a{};
+        a.positions = d_pos; a.out = d_out; a.accept_count = d_acc;
+        a.chains = M; a.n_collect = 1; a.out_pitch = 1; a.eps = 0.05f; a.n_leapfrog = 3; a.seed = 99; a.gemm_path = 3;
+        if (ok && v == 0) ok = dense_tc_prepare(ps) == MMC_OK;   // sees g_hw_trunc == -2 -> tc_hw_trunc = false
+        if (ok) {
+            ps->tc_hw_trunc = v == 1;
+            ok = dense_run(ps, a, nullptr) == MMC_OK && cudaDeviceSynchronize() == cudaSuccess;
+        }
+        if (ok) {
+            out[v].resize(init.size());
+            ok = cudaMemcpy(out[v].data(), d_out, init.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+    }
+    if (ok) {
+        bool moved = false;
+        for (size_t i = 0; i < init.size() && !moved; ++i) moved = out[0][i] != init[i];
+        verdict = moved && memcmp(out[0].data(), out[1].data(), init.size() * 4) == 0 ? 1 : 0;
+    }
+    cudaFree(d_pos); cudaFree(d_out); cudaFree(d_acc);
+    dense_destroy(ps);
+    g_hw_trunc = verdict;
+    return verdict == 1;
+}
+// 1 / 0: what the self-test found on this device (diagnostics: mmc_hmc_gemm_info)
+int dense_tc_hw_trunc_state() { return g_hw_trunc; }
 
 int dense_tc_prepare(DenseState *st) {
     if (st->tc) return MMC_OK;
@@ -597,29 +775,56 @@ int dense_tc_prepare(DenseState *st) {
     MMC_CUDA(cudaMalloc((void **)&st->d_prec_split, 2 * dd));
     MMC_CUDA(cudaMalloc((void **)&st->d_delta_split[0], 2 * md));
     MMC_CUDA(cudaMalloc((void **)&st->d_delta_split[1], 2 * md));
+    // mixed split: bf16 cross-term operands, [rows, 2 D] bf16 = 4 bytes per element of the matrix
+    MMC_CUDA(cudaMalloc((void **)&st->d_prec_x, dd));
+    MMC_CUDA(cudaMalloc((void **)&st->d_delta_x[0], md));
+    MMC_CUDA(cudaMalloc((void **)&st->d_delta_x[1], md));
+    MMC_CUDA(cudaMemset(st->d_delta_x[0], 0, md));
+    MMC_CUDA(cudaMemset(st->d_delta_x[1], 0, md));
     const int64_t n4 = (int64_t)D * D / 4;
     tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(st->d_prec, st->d_prec_split, st->d_prec_split + (size_t)D * D, n4);
+    MMC_CUDA(cudaGetLastError());
+    tc::split_mixed_kernel<<<(unsigned)((n4 / 2 + 255) / 256), 256>>>(st->d_prec, nullptr, st->d_prec_x, n4 / 2, 1);
     MMC_CUDA(cudaGetLastError());
     MMC_CUDA(cudaDeviceSynchronize());
     tc::Maps *maps = new tc::Maps();
     int rc = MMC_OK;
+    const tc::EncodeTiledFn enc = (tc::EncodeTiledFn)fn;
     for (int b = 0; b < 2 && !rc; ++b) {
-        rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->a_hi[b], st->d_delta_split[b], (uint64_t)M, (uint64_t)D, tc::BM);
-        if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->a_lo[b], st->d_delta_split[b] + (size_t)M * D, (uint64_t)M, (uint64_t)D, tc::BM);
+        rc = tc::encode_2d(enc, &maps->a_hi[b], st->d_delta_split[b], (uint64_t)M, (uint64_t)D, tc::BM);
+        if (!rc) rc = tc::encode_2d(enc, &maps->a_lo[b], st->d_delta_split[b] + (size_t)M * D, (uint64_t)M, (uint64_t)D, tc::BM);
+        if (!rc) rc = tc::encode_2d_bf16(enc, &maps->a_x[b], st->d_delta_x[b], (uint64_t)M, (uint64_t)D, tc::BM);
+        if (!rc) rc = tc::encode_2d(enc, &maps->a_full[b], st->d_delta[b], (uint64_t)M, (uint64_t)D, tc::BM);
     }
-    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_hi, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN);
-    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_lo, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN);
-    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_hi_half, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN / 2);
-    if (!rc) rc = tc::encode_2d((tc::EncodeTiledFn)fn, &maps->b_lo_half, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN / 2);
+    if (!rc) rc = tc::encode_2d(enc, &maps->b_hi, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN);
+    if (!rc) rc = tc::encode_2d(enc, &maps->b_lo, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN);
+    if (!rc) rc = tc::encode_2d(enc, &maps->b_hi_half, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN / 2);
+    if (!rc) rc = tc::encode_2d(enc, &maps->b_lo_half, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN / 2);
+    if (!rc) rc = tc::encode_2d_bf16(enc, &maps->b_x_half, st->d_prec_x, (uint64_t)D, (uint64_t)D, tc::BN / 2);
     if (rc) { delete maps; return rc; }
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     st->tc = maps;
+    // Mixed split only: kind::tf32 can read the full-precision Delta directly when the tensor core ignores the low 13
+    // mantissa bits of its fp32 containers, which saves the separate TF32 copy (4 of the epilogue's 24 bytes per element).
+    // PTX leaves unconverted inputs unspecified, so this is enabled only after a one-off self-test on this device has
+    // produced bit-identical transitions both ways (MMC_TC_HW_TRUNC=0 / 1 overrides the test).
+    const char *hw = getenv("MMC_TC_HW_TRUNC");
+    if (hw && (hw[0] == '0' || hw[0] == '1')) st->tc_hw_trunc = hw[0] == '1';
+    else st->tc_hw_trunc = tc_hw_truncates();
     return MMC_OK;
 }
 
-// splits the full-precision Delta written by dense_begin_kernel into buffer 0 of the hi/lo ping-pong
+// splits the full-precision Delta written by dense_begin_kernel into buffer 0 of the operand ping-pong
 int dense_tc_split_delta(DenseState *st, cudaStream_t stream) {
+    if (st->tc_mixed) {
+        const int64_t n8 = st->chains * st->Dp / 8;
+        tc::split_mixed_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(st->d_delta[0], st->tc_hw_trunc ? nullptr : st->d_delta_split[0],
+                                                                                st->d_delta_x[0], n8, 0);
+        MMC_CUDA(cudaGetLastError());
+        return MMC_OK;
+    }
     const int64_t n4 = st->chains * st->Dp / 4;
     float *hi = st->d_delta_split[0];
     tc::split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(st->d_delta[0], hi, hi + (size_t)st->chains * st->Dp, n4);
@@ -649,9 +854,16 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
         attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
-                                    maps->b_lo_half, (const float *)a_hi, (const float *)a_lo, n_hi, n_lo, st->d_mom, st->d_scal, M, D,
-                                    eps, mode, n_tiles2, n_nblocks));
+        if (st->tc_mixed) {
+            MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<true>, st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur],
+                                        maps->a_x[cur], maps->b_hi_half, maps->b_x_half, (const float *)st->d_delta[cur],
+                                        (const float *)nullptr, st->tc_hw_trunc ? (float *)nullptr : n_hi, st->d_delta[cur ^ 1],
+                                        st->d_delta_x[cur ^ 1], st->d_mom, st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
+            return MMC_OK;
+        }
+        MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<false>, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
+                                    maps->b_lo_half, (const float *)a_hi, (const float *)a_lo, n_hi, n_lo, (uint32_t *)nullptr, st->d_mom,
+                                    st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
         return MMC_OK;
     }
     const int n_tiles = n_nblocks * (int)((M + tc::BM - 1) / tc::BM);

@@ -26,7 +26,7 @@ struct mmc_hmc {
     uint64_t seed = 0;
     int32_t exact = 0;
     int64_t out_pitch = 0;       // *_dev runs: draws per chain row of the caller's tensor (0 = n_collect)
-    int32_t gemm_path = -1;      // dense Gaussian: -1 = auto (tcgen05 CTA pairs when dim % 256 == 0), 0 = FP32 SIMT tiles, 1 / 2 = tcgen05 3xTF32
+    int32_t gemm_path = -1;      // dense Gaussian: -1 = auto (tcgen05 CTA pairs, mixed split), 0 = FP32 SIMT tiles, 1 / 2 = tcgen05 3xTF32, 3 = TF32 + BF16 mixed split
     DenseState *dense = nullptr;  // only for MMC_T_DENSE_GAUSSIAN
     float *d_pos = nullptr;
     unsigned long long *d_accept = nullptr;
@@ -222,7 +222,7 @@ int mmc_hmc_set_out_pitch(mmc_hmc *h, int64_t pitch_steps) {
 }
 
 int mmc_hmc_set_gemm_path(mmc_hmc *h, int32_t path) {
-    MMC_REQUIRE(h && path >= -1 && path <= 2, "gemm path must be -1 (auto), 0 (FP32 SIMT), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xTF32, CTA pairs)");
+    MMC_REQUIRE(h && path >= -1 && path <= 3, "gemm path must be -1 (auto), 0 (FP32 SIMT), 1 (tcgen05 3xTF32), 2 (tcgen05 3xTF32, CTA pairs) or 3 (CTA pairs, TF32 + BF16 mixed split)");
     h->gemm_path = path;
     return MMC_OK;
 }
@@ -254,7 +254,7 @@ int mmc_hmc_run_dev(mmc_hmc *h, int64_t n_collect, int64_t n_discard, float *out
         // 128 x 256 tcgen05 tiles do not divide use the FP32 SIMT tiles
         // auto: tcgen05 CTA pairs (any dim: the rows are zero padded to whole 256-column tiles); dim 128 and the reference
         // arithmetic run on the FP32 SIMT tiles
-        a.gemm_path = (h->exact || h->dim == 128) ? 0 : (h->gemm_path >= 0 ? h->gemm_path : 2);
+        a.gemm_path = (h->exact || h->dim == 128) ? 0 : (h->gemm_path >= 0 ? h->gemm_path : 3);
         int rc = dense_run(h->dense, a, (cudaStream_t)stream);
         if (rc) return rc;
         h->step += n_collect + n_discard;

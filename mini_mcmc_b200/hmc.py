@@ -47,7 +47,8 @@ class HMC:
 
     def set_gemm_path(self, path: int):
         """Dense Gaussian target: 0 = FP32 SIMT GEMM tiles, 1 = tcgen05 tensor cores (3xTF32, one CTA per tile),
-        2 = tcgen05 with CTA pairs (cta_group::2, 256 x 256 tiles; the fastest path)."""
+        2 = tcgen05 with CTA pairs (cta_group::2, 256 x 256 tiles), 3 = CTA pairs with the TF32 + BF16 mixed split
+        (hi.hi on TF32, the cross terms hi.lo + lo.hi as one K-concatenated BF16 MMA)."""
         L.check(L.lib.mmc_hmc_set_gemm_path(self._h, C.c_int32(path)))
         return self
 

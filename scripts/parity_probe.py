@@ -36,7 +36,32 @@ def report(name, cmp):
     sys.stdout.flush()
 
 
+def qq(a):
+    a = np.asarray(a, dtype=np.float64)
+    return "p50 %.1e p99 %.1e p99.9 %.1e p99.99 %.1e max %.1e  frac<=1e-5 %.5f" % (
+        np.quantile(a, 0.5), np.quantile(a, 0.99), np.quantile(a, 0.999), np.quantile(a, 0.9999), a.max(), (a <= 1e-5).mean())
+
+
 what = set(sys.argv[1:]) or {"hmc", "nuts", "tree"}
+if "full" in what:   # BASELINE widths (tests/test_gpu_full_width.py)
+    case = st.hmc_case(3, chains=262144)
+    exp = st.hmc_oracle(case)
+    for exact in (True, False):
+        cmp = st.hmc_compare(case, exp, st.hmc_device(mm, case, exact))
+        print(f"C3 full width exact={exact}: differ {int(cmp['differ'].sum())} unexplained {int(cmp['unexplained'].sum())}")
+        for k in ("logp_cur", "logp_prop", "accept_logp", "state"):
+            print(f"    {k:12s} {qq(cmp[k])}")
+    case = st.nuts_full_width_case(mm)
+    exp = st.nuts_oracle(case)
+    print("C5 full width: oracle depth hist", np.bincount(exp["trace"][:, 5].astype(int)))
+    for exact in (True, False):
+        cmp = st.nuts_compare(exp, st.nuts_device(mm, case, 0, exact))
+        print(f"C5 full width exact={exact}: differ {int(cmp['differ'].sum())} unexplained {int(cmp['unexplained'].sum())}")
+        for k in ("joint", "logu", "eps", "alpha", "state"):
+            print(f"    {k:12s} {qq(cmp[k])}")
+        sh = cmp["depth"] <= 5
+        print(f"    state(depth<=5) {qq(cmp['state'][sh])}")
+    sys.stdout.flush()
 if "hmc" in what:
     for D in (2, 3, 5, 8, 16):
         case = st.hmc_case(D)

@@ -164,6 +164,52 @@ def dense(chains=4096, D=1024, L=50, steps=4, path=0):
                           accept=acc / max(tot, 1))))
 
 
+def dense_err(D=1024, chains=512, L=50, eps=0.05):
+    """error of every GEMM path against the oracle (f32 reference arithmetic) and against a float64 evaluation of the same
+    replayed transition: C4 shape, one transition of L leapfrogs"""
+    import oracle
+    rng = np.random.default_rng(42)
+    A = rng.normal(size=(D, D))
+    cov = A @ A.T / D + np.eye(D)
+    mean = rng.normal(size=D)
+    tgt = mm.DenseGaussian(mean, cov)
+    otgt = oracle.dense_gaussian(tgt.mean, tgt.precision, tgt.norm_const)
+    init = (rng.normal(size=(chains, D)) + mean).astype(np.float32)
+    mom = rng.normal(size=(1, chains, D)).astype(np.float32)
+    u = rng.random((1, chains)).astype(np.float32)
+    exp, _, exp_tr = oracle.hmc_run_replay(otgt, init, eps, L, 1, 0, mom, u, want_trace=True)
+    # float64 shadow of the proposal
+    P = np.asarray(tgt.precision, dtype=np.float64)
+    x = init.astype(np.float64) - np.asarray(tgt.mean, dtype=np.float64)
+    p = mom[0].astype(np.float64)
+    e = float(np.float32(eps))
+    g = -(x @ P)
+    for _ in range(L):
+        p = p + g * (e * 0.5)
+        x = x + p * e
+        g = -(x @ P)
+        p = p + g * (e * 0.5)
+    prop64 = x + np.asarray(tgt.mean, dtype=np.float64)
+    lp64 = float(tgt.norm_const) - 0.5 * np.einsum("ij,ij->i", x @ P, x)
+    acc = exp_tr[0, :, 3] == 1
+    ref_state = np.abs(exp[acc, 0] - prop64[acc]).max(axis=1) / np.maximum(1.0, np.abs(prop64[acc]).max(axis=1))
+    print(json.dumps(dict(k="dense_err", path="oracle_f32_vs_f64", state_q50=float(np.median(ref_state)), state_max=float(ref_state.max()),
+                          logp_max=float((np.abs(exp_tr[0, :, 1] - lp64) / np.abs(lp64)).max()))))
+    for path in (0, 2, 3):
+        h = mm.HMC(tgt, init, eps, L).set_gemm_path(path)
+        tr = np.zeros((1, chains, 4), dtype=np.float32)
+        got = h.run(1, 0, replay=dict(momenta=mom, u=u), trace=tr)
+        same = tr[0, :, 3] == exp_tr[0, :, 3]
+        ok = same & acc
+        st_o = np.abs(got[ok, 0] - exp[ok, 0]).max(axis=1) / np.maximum(1.0, np.abs(exp[ok, 0]).max(axis=1))
+        st_64 = np.abs(got[ok, 0] - prop64[ok]).max(axis=1) / np.maximum(1.0, np.abs(prop64[ok]).max(axis=1))
+        lp_o = np.abs(tr[0, :, :2] - exp_tr[0, :, :2]).max(axis=1) / np.maximum(1.0, np.abs(exp_tr[0, :, :2]).max(axis=1))
+        lp_64 = np.abs(tr[0, :, 1] - lp64) / np.abs(lp64)
+        print(json.dumps(dict(k="dense_err", path=path, L=L, same_decisions=float(same.mean()), state_vs_oracle_q50=float(np.median(st_o)),
+                              state_vs_oracle_max=float(st_o.max()), state_vs_f64_q50=float(np.median(st_64)), state_vs_f64_max=float(st_64.max()),
+                              logp_vs_oracle_max=float(lp_o.max()), logp_vs_f64_max=float(lp_64.max()))))
+
+
 def nuts(chains=65536, D=100, n_collect=400, n_discard=400, scalar="f32", layout=0):
     init = mm.init_device(chains, D, 42).cpu().numpy()
     s = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype=scalar, max_depth=10).set_seed(7).set_layout(layout)
@@ -247,6 +293,12 @@ if __name__ == "__main__":
             dense(chains=32768, steps=2, path=1)
         except Exception as e:
             print("tc path:", e)
+    if "dense_tc" in which:   # tensor-core paths only: 3xTF32 CTA pairs vs the TF32 + BF16 mixed split
+        for path in (2, 3):
+            dense(chains=32768, steps=4, path=path)
+            dense(chains=4096, steps=4, path=path)
+    if "dense_err" in which:
+        dense_err()
     if "gibbs" in which:
         gibbs()
     if "sinks" in which:

@@ -138,6 +138,20 @@ def nuts_compare(exp, got):
         unexplained=differ & (exp["margin"] > NUTS_TIE_MARGIN))
 
 
+def nuts_full_width_case(mm, chains=65536, D=100, max_depth=8, delta=0.9, warm=30):
+    """C5 width: the device warms the chains up natively (positions and adaptation state after `warm` transitions), then
+    the transition under test consumes fresh tapes on both sides."""
+    init = mm.init_device(chains, D, 42).cpu().numpy()
+    w = mm.NUTS(mm.RosenbrockND(), init, delta, scalar_dtype="f32", max_depth=max_depth).set_seed(11)
+    w.run_device(1, warm, progress=True)
+    positions, state = w.positions, w.state()
+    del w
+    rng = np.random.default_rng(5)
+    tapes = (rng.normal(size=(chains, D)), rng.exponential(size=(chains, 1)), rng.random((chains, 2 ** (max_depth + 1) + 64)))
+    tapes = tuple(t.astype(np.float32).astype(np.float64) for t in tapes)   # T = f32: the reference's draws are f32 values
+    return dict(D=D, delta=delta, max_depth=max_depth, scalar_f32=True, positions=positions, state=state, tapes=tapes)
+
+
 # ------------------------------------------------------------------ build_tree (src/nuts.rs:764-946)
 def tree_case(D, chains=128, j=4, scalar_f32=True, seed=0):
     rng = np.random.default_rng(3000 + D + seed)

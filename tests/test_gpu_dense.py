@@ -27,7 +27,7 @@ def tc_supported(D):
     return D != 128   # tcgen05 tiles are 256 columns wide: other dims are zero padded inside the library, 128 runs on FP32 tiles
 
 
-@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
 @pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
     if path >= 1 and not tc_supported(D):
@@ -57,7 +57,8 @@ def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
 
 
 def test_tensor_core_path_matches_fp32_path(mm):
-    """Same replayed transition through all GEMM paths (3xTF32 on tcgen05, 1-CTA and CTA-pair, vs FP32 SIMT): ragged chain count."""
+    """Same replayed transition through all GEMM paths (3xTF32 on tcgen05, 1-CTA and CTA-pair, and the TF32 + BF16 mixed split,
+    vs FP32 SIMT): ragged chain count."""
     D, chains, L = 512, 333, 6
     mean, cov = make_problem(D, seed=9)
     tgt = mm.DenseGaussian(mean, cov)
@@ -66,7 +67,7 @@ def test_tensor_core_path_matches_fp32_path(mm):
     mom = rng.normal(size=(3, chains, D)).astype(np.float32)
     u = rng.random((3, chains)).astype(np.float32)
     outs = []
-    for path in (0, 1, 2):
+    for path in (0, 1, 2, 3):
         h = mm.HMC(tgt, init, 0.05, L).set_gemm_path(path)
         tr = np.zeros((3, chains, 4), dtype=np.float32)
         outs.append((h.run(3, 0, replay=dict(momenta=mom, u=u), trace=tr), tr))
@@ -80,7 +81,7 @@ def test_tensor_core_path_matches_fp32_path(mm):
     np.testing.assert_array_equal(outs[1][0], outs[2][0])
 
 
-@pytest.mark.parametrize("path,D", [(0, 128), (1, 256), (2, 256)])
+@pytest.mark.parametrize("path,D", [(0, 128), (1, 256), (2, 256), (3, 256)])
 def test_dense_hmc_native_tape_and_moments(mm, path, D):
     chains, L = 512, 8
     mean, cov = make_problem(D, seed=3)

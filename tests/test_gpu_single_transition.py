@@ -219,10 +219,10 @@ def test_build_tree_random_doublings(mm, D, j):
 
 
 # ------------------------------------------------------------------ C4-shaped dense transition
-@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
 def test_dense_c4_single_transition_golden(mm, path):
-    """D = 1024 dense Gaussian, one transition of L = 5 leapfrogs from the committed fixture, FP32 SIMT path and both
-    tcgen05 3xTF32 paths: log-probs (O(D) magnitudes), accept decisions and states inside RTOL."""
+    """D = 1024 dense Gaussian, one transition of L = 5 leapfrogs from the committed fixture, FP32 SIMT path, both
+    tcgen05 3xTF32 paths and the TF32 + BF16 mixed split: log-probs (O(D) magnitudes), accept decisions and states inside RTOL."""
     import sys
 
     sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "scripts"))
