@@ -24,6 +24,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "mmc_dense.cuh"
@@ -337,7 +338,10 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 constexpr uint32_t kBHalfBytes = kBBytes / 2;
 constexpr uint32_t kStageBytes2 = 2 * kABytes + 2 * kBHalfBytes;
 constexpr int kStages2 = (BK == 32 ? 3 : 6);
-constexpr uint32_t kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+// + one 32 x 32 float transposition tile (8 column groups of 132 floats) per epilogue warp (coalesced epilogue of the mixed-split kernel)
+constexpr uint32_t kEpiTileFloats = 8 * 132;
+constexpr uint32_t kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kEpiWarps * kEpiTileFloats * 4;
+static_assert(kSmemBytes2 <= 232448, "CTA-pair kernel: shared memory over the 227 KB limit");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -403,7 +407,11 @@ __device__ __forceinline__ void stg256u(uint32_t *p, const uint32_t (&v)[8]) {
 // kMixed: map_a_lo / map_b_lo are the bf16 cross-term operands ([rows, 2 D], 64-element boxes), a_hi = the full-precision
 // Delta (read by the epilogue), a_lo unused, n_hi = next TF32 hi (nullptr: not stored, MMC_TC_HW_TRUNC), n_lo = next
 // full-precision Delta, n_x = next bf16 cross-term operand
-template <bool kMixed>
+// kCoal (with kMixed): the epilogue transposes the accumulator chunk through shared memory so that every global access of
+// a warp covers whole 128-byte lines of ONE row (lane = column) instead of one 32-byte sector of 32 different rows
+// (lane = row, the TMEM layout): ncu showed the L1TEX -> XBAR request path as the busiest unit (67 %) with the row-per-lane
+// epilogue issuing 20,480 sector requests per tile next to the 16,384 line requests of the TMA operand loads.
+template <bool kMixed, bool kCoal>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -518,6 +526,111 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
         const int row = q * 32 + lane;
         const float eps_half = eps * 0.5f;
         uint32_t lt = 0;
+        if constexpr (kMixed && kCoal) {
+            // transposition tile of this warp: 8 column groups x (32 rows x 4 columns + 4 floats of padding); lane = row writes
+            // float4 (conflict-free per quarter warp), lane = (row % 4 group, column group) reads float4 (conflict-free)
+            float *zt = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + ew * kEpiTileFloats;
+            const int cg = lane & 7, rg = lane >> 3;   // this lane's 4 columns (4 cg ..) and its row inside a group of 4 rows
+            auto run_tiles = [&](auto mode_c) {
+                constexpr int kMode = decltype(mode_c)::value;
+                for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+                    const int n0 = (tile % n_nblocks) * BN;
+                    const int64_t m_base = (int64_t)(tile / n_nblocks) * (2 * BM) + (int64_t)rank * BM + q * 32;   // row of TMEM lane 0
+                    const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                    float quad = 0.f, ke = 0.f;   // lane = row (m_base + lane), as in the accumulator layout
+                    bool waited = false;
+#pragma unroll 1
+                    for (int chunk = 0; chunk < BN / 64; ++chunk) {
+                        const int col = half * (BN / 2) + chunk * 32;
+                        // iteration it handles rows 4 it + rg: one 128-byte line per row and array, 4 rows per warp access
+                        const int64_t off0 = (m_base + rg) * D + n0 + col + 4 * cg;
+                        const int64_t rows_left = M - m_base - rg;   // row 4 it + rg exists iff 4 it < rows_left
+                        float4 dl[8], pm[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int64_t o = (4 * it < rows_left) ? off0 + (int64_t)(4 * it) * D : (int64_t)(n0 + col + 4 * cg);
+                            dl[it] = __ldg(reinterpret_cast<const float4 *>(a_hi + o));
+                            pm[it] = *reinterpret_cast<const float4 *>(mom + o);
+                        }
+                        if (!waited) {
+                            mbar_wait(tmem_full_bar(as), aph);
+                            tcgen05_fence_after();
+                            waited = true;
+                        }
+                        {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)col, r);
+                            if (chunk == BN / 64 - 1) {
+                                tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    const uint32_t lbar = mapa_shared(tmem_empty_bar(as), 0);
+                                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
+                                }
+                            }
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4)
+                                *reinterpret_cast<float4 *>(zt + c4 * 132 + lane * 4) =
+                                    make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]), __uint_as_float(r[4 * c4 + 2]),
+                                                __uint_as_float(r[4 * c4 + 3]));
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const float4 z4 = *reinterpret_cast<const float4 *>(zt + cg * 132 + (4 * it + rg) * 4);
+                            const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+                            const float d[4] = {dl[it].x, dl[it].y, dl[it].z, dl[it].w};
+                            const float pin[4] = {pm[it].x, pm[it].y, pm[it].z, pm[it].w};
+                            float pp[4], dn[4], hi[4], lo[4];
+                            float qs = 0.f, ks = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float gh = -z[e] * eps_half;
+                                if (kMode == kModeMid) pp[e] = (pin[e] + gh) + gh;
+                                else pp[e] = pin[e] + gh;
+                                dn[e] = kMode == kModeLast ? d[e] : fmaf(eps, pp[e], d[e]);
+                                hi[e] = tf32_hi(dn[e]);
+                                lo[e] = dn[e] - hi[e];
+                                if (kMode != kModeMid) qs = fmaf(z[e], d[e], qs);
+                                if (kMode == kModeLast) ks = fmaf(pp[e], pp[e], ks);
+                            }
+                            if (kMode != kModeMid) {
+                                // row sums over the 8 lanes of a row; lane L owns row L: computed in iteration L / 4 by group L % 4
+#pragma unroll
+                                for (int o = 4; o > 0; o >>= 1) {
+                                    qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                                    if (kMode == kModeLast) ks += __shfl_xor_sync(0xffffffffu, ks, o);
+                                }
+                                const float qrow = __shfl_sync(0xffffffffu, qs, 8 * (lane & 3));
+                                const float krow = kMode == kModeLast ? __shfl_sync(0xffffffffu, ks, 8 * (lane & 3)) : 0.f;
+                                if ((lane >> 2) == it) { quad += qrow; ke += krow; }
+                            }
+                            if (4 * it < rows_left) {
+                                const int64_t o = off0 + (int64_t)(4 * it) * D;
+                                *reinterpret_cast<float4 *>(mom + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                                if (kMode != kModeLast) {
+                                    *reinterpret_cast<float4 *>(n_lo + o) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+                                    if (n_hi) *reinterpret_cast<float4 *>(n_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                                    // bf16 row block of this k-block: words 0..15 = (hi, hi) pairs, 16..31 = (lo, lo) pairs
+                                    uint32_t *xw = n_x + (o - 4 * cg);
+                                    *reinterpret_cast<uint2 *>(xw + 2 * cg) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+                                    *reinterpret_cast<uint2 *>(xw + 16 + 2 * cg) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+                                }
+                            }
+                        }
+                        __syncwarp();   // the tile is rewritten by the next chunk
+                    }
+                    const int64_t m = m_base + lane;
+                    if (m < M && kMode != kModeMid) {
+                        atomicAdd(scal + (kMode == kModeFirst ? 1 : 3) * M + m, quad);
+                        if (kMode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
+                    }
+                }
+            };
+            if (mode == kModeMid) run_tiles(std::integral_constant<int, kModeMid>{});
+            else if (mode == kModeFirst) run_tiles(std::integral_constant<int, kModeFirst>{});
+            else run_tiles(std::integral_constant<int, kModeLast>{});
+        } else
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
             const int n0 = (tile % n_nblocks) * BN;
             const int64_t m = (int64_t)(tile / n_nblocks) * (2 * BM) + (int64_t)rank * BM + row;
@@ -803,8 +916,9 @@ int dense_tc_prepare(DenseState *st) {
     if (!rc) rc = tc::encode_2d_bf16(enc, &maps->b_x_half, st->d_prec_x, (uint64_t)D, (uint64_t)D, tc::BN / 2);
     if (rc) { delete maps; return rc; }
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
-    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     st->tc = maps;
     // Mixed split only: kind::tf32 can read the full-precision Delta directly when the tensor core ignores the low 13
     // mantissa bits of its fp32 containers, which saves the separate TF32 copy (4 of the epilogue's 24 bytes per element).
@@ -855,13 +969,15 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
         if (st->tc_mixed) {
-            MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<true>, st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur],
+            static const bool coal = !(getenv("MMC_TC_EPI") && getenv("MMC_TC_EPI")[0] == '0');   // 0: row-per-lane epilogue (A/B)
+            auto kern = coal ? tc::dense_gemm_tc_pair_kernel<true, true> : tc::dense_gemm_tc_pair_kernel<true, false>;
+            MMC_CUDA(cudaLaunchKernelEx(&cfg, kern, st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur],
                                         maps->a_x[cur], maps->b_hi_half, maps->b_x_half, (const float *)st->d_delta[cur],
                                         (const float *)nullptr, st->tc_hw_trunc ? (float *)nullptr : n_hi, st->d_delta[cur ^ 1],
                                         st->d_delta_x[cur ^ 1], st->d_mom, st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
             return MMC_OK;
         }
-        MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<false>, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
+        MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<false, false>, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
                                     maps->b_lo_half, (const float *)a_hi, (const float *)a_lo, n_hi, n_lo, (uint32_t *)nullptr, st->d_mom,
                                     st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
         return MMC_OK;

@@ -22,6 +22,13 @@ elif which == "dense":
     tgt = mm.DenseGaussian(rng.normal(size=D), A @ A.T / D + np.eye(D))
     h = mm.HMC(tgt, rng.normal(size=(chains, D)).astype(np.float32), 0.05, 8).set_seed(1).set_gemm_path(1)
     h.run_device(1, 0)
+elif which in ("dense2", "dense3"):   # CTA-pair kernels: 3xTF32 (2) and the TF32 + BF16 mixed split (3)
+    D, chains = 1024, 32768
+    rng = np.random.default_rng(42)
+    A = rng.normal(size=(D, D))
+    tgt = mm.DenseGaussian(rng.normal(size=D), A @ A.T / D + np.eye(D))
+    h = mm.HMC(tgt, rng.normal(size=(chains, D)).astype(np.float32), 0.05, 8).set_seed(1).set_gemm_path(int(which[-1]))
+    h.run_device(1, 0)
 elif which == "stats":
     x = torch.randn((65536, 400, 100), device="cuda")
     mm.split_rhat_mean_ess(x)
