@@ -35,6 +35,9 @@ inline int nuts_group_lanes(const mmc_target_desc &t) {
     switch (t.kind) {
     case MMC_T_ROSENBROCK_ND:
         if (t.dim <= 4) return 4;
+#ifdef MMC_NUTS_GROUP_TUNE_G4   // tuning builds: eight chains per warp at D = 100 (E = 26)
+        if (t.dim > 64 && t.dim <= 104) return 4;
+#endif
         if (t.dim <= 104) return 8;
         if (t.dim <= 128) return 16;
         return 0;
@@ -72,6 +75,11 @@ int nuts_group_dispatch_target(const NutsLaunch &L, const NutsParams &p, int64_t
 #ifdef MMC_NUTS_GROUP_TUNE_G16   // tuning builds: two chains per warp at D = 100
         if constexpr (A::kContract) {
             if (t.dim <= 128) MMC_GROUP_LAUNCH_PACKED(8, 16);
+        }
+#endif
+#ifdef MMC_NUTS_GROUP_TUNE_G4
+        if constexpr (A::kContract) {
+            if (t.dim <= 104) MMC_GROUP_LAUNCH_PACKED(26, 4);
         }
 #endif
         if (t.dim <= 104) {

@@ -42,7 +42,14 @@ def peaks():
     except Exception:
         pass
     fp32 = 148 * 128 * 2 * mhz * 1e6 / 1e12
-    return dict(hbm_gbs=hbm, fp32_tflops=fp32, tf32x3_tflops=bf16 / 2.0 / 3.0, source=src)
+    bf16_sus = bf16
+    try:
+        bf16_sus = float(d.get("bf16_tflops_sustained", bf16))
+    except Exception:
+        pass
+    # the mixed split issues 1 TF32 + 1 double-length BF16 MMA per product = 2 TF32-equivalents (3 for the plain 3xTF32 split)
+    return dict(hbm_gbs=hbm, fp32_tflops=fp32, tf32x3_tflops=bf16 / 2.0 / 3.0, tf32x2_tflops=bf16 / 2.0 / 2.0,
+                tf32x2_tflops_sustained=bf16_sus / 2.0 / 2.0, source=src)
 
 
 RESULTS = []
@@ -162,8 +169,8 @@ def c4(args):
     init = mm.init_device(chains, D, 42, chain_offset=RANK * chains).cpu().numpy()
     res = {}
     pk = peaks()
-    # "default" = what a caller of mmc_hmc_create + mmc_hmc_run gets (tcgen05 CTA pairs); the others on request
-    paths = [(-1, "default")] + ([(1, "tcgen05_3xTF32_1cta"), (0, "fp32_simt")] if getattr(args, "all_paths", False) else [])
+    # "default" = what a caller of mmc_hmc_create + mmc_hmc_run gets (tcgen05 CTA pairs, TF32 + BF16 mixed split); the others on request
+    paths = [(-1, "default")] + ([(2, "tcgen05_3xTF32_pair"), (1, "tcgen05_3xTF32_1cta"), (0, "fp32_simt")] if getattr(args, "all_paths", False) else [])
     for path, name in paths:
         h = mm.HMC(tgt, init, 0.05, L).set_seed(1).set_chain_offset(RANK * chains)
         if path >= 0:
@@ -186,10 +193,20 @@ def c4(args):
     d = res["default"]
     emit(config=f"C4 dense Gaussian D=1024 HMC, 32768 chains total ({chains}/GPU, strong), L=50, {steps} transitions",
          scaling="strong", ms=d["ms"], grad_evals_per_s=d["grad_evals_per_s"], us_per_leapfrog=d["us_per_leapfrog"],
-         roofline=dict(bound="tensor", achieved=d["tflops_fp32_equiv_per_gpu"], peak=pk["tf32x3_tflops"], unit="TFLOP/s",
-                       frac=d["tflops_fp32_equiv_per_gpu"] / pk["tf32x3_tflops"], kernel="dense_gemm_tc_pair_kernel",
-                       note="fp32-equivalent flops (2 D^2 + 4 D per grad-eval); the 3xTF32 split issues 3 MMAs per product, "
-                            "so the denominator is TF32 / 3 = measured dense bf16 / 6"),
+         roofline=dict(bound="tensor", achieved=d["tflops_fp32_equiv_per_gpu"], peak=pk["tf32x2_tflops"], unit="TFLOP/s",
+                       frac=d["tflops_fp32_equiv_per_gpu"] / pk["tf32x2_tflops"], kernel="dense_gemm_tc_pair_kernel<mixed>",
+                       frac_of_sustained_peak=d["tflops_fp32_equiv_per_gpu"] / pk["tf32x2_tflops_sustained"],
+                       frac_of_3xTF32_peak=d["tflops_fp32_equiv_per_gpu"] / pk["tf32x3_tflops"],
+                       operand_feed=dict(bound="l2_to_sm", bytes_per_launch=(chains + 255) // 256 * (D // 256) * 4 * 1024 * 1024,
+                                         achieved_TBs=(chains + 255) // 256 * (D // 256) * 4 * 1024 * 1024 / (d["us_per_leapfrog"] * 1e-6) / 1e12,
+                                         note="TMA operand bytes of one GEMM launch (4 MiB per 256 x 256 CTA-pair tile: 8 B per "
+                                              "element of A and B) over the time of one leapfrog; ncu: 6,770 B/clk from L2, the LTS "
+                                              "throughput cap B300_MICROARCH.md measures (~6,300 B/clk) - this feed, not the tensor "
+                                              "pipe (66 % active), bounds the kernel"),
+                       note="fp32-equivalent flops (2 D^2 + 4 D per grad-eval); the mixed split issues 1 TF32 + 1 double-length BF16 "
+                            "MMA per product = 2 TF32-equivalents, so the tensor denominator is TF32 / 2 = measured dense bf16 / 4 "
+                            "(burst); frac_of_sustained_peak uses the back-to-back bf16 figure, frac_of_3xTF32_peak is the "
+                            "round-1 / round-2 denominator (bf16 / 6) for comparison"),
          paths=res, cpu_grad_evals_per_s=cpu_rate, cpu_cores=cores)
 
 
