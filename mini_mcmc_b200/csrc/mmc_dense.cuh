@@ -30,7 +30,8 @@ struct DenseState {
     uint32_t *d_prec_x = nullptr;                   // [D, 2 D] bf16: per 32-column k-block 32 x lo then 32 x hi
     uint32_t *d_delta_x[2] = {nullptr, nullptr};    // [chains, 2 D] bf16: per k-block 32 x hi then 32 x lo
     bool tc_mixed = false;
-    bool tc_hw_trunc = false;                       // MMC_TC_HW_TRUNC=1 experiment (mmc_dense_tc.cu)
+    bool tc_hw_trunc = false;                       // kind::tf32 reads the full-precision Delta (self-tested, mmc_dense_tc.cu)
+    int tc_quad_clusters = 0;                       // resident 4-CTA clusters of the quad kernel (0: not available)
 };
 
 enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };

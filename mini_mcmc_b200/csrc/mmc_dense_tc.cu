@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -55,6 +56,7 @@ struct Maps {
     CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
     CUtensorMap b_hi_half, b_lo_half;   // 128-row boxes for the CTA-pair kernel
     CUtensorMap a_x[2], b_x_half;       // mixed split: bf16 [rows, 2 D] cross-term operands, boxes of 64 x 128
+    CUtensorMap b_hi_q, b_x_q;          // 64-row boxes of B for the 4-CTA cluster kernel (each CTA loads half of its half)
     CUtensorMap a_full[2];              // MMC_TC_HW_TRUNC experiment: the full-precision Delta as the TF32 operand
 };
 
@@ -364,10 +366,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t cta_mask = 3) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
+                 "h"(cta_mask)
                  : "memory");
+}
+// the same load delivered to every CTA of cta_mask at the same CTA-relative offset; the completion bytes of each copy are
+// signalled on the full barrier of the RECEIVING CTA's pair leader (barrier address with the peer bit cleared, as CUTLASS'
+// SM100_TMA_2SM_LOAD_MULTICAST does)
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1,
+                                                    uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                       uint32_t accumulate) {
@@ -411,7 +423,11 @@ __device__ __forceinline__ void stg256u(uint32_t *p, const uint32_t (&v)[8]) {
 // a warp covers whole 128-byte lines of ONE row (lane = column) instead of one 32-byte sector of 32 different rows
 // (lane = row, the TMEM layout): ncu showed the L1TEX -> XBAR request path as the busiest unit (67 %) with the row-per-lane
 // epilogue issuing 20,480 sector requests per tile next to the 16,384 line requests of the TMA operand loads.
-template <bool kMixed, bool kCoal>
+// kQuad: clusters of FOUR CTAs = two CTA pairs that work on the same 256 columns of two consecutive 256-row blocks.  The
+// B half a CTA needs is the same in both pairs, so each CTA loads 64 of its 128 rows and multicasts them to its twin in the
+// other pair: 48 instead of 64 KB per CTA and k-block come from L2, the feed that bounds the kernel.  A
+// stage is reused only after BOTH pairs have consumed it (empty barriers count two multicast commits).
+template <bool kMixed, bool kCoal, bool kQuad = false>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -431,14 +447,19 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = D / BK;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = kQuad ? (crank & 1u) : crank;   // rank inside the CTA pair
+    const uint32_t psel = kQuad ? (crank >> 1) : 0u;      // which pair of the cluster
+    const uint32_t lrank = crank & ~1u;                   // cluster rank of this pair's leader
     const bool leader = rank == 0;
-    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    constexpr int kCl = kQuad ? 4 : 2;
+    const int pair = blockIdx.x / kCl, n_pairs = gridDim.x / kCl;   // cluster index / count: the tile loop strides by clusters
+    auto pair_block = [&](int tile) { return (tile / n_nblocks) * (kQuad ? 2 : 1) + (int)psel; };   // 256-row block of this pair
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages2; ++s) {
             mbar_init(full_bar(s), 1);    // the leader's producer arrives with the bytes of BOTH CTAs
-            mbar_init(empty_bar(s), 1);   // multicast tcgen05.commit of the leader
+            mbar_init(empty_bar(s), kQuad ? 2 : 1);   // multicast tcgen05.commit of the leader (kQuad: of both pairs' leaders)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
@@ -467,19 +488,27 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             uint32_t it = 0;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
                 const int n0 = (tile % n_nblocks) * BN + (int)rank * (BN / 2);
-                const int m0 = (tile / n_nblocks) * (2 * BM) + (int)rank * BM;
+                const int m0 = pair_block(tile) * (2 * BM) + (int)rank * BM;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % kStages2;
                     const uint32_t ph = (it / kStages2) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = smem_base + s * kStageBytes2;
-                    const uint32_t lbar = mapa_shared(full_bar(s), 0);
+                    const uint32_t lbar = mapa_shared(full_bar(s), lrank);
                     if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes2);
                     const int kx = kMixed ? kb * 2 * BK : kb * BK;   // bf16 operands: 2 BK elements (hi | lo) per k-block
                     tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, m0);
                     tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kx, m0);
-                    tma_load_2d_pair(st + 2 * kABytes, &map_b_hi, lbar, kb * BK, n0);
-                    tma_load_2d_pair(st + 2 * kABytes + kBHalfBytes, &map_b_lo, lbar, kx, n0);
+                    if constexpr (kQuad) {
+                        // rows [64 psel, 64 psel + 64) of this CTA's B half, delivered to this CTA and to its twin in the other pair
+                        const uint16_t mc = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));
+                        const uint32_t qoff = psel * (kBHalfBytes / 2);
+                        tma_load_2d_pair_mc(st + 2 * kABytes + qoff, &map_b_hi, lbar, kb * BK, n0 + (int)psel * (BN / 4), mc);
+                        tma_load_2d_pair_mc(st + 2 * kABytes + kBHalfBytes + qoff, &map_b_lo, lbar, kx, n0 + (int)psel * (BN / 4), mc);
+                    } else {
+                        tma_load_2d_pair(st + 2 * kABytes, &map_b_hi, lbar, kb * BK, n0);
+                        tma_load_2d_pair(st + 2 * kABytes + kBHalfBytes, &map_b_lo, lbar, kx, n0);
+                    }
                 }
             }
         }
@@ -513,9 +542,9 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                             tcgen05_mma_tf32_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
                         }
                     }
-                    tcgen05_commit_pair(empty_bar(s));      // frees the stage in both CTAs
+                    tcgen05_commit_pair(empty_bar(s), kQuad ? (uint16_t)0xF : (uint16_t)3);   // frees the stage in every CTA that fills it
                 }
-                tcgen05_commit_pair(tmem_full_bar(as));     // accumulators of both CTAs complete
+                tcgen05_commit_pair(tmem_full_bar(as), (uint16_t)(3u << lrank));   // accumulators of both CTAs of this pair complete
             }
         }
     } else {
@@ -535,7 +564,7 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                 constexpr int kMode = decltype(mode_c)::value;
                 for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
                     const int n0 = (tile % n_nblocks) * BN;
-                    const int64_t m_base = (int64_t)(tile / n_nblocks) * (2 * BM) + (int64_t)rank * BM + q * 32;   // row of TMEM lane 0
+                    const int64_t m_base = (int64_t)pair_block(tile) * (2 * BM) + (int64_t)rank * BM + q * 32;   // row of TMEM lane 0
                     const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
                     float quad = 0.f, ke = 0.f;   // lane = row (m_base + lane), as in the accumulator layout
                     bool waited = false;
@@ -564,7 +593,7 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                                 tcgen05_fence_before();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    const uint32_t lbar = mapa_shared(tmem_empty_bar(as), 0);
+                                    const uint32_t lbar = mapa_shared(tmem_empty_bar(as), lrank);
                                     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
                                 }
                             }
@@ -633,7 +662,7 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
         } else
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
             const int n0 = (tile % n_nblocks) * BN;
-            const int64_t m = (int64_t)(tile / n_nblocks) * (2 * BM) + (int64_t)rank * BM + row;
+            const int64_t m = (int64_t)pair_block(tile) * (2 * BM) + (int64_t)rank * BM + row;
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
             const bool row_ok = m < M;
             float quad = 0.f, ke = 0.f;
@@ -660,7 +689,7 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        const uint32_t lbar = mapa_shared(tmem_empty_bar(as), 0);
+                        const uint32_t lbar = mapa_shared(tmem_empty_bar(as), lrank);
                         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
                     }
                 }
@@ -914,11 +943,32 @@ int dense_tc_prepare(DenseState *st) {
     if (!rc) rc = tc::encode_2d(enc, &maps->b_hi_half, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN / 2);
     if (!rc) rc = tc::encode_2d(enc, &maps->b_lo_half, st->d_prec_split + (size_t)D * D, (uint64_t)D, (uint64_t)D, tc::BN / 2);
     if (!rc) rc = tc::encode_2d_bf16(enc, &maps->b_x_half, st->d_prec_x, (uint64_t)D, (uint64_t)D, tc::BN / 2);
+    if (!rc) rc = tc::encode_2d(enc, &maps->b_hi_q, st->d_prec_split, (uint64_t)D, (uint64_t)D, tc::BN / 4);
+    if (!rc) rc = tc::encode_2d_bf16(enc, &maps->b_x_q, st->d_prec_x, (uint64_t)D, (uint64_t)D, tc::BN / 4);
     if (rc) { delete maps; return rc; }
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    {   // how many 4-CTA clusters of the quad kernel are resident at once (GPCs whose SM count is not a multiple of 4 strand SMs)
+        cudaLaunchConfig_t qc{};
+        qc.gridDim = dim3((unsigned)(sm_count() / 4 * 4));
+        qc.blockDim = dim3(tc::kThreads);
+        qc.dynamicSmemBytes = tc::kSmemBytes2;
+        cudaLaunchAttribute qa{};
+        qa.id = cudaLaunchAttributeClusterDimension;
+        qa.val.clusterDim.x = 4; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+        qc.attrs = &qa;
+        qc.numAttrs = 1;
+        int n = 0;
+        const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, tc::dense_gemm_tc_pair_kernel<true, true, true>, &qc);
+        if (qe == cudaSuccess) st->tc_quad_clusters = n;
+        else (void)cudaGetLastError();
+        if (getenv("MMC_TC_VERBOSE"))
+            fprintf(stderr, "[minimcmc] dense tcgen05: resident 4-CTA clusters = %d (%s), hardware tf32 truncation self-test pending\n", n,
+                    cudaGetErrorString(qe));
+    }
     st->tc = maps;
     // Mixed split only: kind::tf32 can read the full-precision Delta directly when the tensor core ignores the low 13
     // mantissa bits of its fp32 containers, which saves the separate TF32 copy (4 of the epilogue's 24 bytes per element).
@@ -969,6 +1019,24 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
         if (st->tc_mixed) {
+            // 4-CTA clusters (B halves multicast to two pairs): opt-in with MMC_TC_QUAD=1.  Measured on C4 (profiles/
+            // r3_dense_quad_cluster.log): 33 clusters are resident (132 of 148 SMs: GPCs whose SM count is not a multiple of 4
+            // strand SMs) and 256 tiles of 512 x 256 take 8 waves instead of the 7 of the pair kernel, which cancels the 12 %
+            // a tile gains from the smaller operand feed (60.0 vs 58.3-59.0 ms per 4 transitions).
+            const char *quad_env = getenv("MMC_TC_QUAD");
+            const int n_tiles4 = n_nblocks * (int)((M + 4 * tc::BM - 1) / (4 * tc::BM));
+            const bool quad = quad_env && quad_env[0] == '1' && st->tc_quad_clusters > 0 && M >= 4 * tc::BM;
+            if (quad) {
+                const int clusters = n_tiles4 < st->tc_quad_clusters ? n_tiles4 : st->tc_quad_clusters;
+                cfg.gridDim = dim3((unsigned)(4 * clusters));
+                attr.val.clusterDim.x = 4;
+                MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<true, true, true>,
+                                            st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur], maps->a_x[cur], maps->b_hi_q, maps->b_x_q,
+                                            (const float *)st->d_delta[cur], (const float *)nullptr,
+                                            st->tc_hw_trunc ? (float *)nullptr : n_hi, st->d_delta[cur ^ 1], st->d_delta_x[cur ^ 1], st->d_mom,
+                                            st->d_scal, M, D, eps, mode, n_tiles4, n_nblocks));
+                return MMC_OK;
+            }
             static const bool coal = !(getenv("MMC_TC_EPI") && getenv("MMC_TC_EPI")[0] == '0');   // 0: row-per-lane epilogue (A/B)
             auto kern = coal ? tc::dense_gemm_tc_pair_kernel<true, true> : tc::dense_gemm_tc_pair_kernel<true, false>;
             MMC_CUDA(cudaLaunchKernelEx(&cfg, kern, st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur],

@@ -500,6 +500,12 @@ int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p
         if (G < 1) G = 1;
         const int64_t steps = std::max<int64_t>(1, N - lag0);
         if (G > (int)((steps + LB - 1) / LB)) G = (int)((steps + LB - 1) / LB);   // a segment is at least one block of LB steps
+        // small split-chain blocks (few parameters): prefer more staged chains per round over more time segments per
+        // chain, so that a round moves >= 32 KB with its bulk copies (with K = 1 a 3 KB block per round is latency bound:
+        // the all-lag pass of the C3 sample took 13 ms for 0.03 TMAC)
+        const int64_t ktarget = std::min<int64_t>(16, ((int64_t)32 * 1024 + (int64_t)blk_bytes - 1) / (int64_t)blk_bytes);
+        const int64_t gcap = std::max<int64_t>(1, tmax / (p2 * H * ktarget));
+        if (G > gcap) G = (int)gcap;
         int K = (int)std::min<int64_t>(16, tmax / (p2 * H * G));
         if (K < 1) K = 1;
         const size_t budget = twin ? 112 * 1024 : 200 * 1024;

@@ -28,7 +28,7 @@ def tc_supported(D):
 
 
 @pytest.mark.parametrize("path", [0, 1, 2, 3])
-@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4)])
+@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4), (512, 700, 4)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
     if path >= 1 and not tc_supported(D):
         pytest.skip("dim 128 runs on the FP32 tiles")
@@ -119,3 +119,27 @@ def test_dense_padded_dims_default_path_and_native_run(mm):
     np.testing.assert_allclose(flat.std(axis=0), np.sqrt(np.diag(cov)), rtol=0.1)
     part = mm.HMC(tgt, init[200:], 0.15, 8).set_seed(4).set_chain_offset(200).run(60, 60)
     np.testing.assert_array_equal(part, s[200:])
+
+
+def test_quad_cluster_kernel_matches_pair_kernel(mm, monkeypatch):
+    """MMC_TC_QUAD=1: clusters of four CTAs (two CTA pairs on the same columns, every B half loaded once and multicast to both
+    pairs, stages released by the commits of both leaders) issue the same MMAs on the same operands as the pair kernel:
+    identical trajectories, also with a ragged last 512-row block."""
+    D, chains, L = 512, 1500, 6
+    mean, cov = make_problem(D, seed=11)
+    tgt = mm.DenseGaussian(mean, cov)
+    rng = np.random.default_rng(2)
+    init = (rng.normal(size=(chains, D)) + mean).astype(np.float32)
+    mom = rng.normal(size=(2, chains, D)).astype(np.float32)
+    u = rng.random((2, chains)).astype(np.float32)
+    outs = []
+    for quad in ("0", "1"):
+        monkeypatch.setenv("MMC_TC_QUAD", quad)
+        h = mm.HMC(tgt, init, 0.05, L).set_gemm_path(3)
+        tr = np.zeros((2, chains, 4), dtype=np.float32)
+        outs.append((h.run(2, 0, replay=dict(momenta=mom, u=u), trace=tr), tr))
+    monkeypatch.delenv("MMC_TC_QUAD")
+    same = (outs[0][1][..., 3] == outs[1][1][..., 3]).all(axis=0)   # log-probs are summed with float atomics: exact ties may flip
+    assert same.mean() > 0.999
+    np.testing.assert_array_equal(outs[0][0][same], outs[1][0][same])
+    np.testing.assert_allclose(outs[0][1][..., :2], outs[1][1][..., :2], rtol=2e-6)
