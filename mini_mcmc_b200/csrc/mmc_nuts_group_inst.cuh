@@ -38,6 +38,9 @@ inline int nuts_group_lanes(const mmc_target_desc &t) {
 #ifdef MMC_NUTS_GROUP_TUNE_G4   // tuning builds: eight chains per warp at D = 100 (E = 26)
         if (t.dim > 64 && t.dim <= 104) return 4;
 #endif
+#ifdef MMC_NUTS_GROUP_TUNE_G16   // tuning builds: two chains per warp at D = 100 (E = 8)
+        if (t.dim > 64 && t.dim <= 128) return 16;
+#endif
         if (t.dim <= 104) return 8;
         if (t.dim <= 128) return 16;
         return 0;
