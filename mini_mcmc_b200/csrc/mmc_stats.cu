@@ -535,6 +535,11 @@ int launch_block_pass(const float *sample, int64_t c_local, int64_t n, int64_t p
     int G = (int)(512 / ((int64_t)p * H));     // time segments: fill the CTA when few lag groups are requested
     if (G < 1) G = 1;
     if (G > (int)((N + kLagBlock - 1) / kLagBlock)) G = (int)((N + kLagBlock - 1) / kLagBlock);
+    {   // small blocks: chains per round before time segments per chain (see the packed path above)
+        const int64_t ktarget = std::min<int64_t>(16, ((int64_t)32 * 1024 + (int64_t)blk_bytes - 1) / (int64_t)blk_bytes);
+        const int64_t gcap = std::max<int64_t>(1, 512 / (p * H * ktarget));
+        if (G > gcap) G = (int)gcap;
+    }
     // small p: stage K split chains per round so that the CTA still has ~512 threads of work
     int K = (int)std::min<int64_t>(16, 512 / ((int64_t)p * H * G));
     if (K < 1) K = 1;
