@@ -136,6 +136,11 @@ def c3(args):
     ms = timed(lambda: h.run_device(nc, nd, out=out), warm=1, reps=3)
     tr = chains * (nc + nd) * WORLD
     rhat, ess = mm.split_rhat_mean_ess(out, group=None if WORLD > 1 else False)
+    # the reference-arithmetic kernel (set_exact: no FMA contraction, the reference's operation order; bit-identical to the
+    # oracle under replay, tests/test_gpu_full_width.py) on the same workload
+    hx = mm.HMC(mm.RosenbrockND(), init, 0.01, L).set_seed(1).set_chain_offset(RANK * chains).set_exact(True)
+    ms_exact = timed(lambda: hx.run_device(nc, nd, out=out), warm=1, reps=3)
+    del hx
     cpu_rate = cores = cpu_ess = None
     if RANK == 0 and not args.no_cpu:
         cpu_out = {}
@@ -153,6 +158,10 @@ def c3(args):
          tflops_per_gpu=tf,
          roofline=dict(bound="fp32", achieved=tf, peak=pk["fp32_tflops"], unit="TFLOP/s", frac=tf / pk["fp32_tflops"],
                        kernel="hmc_run_pair_kernel", algorithmic_flop_per_transition=2442),
+         exact_arithmetic=dict(kernel="hmc_run_kernel<Exact>", ms=ms_exact, transitions_per_s=tr / ms_exact * 1e3,
+                               tflops_per_gpu=tr / WORLD * 2442 / ms_exact / 1e9,
+                               frac=tr / WORLD * 2442 / ms_exact / 1e9 / pk["fp32_tflops"],
+                               note="reference operation order, no FMA contraction: reproduces the oracle bit for bit under replay"),
          ess_min=float(ess.min()), ess_per_s=float(ess.min()) / ms * 1e3, cpu_transitions_per_s=cpu_rate, cpu_cores=cores,
          cpu_ess_per_s=cpu_ess, cpu_sample="8192 chains, same run(400,50); ESS/s = min-ESS of those chains / their wall time")
     del out
@@ -247,6 +256,20 @@ def c5(args):
         if WORLD > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         stats_ms = dt.item() if stats_ms is None else min(stats_ms, dt.item())
+    # the reference-arithmetic group kernel (set_exact: unpacked, no FMA contraction, E = 13 lanes) on the same run
+    sx = mm.NUTS(mm.RosenbrockND(), init, 0.95, scalar_dtype="f32", max_depth=10).set_seed(7).set_chain_offset(RANK * chains).set_exact(True)
+    barrier()
+    a.record()
+    sx.run_device(nc, nd, progress=True, out=out)
+    b.record()
+    barrier()
+    tx = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+    gx = torch.tensor([sx.counters()["n_grad"]], dtype=torch.float64, device="cuda")
+    if WORLD > 1:
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(gx)
+    ms_exact = tx.item()
+    del sx
     cpu_rate = cores = cpu_ess = None
     if RANK == 0 and not args.no_cpu:
         cpu_out = {}
@@ -267,6 +290,9 @@ def c5(args):
          grad_evals_per_s=g[0].item() / ms * 1e3, transitions_per_s=g[1].item() / ms * 1e3, tflops_per_gpu=tf,
          roofline=dict(bound="fp32", achieved=tf, peak=pk["fp32_tflops"], unit="TFLOP/s", frac=tf / pk["fp32_tflops"],
                        kernel="nuts_group_kernel", algorithmic_flop_per_grad_eval=2285),
+         exact_arithmetic=dict(kernel="nuts_group_kernel<Exact>", sample_ms=ms_exact, grad_evals_per_s=gx.item() / ms_exact * 1e3,
+                               frac=gx.item() / WORLD * 2285 / ms_exact / 1e9 / pk["fp32_tflops"],
+                               note="reference operation order, no FMA contraction (states 1e-6 against the oracle under replay)"),
          stats=dict(ms=stats_ms, sample_GB=chains * nc * D * 4 / 1e9, collective="ncclAllReduce (libminimcmc communicator)" if WORLD > 1 else None),
          ess_min=float(ess.min()), ess_per_s_sampling=float(ess.min()) / ms * 1e3,
          ess_per_s_incl_stats=float(ess.min()) / (ms + stats_ms) * 1e3,
