@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -850,10 +851,11 @@ int dense_tc_prepare(DenseState *st);
 
 // One-off self-test per process: the same short mixed-split run with the pre-truncated TF32 copy and with the
 // full-precision Delta as the kind::tf32 operand; 1 = bit-identical (the hardware truncates), 0 = not, cached.
-static int g_hw_trunc = -1;   // -1 unknown, -2 probing
+static std::atomic<int> g_hw_trunc{-1};   // -1 unknown, -2 probing
 static bool tc_hw_truncates() {
-    if (g_hw_trunc >= 0) return g_hw_trunc == 1;
-    if (g_hw_trunc == -2) return false;   // the probe's own handles
+    const int seen = g_hw_trunc.load();
+    if (seen >= 0) return seen == 1;
+    if (seen == -2) return false;   // the probe's own handles (or a second thread while the probe runs: it keeps the TF32 copy)
     g_hw_trunc = -2;
     int verdict = 0;
     const int D = 256;
@@ -902,7 +904,7 @@ static bool tc_hw_truncates() {
     return verdict == 1;
 }
 // 1 / 0: what the self-test found on this device (diagnostics: mmc_hmc_gemm_info)
-int dense_tc_hw_trunc_state() { return g_hw_trunc; }
+int dense_tc_hw_trunc_state() { return g_hw_trunc.load(); }
 
 int dense_tc_prepare(DenseState *st) {
     if (st->tc) return MMC_OK;
