@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_dense.py -q -m gpu -k "replay and 512 and 3" -x > gpurun_out/r3n_racecheck_full.log 2>&1
-grep -o "mmc_dense_tc.cu:[0-9]*" gpurun_out/r3n_racecheck_full.log | sort | uniq -c | sort -rn | head -20
-grep -c "hazard" gpurun_out/r3n_racecheck_full.log
-grep -m3 -A12 "hazard detected\|Race reported" gpurun_out/r3n_racecheck_full.log | cut -c1-400 | head -60
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_stats.py -q -m gpu -x 2>&1 | tail -6 | tee gpurun_out/r3n_sanitizer_stats.log
+echo "exit ${PIPESTATUS[0]}" | tee -a gpurun_out/r3n_sanitizer_stats.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python - <<'PY' 2>&1 | tail -4 | tee -a gpurun_out/r3n_sanitizer_stats.log
+import torch, mini_mcmc_b200 as mm
+for (c, n, p) in ((4096, 400, 3), (4096, 400, 4), (2048, 200, 2), (1024, 400, 1), (512, 64, 6), (300, 100, 10)):
+    x = torch.randn((c, n, p), device="cuda").cumsum(dim=1) * 0.05 + torch.randn((c, n, p), device="cuda")   # slow mixing: all lag windows
+    r, e = mm.split_rhat_mean_ess(x)
+    print(c, n, p, float(r.min()), float(e.min()))
+PY

@@ -35,6 +35,8 @@ def _ar1(rng, c, n, p, phi, offset=0.0):
     (37, 64, 4, 0.5, 1.0),       # even p: packed two-parameters-per-thread kernel, ragged last round
     (9, 600, 6, 0.97, -3.0),     # packed kernel, many lag blocks
     (5, 100, 256, 0.3, 0.0),     # packed kernel, wide rows (128 parameter pairs)
+    (701, 400, 3, 0.97, 2.0),    # C3 row shape, slow mixing: all lag windows with many small blocks per round (scalar kernels)
+    (701, 400, 4, 0.97, 2.0),    # the same on the packed kernels, ragged last round
 ])
 def test_split_rhat_ess_matches_oracle(mm, c, n, p, phi, offset):
     rng = np.random.default_rng(c * 1000 + n)
