@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(256) dense_gemm_simt_kernel(const float *__res
 }
 
 int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode, cudaStream_t stream);  // mmc_dense_tc.cu
+int dense_gemm_tc_chain(DenseState *st, int64_t M, int D, float eps, int L, cudaStream_t stream);
 int dense_tc_prepare(DenseState *st);
 int dense_tc_split_delta(DenseState *st, cudaStream_t stream);
 void dense_tc_destroy(DenseState *st);
@@ -263,6 +264,7 @@ void dense_destroy(DenseState *st) {
     cudaFree(st->d_prec_x);
     cudaFree(st->d_delta_x[0]);
     cudaFree(st->d_delta_x[1]);
+    cudaFree(st->d_ready);
     delete st;
 }
 
@@ -290,7 +292,13 @@ int dense_run(DenseState *st, const DenseRunArgs &a, cudaStream_t stream) {
             if (rc) return rc;
         }
         int cur = 0;
-        for (int l = 0; l <= a.n_leapfrog; ++l) {
+        bool chained = false;
+        if (a.gemm_path == 3) {   // all L + 1 GEMMs of the transition in one launch where the chain kernel applies
+            const int rc = dense_gemm_tc_chain(st, M, Dp, a.eps, a.n_leapfrog, stream);
+            if (rc == MMC_OK) { chained = true; cur = a.n_leapfrog & 1; }
+            else if (rc != MMC_ERR_UNSUPPORTED) return rc;
+        }
+        for (int l = 0; l <= a.n_leapfrog && !chained; ++l) {
             const int mode = l == 0 ? kModeFirst : (l == a.n_leapfrog ? kModeLast : kModeMid);
             if (a.gemm_path >= 1) {
                 int rc = dense_gemm_tc(st, cur, M, Dp, a.eps, mode, stream);

@@ -32,6 +32,10 @@ struct DenseState {
     bool tc_mixed = false;
     bool tc_hw_trunc = false;                       // kind::tf32 reads the full-precision Delta (self-tested, mmc_dense_tc.cu)
     int tc_quad_clusters = 0;                       // resident 4-CTA clusters of the quad kernel (0: not available)
+    int tc_chain_pairs = 0;                         // resident CTA pairs of the leapfrog-chain kernel (its grid must be co-resident)
+    bool tc_chain_coop = true;                      // launch it cooperatively (co-residency guaranteed by the driver)
+    int *d_ready = nullptr;                         // chain kernel: [L + 2][row blocks] completion counters
+    size_t ready_bytes = 0;
 };
 
 enum { kModeFirst = 0, kModeMid = 1, kModeLast = 2 };

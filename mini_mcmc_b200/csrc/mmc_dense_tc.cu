@@ -420,6 +420,26 @@ __device__ __forceinline__ void stg256u(uint32_t *p, const uint32_t (&v)[8]) {
 // kMixed: map_a_lo / map_b_lo are the bf16 cross-term operands ([rows, 2 D], 64-element boxes), a_hi = the full-precision
 // Delta (read by the epilogue), a_lo unused, n_hi = next TF32 hi (nullptr: not stored, MMC_TC_HW_TRUNC), n_lo = next
 // full-precision Delta, n_x = next bf16 cross-term operand
+// kChain: ONE launch runs all L + 1 GEMMs of a transition.  A tile of leapfrog l only depends on the column tiles of its own
+// 256-row block at leapfrog l - 1 (they wrote the block's next Delta), so instead of a launch boundary the TMA producers wait
+// on a per-(leapfrog, row block) counter that the epilogue warps bump after their stores.  The TMA / MMA / epilogue pipeline
+// (stage ring, double-buffered TMEM) then runs across leapfrogs without draining: no launch gap, no prologue and no
+// un-overlapped last epilogue per GEMM (about 11 us of the 42 us a 4,096-chain shard spends per leapfrog).
+struct ChainCtl {
+    const float *dfull[2];   // full-precision Delta ping-pong (leapfrog l reads [l & 1], writes [(l & 1) ^ 1])
+    float *dfull_w[2];
+    float *hi[2];            // TF32 copies of Delta (nullptr: the tensor core truncates, see tc_hw_truncates)
+    uint32_t *x[2];          // bf16 cross-term operands
+    int *ready;              // [n_leap + 2][n_mblocks] epilogue-warp arrivals per 256-row block
+    int n_leap;              // L: leapfrog l = 0 is the first gradient, l = L the last half kick
+    int n_mblocks;
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // kCoal (with kMixed): the epilogue transposes the accumulator chunk through shared memory so that every global access of
 // a warp covers whole 128-byte lines of ONE row (lane = column) instead of one 32-byte sector of 32 different rows
 // (lane = row, the TMEM layout): ncu showed the L1TEX -> XBAR request path as the busiest unit (67 %) with the row-per-lane
@@ -428,13 +448,17 @@ __device__ __forceinline__ void stg256u(uint32_t *p, const uint32_t (&v)[8]) {
 // B half a CTA needs is the same in both pairs, so each CTA loads 64 of its 128 rows and multicasts them to its twin in the
 // other pair: 48 instead of 64 KB per CTA and k-block come from L2, the feed that bounds the kernel.  A
 // stage is reused only after BOTH pairs have consumed it (empty barriers count two multicast commits).
-template <bool kMixed, bool kCoal, bool kQuad = false>
+template <bool kMixed, bool kCoal, bool kQuad = false, bool kChain = false>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                           const float *__restrict__ a_hi, const float *__restrict__ a_lo, float *__restrict__ n_hi,
                           float *__restrict__ n_lo, uint32_t *__restrict__ n_x, float *__restrict__ mom, float *__restrict__ scal,
-                          int64_t M, int D, float eps, int mode, int n_tiles, int n_nblocks) {
+                          int64_t M, int D, float eps, int mode, int n_tiles, int n_nblocks,
+                          const __grid_constant__ CUtensorMap map_a_hi1, const __grid_constant__ CUtensorMap map_a_lo1,
+                          const ChainCtl ctl) {
+    static_assert(!kChain || (kMixed && kCoal && !kQuad), "the leapfrog chain exists for the mixed-split CTA-pair kernel");
+    const int n_l = kChain ? ctl.n_leap + 1 : 1;   // GEMMs of this launch
     static_assert(!kMixed || BK == 32, "the mixed split is written for 128-byte swizzle rows");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -487,9 +511,19 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
         // ===== TMA producer (one per CTA; both signal the leader's full barrier) =====
         if (lane == 0) {
             uint32_t it = 0;
+            for (int l = 0; l < n_l; ++l) {
+            const CUtensorMap *ma_hi = (kChain && (l & 1)) ? &map_a_hi1 : &map_a_hi;
+            const CUtensorMap *ma_lo = (kChain && (l & 1)) ? &map_a_lo1 : &map_a_lo;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
                 const int n0 = (tile % n_nblocks) * BN + (int)rank * (BN / 2);
                 const int m0 = pair_block(tile) * (2 * BM) + (int)rank * BM;
+                if (kChain && l > 0) {
+                    // every epilogue warp of both CTAs of every column tile of this row block has stored leapfrog l - 1
+                    const int *flag = ctl.ready + (int64_t)l * ctl.n_mblocks + pair_block(tile);
+                    const int target = n_nblocks * 2 * kEpiWarps;
+                    while (ld_acquire_gpu(flag) < target) __nanosleep(40);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores observed above -> the TMA (async proxy) reads below
+                }
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % kStages2;
                     const uint32_t ph = (it / kStages2) & 1u;
@@ -498,8 +532,8 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     const uint32_t lbar = mapa_shared(full_bar(s), lrank);
                     if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes2);
                     const int kx = kMixed ? kb * 2 * BK : kb * BK;   // bf16 operands: 2 BK elements (hi | lo) per k-block
-                    tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, m0);
-                    tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kx, m0);
+                    tma_load_2d_pair(st, ma_hi, lbar, kb * BK, m0);
+                    tma_load_2d_pair(st + kABytes, ma_lo, lbar, kx, m0);
                     if constexpr (kQuad) {
                         // rows [64 psel, 64 psel + 64) of this CTA's B half, delivered to this CTA and to its twin in the other pair
                         const uint16_t mc = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));
@@ -512,12 +546,14 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
         if (leader && lane == 0) {
             constexpr uint32_t idesc = make_idesc_pair();
             uint32_t it = 0, lt = 0;
+            for (int l = 0; l < n_l; ++l)
             for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
                 const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(as), aph ^ 1u);
@@ -561,8 +597,16 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             // float4 (conflict-free per quarter warp), lane = (row % 4 group, column group) reads float4 (conflict-free)
             float *zt = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + ew * kEpiTileFloats;
             const int cg = lane & 7, rg = lane >> 3;   // this lane's 4 columns (4 cg ..) and its row inside a group of 4 rows
-            auto run_tiles = [&](auto mode_c) {
+            const float *const a_hi_arg = a_hi;
+            float *const n_lo_arg = n_lo, *const n_hi_arg = n_hi;
+            uint32_t *const n_x_arg = n_x;
+            auto run_tiles = [&](auto mode_c, int l) {
                 constexpr int kMode = decltype(mode_c)::value;
+                // this GEMM's operands: the launch arguments, or leapfrog l of the chain
+                const float *const a_hi = kChain ? ctl.dfull[l & 1] : a_hi_arg;
+                float *const n_lo = kChain ? ctl.dfull_w[(l & 1) ^ 1] : n_lo_arg;
+                float *const n_hi = kChain ? ctl.hi[(l & 1) ^ 1] : n_hi_arg;
+                uint32_t *const n_x = kChain ? ctl.x[(l & 1) ^ 1] : n_x_arg;
                 for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
                     const int n0 = (tile % n_nblocks) * BN;
                     const int64_t m_base = (int64_t)pair_block(tile) * (2 * BM) + (int64_t)rank * BM + q * 32;   // row of TMEM lane 0
@@ -655,11 +699,20 @@ dense_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                         atomicAdd(scal + (kMode == kModeFirst ? 1 : 3) * M + m, quad);
                         if (kMode == kModeLast) atomicAdd(scal + 2 * M + m, ke);
                     }
+                    if constexpr (kChain) {
+                        // release this warp's part of the row block to leapfrog l + 1 (every lane fences its own stores)
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(ctl.ready + (int64_t)(l + 1) * ctl.n_mblocks + pair_block(tile), 1);
+                    }
                 }
             };
-            if (mode == kModeMid) run_tiles(std::integral_constant<int, kModeMid>{});
-            else if (mode == kModeFirst) run_tiles(std::integral_constant<int, kModeFirst>{});
-            else run_tiles(std::integral_constant<int, kModeLast>{});
+            for (int l = 0; l < n_l; ++l) {
+                const int mode_l = kChain ? (l == 0 ? (int)kModeFirst : (l == ctl.n_leap ? (int)kModeLast : (int)kModeMid)) : mode;
+                if (mode_l == kModeMid) run_tiles(std::integral_constant<int, kModeMid>{}, l);
+                else if (mode_l == kModeFirst) run_tiles(std::integral_constant<int, kModeFirst>{}, l);
+                else run_tiles(std::integral_constant<int, kModeLast>{}, l);
+            }
         } else
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
             const int n0 = (tile % n_nblocks) * BN;
@@ -953,6 +1006,21 @@ int dense_tc_prepare(DenseState *st) {
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    MMC_CUDA(cudaFuncSetAttribute(tc::dense_gemm_tc_pair_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    {   // the chain kernel's producers wait on other CTAs: all of its clusters must be resident at once
+        cudaLaunchConfig_t qc{};
+        qc.gridDim = dim3((unsigned)(sm_count() / 2 * 2));
+        qc.blockDim = dim3(tc::kThreads);
+        qc.dynamicSmemBytes = tc::kSmemBytes2;
+        cudaLaunchAttribute qa{};
+        qa.id = cudaLaunchAttributeClusterDimension;
+        qa.val.clusterDim.x = 2; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+        qc.attrs = &qa;
+        qc.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tc::dense_gemm_tc_pair_kernel<true, true, false, true>, &qc) == cudaSuccess) st->tc_chain_pairs = n;
+        else (void)cudaGetLastError();
+    }
     {   // how many 4-CTA clusters of the quad kernel are resident at once (GPCs whose SM count is not a multiple of 4 strand SMs)
         cudaLaunchConfig_t qc{};
         qc.gridDim = dim3((unsigned)(sm_count() / 4 * 4));
@@ -1036,7 +1104,7 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
                                             st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur], maps->a_x[cur], maps->b_hi_q, maps->b_x_q,
                                             (const float *)st->d_delta[cur], (const float *)nullptr,
                                             st->tc_hw_trunc ? (float *)nullptr : n_hi, st->d_delta[cur ^ 1], st->d_delta_x[cur ^ 1], st->d_mom,
-                                            st->d_scal, M, D, eps, mode, n_tiles4, n_nblocks));
+                                            st->d_scal, M, D, eps, mode, n_tiles4, n_nblocks, maps->a_full[cur], maps->a_x[cur], tc::ChainCtl{}));
                 return MMC_OK;
             }
             static const bool coal = !(getenv("MMC_TC_EPI") && getenv("MMC_TC_EPI")[0] == '0');   // 0: row-per-lane epilogue (A/B)
@@ -1044,12 +1112,13 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
             MMC_CUDA(cudaLaunchKernelEx(&cfg, kern, st->tc_hw_trunc ? maps->a_full[cur] : maps->a_hi[cur],
                                         maps->a_x[cur], maps->b_hi_half, maps->b_x_half, (const float *)st->d_delta[cur],
                                         (const float *)nullptr, st->tc_hw_trunc ? (float *)nullptr : n_hi, st->d_delta[cur ^ 1],
-                                        st->d_delta_x[cur ^ 1], st->d_mom, st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
+                                        st->d_delta_x[cur ^ 1], st->d_mom, st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks,
+                                        maps->a_full[cur], maps->a_x[cur], tc::ChainCtl{}));
             return MMC_OK;
         }
         MMC_CUDA(cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<false, false>, maps->a_hi[cur], maps->a_lo[cur], maps->b_hi_half,
                                     maps->b_lo_half, (const float *)a_hi, (const float *)a_lo, n_hi, n_lo, (uint32_t *)nullptr, st->d_mom,
-                                    st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks));
+                                    st->d_scal, M, D, eps, mode, n_tiles2, n_nblocks, maps->a_hi[cur], maps->a_lo[cur], tc::ChainCtl{}));
         return MMC_OK;
     }
     const int n_tiles = n_nblocks * (int)((M + tc::BM - 1) / tc::BM);
@@ -1058,6 +1127,73 @@ int dense_gemm_tc(DenseState *st, int cur, int64_t M, int D, float eps, int mode
                                                                              maps->b_lo, a_hi, a_lo, n_hi, n_lo, st->d_mom,
                                                                              st->d_scal, M, D, eps, mode, n_tiles, n_nblocks);
     MMC_CUDA(cudaGetLastError());
+    return MMC_OK;
+}
+
+// All L + 1 GEMMs of one transition in ONE launch of the mixed-split CTA-pair kernel (kChain); Delta ends in d_delta[L & 1].
+// Returns MMC_ERR_UNSUPPORTED when the path does not apply (the caller then launches the GEMMs one by one).
+int dense_gemm_tc_chain(DenseState *st, int64_t M, int D, float eps, int L, cudaStream_t stream) {
+    const char *env = getenv("MMC_TC_CHAIN");
+    if (!st->tc || !st->tc_mixed || !st->tc_pair || st->tc_chain_pairs <= 0 || (env && env[0] == '0')) return MMC_ERR_UNSUPPORTED;
+    const char *quad_env = getenv("MMC_TC_QUAD");
+    if (quad_env && quad_env[0] == '1') return MMC_ERR_UNSUPPORTED;
+    tc::Maps *maps = static_cast<tc::Maps *>(st->tc);
+    const int n_nblocks = D / tc::BN;
+    const int n_mblocks = (int)((M + 2 * tc::BM - 1) / (2 * tc::BM));
+    const int n_tiles2 = n_nblocks * n_mblocks;
+    const int pairs = n_tiles2 < st->tc_chain_pairs ? n_tiles2 : st->tc_chain_pairs;
+    const size_t need = (size_t)(L + 2) * n_mblocks * sizeof(int);
+    if (need > st->ready_bytes) {
+        cudaFree(st->d_ready);
+        st->d_ready = nullptr;
+        st->ready_bytes = 0;
+        MMC_CUDA(cudaMalloc((void **)&st->d_ready, need));
+        st->ready_bytes = need;
+    }
+    MMC_CUDA(cudaMemsetAsync(st->d_ready, 0, need, stream));
+    tc::ChainCtl ctl{};
+    for (int b = 0; b < 2; ++b) {
+        ctl.dfull[b] = st->d_delta[b];
+        ctl.dfull_w[b] = st->d_delta[b];
+        ctl.hi[b] = st->tc_hw_trunc ? nullptr : st->d_delta_split[b];
+        ctl.x[b] = st->d_delta_x[b];
+    }
+    ctl.ready = st->d_ready;
+    ctl.n_leap = L;
+    ctl.n_mblocks = n_mblocks;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::kSmemBytes2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    // producers of one CTA wait for epilogues of others: the whole grid has to be resident at once, which a cooperative
+    // launch guarantees (the kernel never calls grid.sync(); a device that cannot co-schedule it refuses the launch and the
+    // caller falls back to one launch per GEMM)
+    cudaLaunchAttribute attrs[2];
+    attrs[0] = attr;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = st->tc_chain_coop ? 2 : 1;
+    const bool hw = st->tc_hw_trunc;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc::dense_gemm_tc_pair_kernel<true, true, false, true>, hw ? maps->a_full[0] : maps->a_hi[0],
+                                       maps->a_x[0], maps->b_hi_half, maps->b_x_half, (const float *)nullptr, (const float *)nullptr,
+                                       (float *)nullptr, (float *)nullptr, (uint32_t *)nullptr, st->d_mom, st->d_scal, M, D, eps,
+                                       (int)kModeMid, n_tiles2, n_nblocks, hw ? maps->a_full[1] : maps->a_hi[1], maps->a_x[1], ctl);
+    if (e != cudaSuccess && st->tc_chain_coop) {
+        // cooperative + cluster launches are refused on this driver / device: remember it and use plain launches of the GEMMs
+        (void)cudaGetLastError();
+        st->tc_chain_coop = false;
+        st->tc_chain_pairs = 0;
+        if (getenv("MMC_TC_VERBOSE")) fprintf(stderr, "[minimcmc] dense tcgen05: cooperative chain launch refused (%s)\n", cudaGetErrorString(e));
+        return MMC_ERR_UNSUPPORTED;
+    }
+    MMC_CUDA(e);
     return MMC_OK;
 }
 
