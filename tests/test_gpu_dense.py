@@ -28,7 +28,7 @@ def tc_supported(D):
 
 
 @pytest.mark.parametrize("path", [0, 1, 2, 3])
-@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4), (512, 700, 4)])
+@pytest.mark.parametrize("D,chains,L", [(128, 200, 4), (256, 384, 7), (1024, 256, 3), (384, 300, 5), (100, 130, 4), (512, 700, 4), (256, 300, 1), (512, 520, 2)])
 def test_dense_hmc_replay_matches_oracle(mm, path, D, chains, L):
     if path >= 1 and not tc_supported(D):
         pytest.skip("dim 128 runs on the FP32 tiles")
