@@ -47,7 +47,8 @@ def _worker(rank, world, port, x, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_stats_and_sharding_invariance(cuda_device):
+@pytest.mark.parametrize("phi", [0.9, 0.995])   # 0.995: the first lag window predicts slow decay and the ranks skip the 64-lag round together
+def test_two_gpu_sharded_stats_and_sharding_invariance(cuda_device, phi):
     import torch
     import torch.multiprocessing as mp
 
@@ -57,7 +58,7 @@ def test_two_gpu_sharded_stats_and_sharding_invariance(cuda_device):
     c, n, p = 12, 400, 100
     x = rng.normal(size=(c, n, p)).astype(np.float32)
     for t in range(1, n):
-        x[:, t] = 0.9 * x[:, t - 1] + 0.4 * x[:, t]
+        x[:, t] = phi * x[:, t - 1] + np.float32(np.sqrt(1.0 - phi * phi)) * x[:, t]
     x[2] += 0.5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
