@@ -143,3 +143,27 @@ def test_quad_cluster_kernel_matches_pair_kernel(mm, monkeypatch):
     assert same.mean() > 0.999
     np.testing.assert_array_equal(outs[0][0][same], outs[1][0][same])
     np.testing.assert_allclose(outs[0][1][..., :2], outs[1][1][..., :2], rtol=2e-6)
+
+
+def test_chain_launch_matches_per_gemm_launches(mm, monkeypatch):
+    """The default dense path runs the L + 1 GEMMs of a transition in ONE cooperative launch (row-block completion counters
+    instead of launch boundaries); MMC_TC_CHAIN=0 launches them one by one.  Same kernel code, same operands: identical
+    trajectories, for several row blocks per CTA pair, a ragged last block and both parities of L."""
+    for D, chains, L in ((512, 1111, 5), (256, 40000, 4)):
+        mean, cov = make_problem(D, seed=13)
+        tgt = mm.DenseGaussian(mean, cov)
+        rng = np.random.default_rng(3)
+        init = (rng.standard_normal(size=(chains, D), dtype=np.float32) + mean.astype(np.float32))
+        mom = rng.standard_normal(size=(2, chains, D), dtype=np.float32)
+        u = rng.random((2, chains), dtype=np.float32)
+        outs = []
+        for chain in ("1", "0"):
+            monkeypatch.setenv("MMC_TC_CHAIN", chain)
+            h = mm.HMC(tgt, init, 0.05, L)
+            tr = np.zeros((2, chains, 4), dtype=np.float32)
+            outs.append((h.run(2, 0, replay=dict(momenta=mom, u=u), trace=tr), tr))
+        monkeypatch.delenv("MMC_TC_CHAIN")
+        same = (outs[0][1][..., 3] == outs[1][1][..., 3]).all(axis=0)   # log-probs are summed with float atomics: exact ties may flip
+        assert same.mean() > 0.999
+        np.testing.assert_array_equal(outs[0][0][same], outs[1][0][same])
+        np.testing.assert_allclose(outs[0][1][..., :2], outs[1][1][..., :2], rtol=2e-6)
